@@ -1,0 +1,227 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the EDT -> local_thickness / porosimetry path.
+
+Nothing under `porespy_b200/` imports this module.  Allowed callers: `tests/`,
+`__graft_entry__.smoke()`, and `bench.py`'s `cpu_baseline` / `--impl reference` legs.
+
+It restates, on the CPU and in *float semantics* (float32 distance map compared against
+the radius objects exactly the way numpy does it in the reference), the algorithm of
+
+* `porosimetry`              /root/reference/src/porespy/filters/_funcs.py:1124-1148, 1177-1212
+* `local_thickness`          /root/reference/src/porespy/filters/_funcs.py:1027-1029
+* `trim_disconnected_blobs`  /root/reference/src/porespy/filters/_funcs.py:1252-1270
+* `get_border(mode='faces')` /root/reference/src/porespy/generators/_borders.py:93-100
+* `ps_round/ps_ball/ps_disk` /root/reference/src/porespy/tools/_funcs.py:1149-1156
+* `fftmorphology` dilation   /root/reference/src/porespy/filters/_fftmorphology.py:75-93
+* `blobs` / `norm_to_uniform`/root/reference/src/porespy/generators/_imgen.py:1023-1051,
+                             /root/reference/src/porespy/tools/_funcs.py:963-969
+* `edt.edt` (third-party, unpinned, not vendored) -> `oracle/edt_oracle.c`.
+
+Parity pinning: `tests/test_oracle.py` checks these restatements against the golden
+vectors in `tests/golden/`, which `tests/golden/make_golden.py` produced by running the
+reference's own source (via `oracle/ref_shim.py`), and against the golden numbers the
+reference's tests assert (test/unit/test_filters.py:36-42, 53-56, 266-279;
+test/unit/test_tools.py:309-316).
+
+The product (CUDA) path works on integer squared distances and integer thresholds; this
+oracle deliberately does NOT -- it compares float32 distances with the radii like the
+reference, so the product's threshold logic is checked rather than mirrored.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+INF_U32 = 0xFFFFFFFF
+
+
+def build(force=False):
+    """Compile oracle/edt_oracle.c -> oracle/liboracle.so (gcc + OpenMP)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "edt_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        lib = ctypes.CDLL(build())
+        lib.oracle_edt_sq.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+        lib.oracle_edt_sq.restype = ctypes.c_int
+        lib.oracle_sqrt_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.c_int]
+        lib.oracle_sqrt_f32.restype = ctypes.c_int
+        lib.oracle_num_threads.restype = ctypes.c_int
+        _LIB = lib
+    return _LIB
+
+
+def num_threads():
+    return int(_lib().oracle_num_threads())
+
+
+def _as3d(shape):
+    if len(shape) == 1:
+        return (1, 1, shape[0])
+    if len(shape) == 2:
+        return (1, shape[0], shape[1])
+    if len(shape) == 3:
+        return tuple(shape)
+    raise ValueError("oracle supports 1-D, 2-D and 3-D arrays")
+
+
+def edt_sq(data, nthreads=0):
+    """Exact integer squared EDT (uint32; INF_U32 where no background exists)."""
+    a = np.ascontiguousarray(np.asarray(data) != 0, dtype=np.uint8)
+    out = np.empty(a.shape, dtype=np.uint32)
+    if a.size == 0:
+        return out
+    nz, ny, nx = _as3d(a.shape)
+    rc = _lib().oracle_edt_sq(a.ctypes.data, out.ctypes.data, nz, ny, nx, int(nthreads))
+    assert rc == 0
+    return out
+
+
+def edt(data, anisotropy=None, black_border=False, order="K", parallel=1,
+        voxel_graph=None):
+    """`edt.edt` as PoreSpy calls it: float32(sqrt(d2)); `parallel<=0` = all cores."""
+    if anisotropy is not None or black_border or voxel_graph is not None:
+        raise NotImplementedError("oracle restates only the options PoreSpy uses")
+    d2 = edt_sq(data, nthreads=0 if parallel <= 0 else parallel)
+    out = np.empty(d2.shape, dtype=np.float32)
+    if d2.size:
+        _lib().oracle_sqrt_f32(d2.ctypes.data, out.ctypes.data, d2.size, 0)
+    return out
+
+
+# ----------------------------------------------------------------------------- inputs
+def norm_to_uniform(im, scale=None):
+    """T:963-969 -- normal -> uniform greyscale via the error function."""
+    from scipy.special import erfc
+    lo, hi = (im.min(), im.max()) if scale is None else scale
+    im = (im - np.mean(im)) / np.std(im)
+    im = 1 / 2 * erfc(-im / np.sqrt(2))
+    im = (im - im.min()) / (im.max() - im.min())
+    return im * (hi - lo) + lo
+
+
+def blobs(shape, porosity=0.5, blobiness=1, seed=None):
+    """_imgen.py:1023-1051 -- noise, gaussian blur, uniformise, threshold (divs=1)."""
+    import scipy.ndimage as spim
+    if seed is not None:
+        np.random.seed(seed)
+    if isinstance(shape, int):
+        shape = [shape] * 3
+    if len(shape) == 1:
+        shape = [shape[0]] * 3
+    shape = np.array(shape)
+    if isinstance(blobiness, int):
+        blobiness = [blobiness] * len(shape)
+    sigma = np.mean(shape) / (40 * np.array(blobiness))
+    field = spim.gaussian_filter(np.random.random(shape), sigma=sigma)
+    field = norm_to_uniform(field, scale=[0, 1])
+    return field < porosity if porosity else field
+
+
+def border_faces(shape, thickness=1):
+    """_borders.py:93-100 -- True on every face voxel (2-D / 3-D; other ndim: all True)."""
+    t = thickness
+    out = np.ones(shape, dtype=bool)
+    if len(shape) == 2:
+        out[t:-t, t:-t] = False
+    elif len(shape) == 3:
+        out[t:-t, t:-t, t:-t] = False
+    return out
+
+
+def _cross(ndim):
+    import scipy.ndimage as spim
+    return spim.generate_binary_structure(ndim, 1)   # == skimage ball(1) / disk(1)
+
+
+def _full(ndim):
+    return np.ones((3,) * ndim, dtype=bool)          # == skimage cube(3) / square(3)
+
+
+def ps_round(r, ndim, smooth=True):
+    """T:1149-1156 -- EDT-defined ball/disk; strict `<` when smooth."""
+    half = int(np.ceil(r))
+    probe = np.ones([2 * half + 1] * ndim, dtype=bool)
+    probe[(half,) * ndim] = False
+    d = edt(probe)
+    return d < r if smooth else d <= r
+
+
+# ------------------------------------------------------------------------ the hot path
+def trim_disconnected_blobs(im, inlets, strel=None):
+    """F:1252-1270 -- keep foreground whose `strel`-component of (inlets | im) holds an inlet."""
+    import scipy.ndimage as spim
+    if isinstance(inlets, tuple):
+        where = np.copy(inlets)
+        inlets = np.zeros_like(im, dtype=bool)
+        inlets[where] = True
+    elif (inlets.shape == im.shape) and (inlets.max() == 1):
+        inlets = inlets.astype(bool)
+    else:
+        raise Exception("inlets not valid, refer to docstring for info")
+    if strel is None:
+        strel = _full(im.ndim)
+    lab = spim.label(inlets + (im > 0), structure=strel)[0]
+    wanted = np.unique(lab[inlets])
+    wanted = wanted[wanted > 0]
+    return np.isin(lab, wanted) * im
+
+
+def _dilate_fft(mask, strel):
+    """_fftmorphology.py:75-93 -- zero-pad by 1, fftconvolve 'same' > 0.1, crop."""
+    from scipy.signal import fftconvolve
+    padded = np.pad(mask, pad_width=1, mode="constant", constant_values=0)
+    hit = fftconvolve(padded, strel, mode="same") > 0.1
+    return hit[(slice(1, -1),) * mask.ndim]
+
+
+def porosimetry(im, sizes=25, inlets=None, access_limited=True, mode="hybrid", divs=1,
+                nthreads=0):
+    """F:1124-1148 + loop bodies F:1177-1192 ('dt') and F:1193-1209 ('hybrid').
+
+    `divs` is accepted and ignored (results are chunk-invariant, F:1517-1520);
+    mode 'mio' is outside the path.
+    """
+    if mode not in ("dt", "hybrid"):
+        if mode == "mio":
+            raise NotImplementedError("mode 'mio' is outside the oracle's scope")
+        raise Exception("Unrecognized mode " + mode)
+    im = np.squeeze(im)
+    par = nthreads if nthreads > 0 else 0
+    dt = edt(im > 0, parallel=par)
+    if inlets is None:
+        inlets = border_faces(im.shape)
+    if isinstance(sizes, int):
+        sizes = np.logspace(start=np.log10(np.amax(dt)), stop=0, num=sizes)
+    else:
+        sizes = np.unique(sizes)[-1::-1]
+    conn = _cross(im.ndim)
+    out = np.zeros(np.shape(im))
+    for r in sizes:
+        seeds = dt >= r
+        if access_limited:
+            seeds = trim_disconnected_blobs(seeds, inlets, strel=conn)
+        if not np.any(seeds):
+            continue
+        if mode == "dt":
+            fill = edt(~seeds, parallel=par) < r
+        else:
+            fill = _dilate_fft(seeds, ps_round(r, im.ndim))
+        out[(out == 0) * fill] = r
+    return out
+
+
+def local_thickness(im, sizes=25, mode="hybrid", divs=1, nthreads=0):
+    """F:1027-1029 -- porosimetry without access limitation."""
+    return porosimetry(im, sizes=sizes, access_limited=False, mode=mode, divs=divs,
+                       nthreads=nthreads)

@@ -1,0 +1,142 @@
+"""CPU suite: pins the oracle (oracle/cpu.py + oracle/edt_oracle.c) against the golden
+vectors produced by the reference's own source (tests/golden/make_golden.py) and against
+the golden numbers asserted by the reference's tests."""
+import numpy as np
+import pytest
+
+from oracle import cpu as oc
+from tests.golden_io import sha
+
+
+def _scipy_d2(mask):
+    import scipy.ndimage as spim
+    idx = spim.distance_transform_edt(mask, return_distances=False, return_indices=True)
+    d2 = np.zeros(mask.shape, dtype=np.int64)
+    grids = np.meshgrid(*[np.arange(n) for n in mask.shape], indexing="ij", sparse=True)
+    for ax in range(mask.ndim):
+        d2 += (idx[ax].astype(np.int64) - grids[ax]) ** 2
+    return d2.astype(np.uint32)
+
+
+@pytest.mark.parametrize("shape,p", [((37, 29, 41), 0.5), ((64, 64, 64), 0.97), ((1, 50, 60), 0.8),
+                                     ((5, 1, 7), 0.6), ((17, 251), 0.9), ((129,), 0.95)])
+def test_edt_oracle_vs_scipy(shape, p):
+    rng = np.random.default_rng(hash(shape) & 0xFFFF)
+    im = rng.random(shape) < p
+    im.flat[rng.integers(im.size)] = False          # at least one background voxel
+    assert np.array_equal(oc.edt_sq(im), _scipy_d2(im))
+
+
+def test_edt_oracle_degenerate():
+    assert np.all(oc.edt_sq(np.ones((4, 5, 6), bool)) == oc.INF_U32)
+    assert np.all(np.isinf(oc.edt(np.ones((4, 5, 6), bool))))
+    assert np.all(oc.edt_sq(np.zeros((4, 5, 6), bool)) == 0)
+    one = np.ones((9, 9, 9), bool)
+    one[4, 4, 4] = False
+    z, y, x = np.mgrid[-4:5, -4:5, -4:5]
+    assert np.array_equal(oc.edt_sq(one), (x * x + y * y + z * z).astype(np.uint32))
+
+
+def test_edt_oracle_golden(golden):
+    g = golden.blobs100
+    im = g.mask("im")
+    assert im.sum() / im.size == 0.499829                 # TF:17
+    d2 = oc.edt_sq(im)
+    assert sha(d2) == str(g.raw("d2_sha"))
+    assert int(d2.max()) == int(g.raw("d2_max"))
+    assert np.array_equal(d2[:, :, 50], g.raw("d2_slice50"))
+    assert np.array_equal(oc.edt_sq(im, nthreads=1), d2)
+
+
+def test_blobs_restatement_reproduces_reference_image(golden):
+    np.random.seed(0)
+    im = oc.blobs(shape=[100, 100, 100], blobiness=2)
+    assert np.array_equal(im, golden.blobs100.mask("im"))
+    im = oc.blobs([200, 200], porosity=0.55, blobiness=2, seed=0)
+    assert np.array_equal(im, golden.trim.mask("im2d"))
+
+
+def test_strels_golden(golden):
+    g = golden.strels
+    assert list(g.raw("sums")) == [25, 93, 29, 123]        # test_tools.py:309-316
+    assert np.array_equal(oc.ps_round(3, 2), g.mask("disk3"))
+    assert np.array_equal(oc.ps_round(3, 3), g.mask("ball3"))
+    assert np.array_equal(oc.ps_round(3, 2, smooth=False), g.mask("disk3_rough"))
+    assert np.array_equal(oc.ps_round(3, 3, smooth=False), g.mask("ball3_rough"))
+    assert np.array_equal(oc.ps_round(np.float32(4.2426405), 3), g.mask("ball_4p2426"))
+
+
+def test_porosimetry_num_points(golden):
+    im = golden.blobs100.mask("im")
+    mip = oc.porosimetry(im=im, sizes=10)
+    ans = np.array([0.00000000, 1.00000000, 1.37871571, 1.61887041, 1.90085700, 2.23196205,
+                    2.62074139, 3.07724114, 3.61325732])    # TF:39-41
+    assert np.allclose(np.unique(mip), ans)
+    assert np.array_equal(mip, golden.blobs100.rmap("poro_hybrid_sizes10"))
+    assert np.array_equal(oc.porosimetry(im=im, sizes=10, mode="dt"), mip)
+
+
+def test_porosimetry_modes_and_sizes(golden):
+    g = golden.blobs100
+    im = g.mask("im")
+    sizes = np.arange(25, 1, -1)
+    assert np.array_equal(oc.porosimetry(im, sizes=sizes, mode="dt"), g.rmap("poro_dt_arange_3d"))
+    im2d = im[:, :, 50]
+    assert np.array_equal(oc.porosimetry(im2d, sizes=sizes, mode="dt"), g.rmap("poro_dt_arange_2d"))
+    assert np.array_equal(oc.porosimetry(im2d, sizes=sizes, mode="hybrid"), g.rmap("poro_dt_arange_2d"))
+    s = np.logspace(0.01, 0.6, 5)
+    mip = oc.porosimetry(im=im, sizes=s, mode="dt")
+    assert np.allclose(np.unique(mip)[1:], s)                # TF:53-56
+    assert np.array_equal(mip, g.rmap("poro_logsizes"))
+
+
+def test_local_thickness_golden(golden):
+    g = golden.blobs100
+    im = g.mask("im")
+    lt = oc.local_thickness(im, mode="dt")
+    np.testing.assert_almost_equal(lt.max(), oc.edt(im).max(), decimal=6)   # TF:266-272
+    assert np.array_equal(lt, g.rmap("lt_dt_25"))
+    assert np.array_equal(oc.local_thickness(im[:, :, 50]), g.rmap("lt_2d_25"))
+    assert np.array_equal(oc.local_thickness(im, sizes=[6, 4.5, 3, 2, 1], mode="dt"),
+                          g.rmap("lt_list_sizes"))
+    assert np.array_equal(oc.porosimetry(im[:, :, 50], sizes=9, access_limited=False),
+                          g.rmap("poro_2d_noaccess"))
+
+
+def test_porosimetry_single_face_inlet(golden):
+    g = golden.blobs100
+    im = g.mask("im")
+    inlets = np.zeros_like(im)
+    inlets[0, ...] = True
+    assert np.array_equal(oc.porosimetry(im, sizes=12, inlets=inlets, mode="dt"),
+                          g.rmap("poro_inlet0_dt_12"))
+
+
+def test_trim_disconnected_blobs_golden(golden):
+    g = golden.trim
+    im, inl = g.mask("im2d"), g.mask("inlets2d")
+    assert np.array_equal(oc.trim_disconnected_blobs(im, inl), g.mask("out8"))
+    assert np.array_equal(oc.trim_disconnected_blobs(im, inl, strel=oc._cross(2)), g.mask("out4"))
+    im, inl = g.mask("im3d"), g.mask("inlets3d")
+    assert np.array_equal(oc.trim_disconnected_blobs(im, inl), g.mask("out26"))
+    assert np.array_equal(oc.trim_disconnected_blobs(im, inl, strel=oc._cross(3)), g.mask("out6"))
+    with pytest.raises(Exception, match="inlets not valid"):
+        oc.trim_disconnected_blobs(im, np.zeros((3, 3, 3)))
+
+
+def test_misc2d_golden(golden):
+    g = golden.misc2d
+    lt = oc.local_thickness(g.mask("rsa"), sizes=[20, 10])
+    assert np.all(np.unique(lt) == [0, 10, 20])               # TF:274-279
+    assert np.array_equal(lt, g.rmap("lt_rsa"))
+    drn = g.mask("drn")
+    lt = oc.local_thickness(drn)
+    assert np.array_equal(lt, g.rmap("lt_drn"))
+    assert (lt > 25).sum() / drn.sum() == 0.34427115020497745  # test_drainage.py:17-18,49
+
+
+def test_numpy_integer_scalar_is_one_radius(golden):
+    """sizes=np.int64(n) is NOT n log-spaced radii (F:1131-1134)."""
+    im = golden.blobs100.mask("im")[:40, :40, :40]
+    lt = oc.local_thickness(im, sizes=np.int64(2), mode="dt")
+    assert set(np.unique(lt)) <= {0.0, 2.0}
