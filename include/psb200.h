@@ -1,0 +1,152 @@
+/*
+ * psb200.h -- C ABI of libpsb200.so: B200 (sm_100a) kernels for PoreSpy's hot path
+ *             edt.edt -> porosimetry / local_thickness (+ trim_disconnected_blobs).
+ *
+ * This is the drop-in boundary.  PoreSpy is pure Python, so the "FFI" a maintainer
+ * would bind is ctypes (shown in INTEGRATION.md); every entry point below replaces one
+ * piece of the reference path and cites it:
+ *
+ *   F  = /root/reference/src/porespy/filters/_funcs.py
+ *   T  = /root/reference/src/porespy/tools/_funcs.py
+ *   B  = /root/reference/src/porespy/generators/_borders.py
+ *   edt = third-party `edt.edt` (seung-lab/euclidean-distance-transform-3d, unpinned in
+ *         /root/reference/pyproject.toml:29), call sites F:1126, F:1191, T:1153.
+ *
+ * Conventions
+ *   - Volumes are C-contiguous [nz][ny][nx] (x fastest); 2-D images pass nz = 1,
+ *     1-D lines pass nz = ny = 1.  Each dimension must be <= PSB200_MAX_DIM.
+ *   - All data pointers are DEVICE pointers unless the comment says "host".
+ *   - The library never allocates user-visible memory: scratch space comes from a
+ *     caller-provided workspace whose size the matching *_workspace_bytes() reports.
+ *   - Calls are asynchronous on the caller's stream (a cudaStream_t passed as void*),
+ *     except where "synchronises" is stated.  No global mutable state beyond the ctx.
+ *   - Every function returns a status (0 = OK, negative = error); the message of the
+ *     last error on the calling thread is returned by psb200_last_error().
+ *   - No torch types, no C++ exceptions across this boundary.
+ */
+#ifndef PSB200_H
+#define PSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSB200_VERSION 100            /* 0.1.0 */
+#define PSB200_MAX_DIM 32767          /* per-axis limit: 3*(MAX_DIM-1)^2 < 2^32 */
+#define PSB200_MAX_THRESHOLDS 253     /* radii (distinct thresholds) per *_idx call */
+#define PSB200_INF_U32 0xFFFFFFFFu    /* squared distance when no background exists */
+#define PSB200_IDX_KEEP 255           /* idx value: "already written by an earlier call" */
+
+#define PSB200_OK 0
+#define PSB200_ERR_INVALID (-1)       /* bad argument */
+#define PSB200_ERR_CUDA (-2)          /* CUDA runtime error (see psb200_last_error) */
+#define PSB200_ERR_WORKSPACE (-3)     /* workspace too small / missing */
+#define PSB200_ERR_UNSUPPORTED (-4)   /* outside the implemented envelope */
+
+/* inlet_mode of the access-limited paths (F:1128-1129, F:1181-1183) */
+#define PSB200_INLETS_NONE 0          /* access_limited=False (local_thickness) */
+#define PSB200_INLETS_FACES 1         /* default: get_border(shape,'faces') (B:93-100), never materialised */
+#define PSB200_INLETS_MASK 2          /* user mask, uint8 [nz][ny][nx], non-zero = inlet */
+
+/* algorithm selector (ctx option "algo") */
+#define PSB200_ALGO_FAST 0            /* bounded u8 pipeline (default) */
+#define PSB200_ALGO_GENERIC 1         /* three full u32 EDT passes per radius (slow, unbounded) */
+
+/* flags */
+#define PSB200_FLAG_IDX_PREINIT 1     /* local_thickness_idx: idx already holds 0 / PSB200_IDX_KEEP */
+#define PSB200_FLAG_EXPAND_MERGE 1    /* expand_idx_f64: leave out[] untouched where idx is 0 or KEEP */
+
+typedef struct psb200_ctx psb200_ctx;
+typedef void *psb200_stream;          /* cudaStream_t */
+
+int psb200_version(void);
+const char *psb200_last_error(void);
+
+/* One context per device (per rank).  Selects the device for subsequent calls. */
+int psb200_create(int device, psb200_ctx **ctx);
+int psb200_destroy(psb200_ctx *ctx);
+/* name: "algo" (PSB200_ALGO_*).  Returns PSB200_ERR_INVALID for unknown names. */
+int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t value);
+/* Number of kernel launches issued through this ctx since creation (bench bookkeeping). */
+int64_t psb200_launch_count(const psb200_ctx *ctx);
+
+/* ---------------------------------------------------------------- exact squared EDT
+ * Replaces edt.edt(data) at F:1126 / F:1191 / T:1153 (black_border=False, isotropic,
+ * binary).  d2_out[v] = exact integer squared distance from voxel v to the nearest
+ * zero voxel of `in`; 0 where in[v]==0; PSB200_INF_U32 everywhere if `in` has no zero.
+ * `in` is read-only.  d2_out may not alias in. */
+size_t psb200_edt_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx);
+int psb200_edt_sq_u8(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2_out,
+                     int64_t nz, int64_t ny, int64_t nx,
+                     void *ws, size_t ws_bytes, psb200_stream stream);
+
+/* Single passes of the separable transform, exposed for z-slab sharded volumes
+ * (SURVEY 8(e)): x and y passes run on the local slab, the z pass on the pencil
+ * layout [nz][ny/P][nx] after the all-to-all.  axis: 2 = x (reads `in`, writes d2),
+ * 1 = y, 0 = z (in place on d2; `in` ignored). */
+int psb200_edt_pass(psb200_ctx *ctx, int axis, const uint8_t *in, uint32_t *d2,
+                    int64_t nz, int64_t ny, int64_t nx,
+                    void *ws, size_t ws_bytes, psb200_stream stream);
+
+/* out[i] = float32(sqrt(d2[i])) (IEEE, correctly rounded == np.sqrt(float32));
+ * PSB200_INF_U32 -> +inf.  This is the float32 array edt.edt returns. */
+int psb200_sqrt_f32(psb200_ctx *ctx, const uint32_t *d2, float *out, int64_t n,
+                    psb200_stream stream);
+
+/* *dev_out = max(d2[0..n)) (device scalar, overwritten).  np.amax(dt) at F:1132. */
+int psb200_max_u32(psb200_ctx *ctx, const uint32_t *d2, int64_t n, uint32_t *dev_out,
+                   psb200_stream stream);
+
+/* ------------------------------------------------ sphere-insertion loop (F:1177-1209)
+ * For k = 0..nT-1 (thresholds strictly descending, host array T[k] = min{n : sqrt_f32(n)
+ * >= r_k}):   seeds = d2 >= T[k]  [F:1180/1196];  if inlet_mode != NONE keep only seeds
+ * connected (6-conn in 3-D, 4-conn in 2-D) to the inlets through seeds|inlets
+ * [F:1181-1183 -> F:1252-1270];  fill = {v : exists seed s, |v-s|^2 < T[k]}  [F:1191 ==
+ * F:1207];  idx[v] = k+1 where idx[v]==0 and fill  [F:1192/1209].
+ * idx is uint8 [nz][ny][nx]; zero-initialised by the call unless PSB200_FLAG_IDX_PREINIT.
+ * ndim (1,2,3) is the dimensionality of the squeezed image (selects the faces predicate).
+ * d2 is read-only. */
+size_t psb200_local_thickness_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny,
+                                              int64_t nx, int inlet_mode);
+int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2,
+                               const uint32_t *T_host, int nT, uint8_t *idx,
+                               const uint8_t *inlets, int inlet_mode, int ndim,
+                               int64_t nz, int64_t ny, int64_t nx, int flags,
+                               void *ws, size_t ws_bytes, psb200_stream stream);
+
+/* Step-level entry points of the same loop, for z-slab sharded volumes: the xy part of
+ * one radius is slab-local; the z part needs up to W = ceil(sqrt(T))-1 halo planes of
+ * the reach map from each z-neighbour (m_lo = the nlo planes just below local z=0 in
+ * ascending z order, m_hi = the nhi planes just above local z=nz-1; NULL/0 at the ends). */
+int psb200_lt_classify(psb200_ctx *ctx, const uint32_t *d2, const uint32_t *T_host, int nT,
+                       uint8_t *cls, int64_t n, psb200_stream stream);
+int psb200_lt_xy(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t *reach,
+                 int64_t nz, int64_t ny, int64_t nx, psb200_stream stream);
+int psb200_lt_z(psb200_ctx *ctx, const uint8_t *reach, const uint8_t *m_lo, int nlo,
+                const uint8_t *m_hi, int nhi, uint8_t *idx, int k, uint32_t T,
+                int64_t nz, int64_t ny, int64_t nx, psb200_stream stream);
+
+/* out[i] = lut_host[idx[i]] as float64 (np.zeros(shape) + radii, F:1178, F:1192, F:1212).
+ * lut_host has nlut entries (entry 0 must be 0.0).  With PSB200_FLAG_EXPAND_MERGE only
+ * voxels with idx in [1, nlut) are written. */
+int psb200_expand_idx_f64(psb200_ctx *ctx, const uint8_t *idx, const double *lut_host,
+                          int nlut, double *out, int64_t n, int flags, psb200_stream stream);
+/* idx[i] = out[i] != 0 ? PSB200_IDX_KEEP : 0   (continuation across >253 thresholds) */
+int psb200_mark_written(psb200_ctx *ctx, const double *out, uint8_t *idx, int64_t n,
+                        psb200_stream stream);
+
+/* ---------------------------------------------- trim_disconnected_blobs (F:1215-1270)
+ * out[v] = mask[v] && (the conn-component of (mask | inlets) containing v holds an inlet).
+ * conn: 6 or 26 (3-D), 4 or 8 (2-D, nz = 1).  inlets: uint8 mask (non-zero = inlet). */
+size_t psb200_flood_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx);
+int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t *inlets, uint8_t *out,
+                 int conn, int64_t nz, int64_t ny, int64_t nx,
+                 void *ws, size_t ws_bytes, psb200_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSB200_H */

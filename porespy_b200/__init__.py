@@ -1,0 +1,23 @@
+"""porespy_b200 -- B200-native (sm_100a) implementation of PoreSpy's hot path:
+exact 3-D EDT (`edt.edt`) -> `filters.local_thickness` / `filters.porosimetry`
+(+ `filters.trim_disconnected_blobs`), behind the reference's own signatures.
+
+    import porespy_b200 as psb
+    lt = psb.filters.local_thickness(im, sizes=25)          # same array PoreSpy returns
+    psb.install()                                           # or: accelerate an unmodified PoreSpy
+"""
+from . import _lib
+from . import edt as edt_module
+from . import filters
+from .edt import edt, edtsq
+from .filters import local_thickness, porosimetry, trim_disconnected_blobs
+from .patch import install, uninstall
+
+__version__ = "0.1.0"
+__all__ = ["edt", "edtsq", "filters", "local_thickness", "porosimetry",
+           "trim_disconnected_blobs", "install", "uninstall", "build"]
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library in-tree (nvcc, sm_100a)."""
+    return _lib.build(force=force, verbose=verbose)

@@ -1,0 +1,96 @@
+"""Thin device-side helpers: torch tensors are used only as device allocations and for the
+host<->device copies; every computation is a call into libpsb200.so."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._host import shape3
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def stream_ptr():
+    return ctypes.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def to_device_u8(arr, ctx, nonzero=True):
+    """Host array (bool / any numeric) or torch tensor -> contiguous uint8 device tensor (1 = non-zero)."""
+    torch = _torch()
+    dev = f"cuda:{ctx.device}"
+    if isinstance(arr, torch.Tensor):
+        t = arr.to(dev)
+        return (t != 0).to(torch.uint8).contiguous() if t.dtype != torch.uint8 or nonzero else t.contiguous()
+    a = np.asarray(arr)
+    if a.dtype == np.bool_:
+        a = np.ascontiguousarray(a).view(np.uint8)
+    elif a.dtype == np.uint8 and not nonzero:
+        a = np.ascontiguousarray(a)
+    else:
+        a = np.ascontiguousarray(a != 0).view(np.uint8)
+    return torch.from_numpy(a).to(dev, non_blocking=False)
+
+
+def edt_sq(ctx, im_u8, shape):
+    """uint8 device volume -> uint32 squared distances (device tensor)."""
+    torch = _torch()
+    nz, ny, nx = shape3(shape)
+    d2 = torch.empty(nz * ny * nx, dtype=torch.int32, device=im_u8.device)
+    nbytes = ctx.lib.psb200_edt_workspace_bytes(ctx.handle, nz, ny, nx)
+    ws = ctx.workspace(nbytes)
+    _lib.check(ctx.lib.psb200_edt_sq_u8(ctx.handle, ptr(im_u8), ptr(d2), nz, ny, nx, ptr(ws),
+                                        ws.numel(), stream_ptr()))
+    return d2
+
+
+def max_u32(ctx, d2):
+    torch = _torch()
+    out = torch.zeros(1, dtype=torch.int32, device=d2.device)
+    _lib.check(ctx.lib.psb200_max_u32(ctx.handle, ptr(d2), d2.numel(), ptr(out), stream_ptr()))
+    return int(out.cpu().numpy().view(np.uint32)[0])
+
+
+def sqrt_f32(ctx, d2):
+    torch = _torch()
+    out = torch.empty(d2.numel(), dtype=torch.float32, device=d2.device)
+    _lib.check(ctx.lib.psb200_sqrt_f32(ctx.handle, ptr(d2), ptr(out), d2.numel(), stream_ptr()))
+    return out
+
+
+def local_thickness_idx(ctx, d2, T, idx, inlets_u8, inlet_mode, ndim, shape, flags=0):
+    nz, ny, nx = shape3(shape)
+    nbytes = ctx.lib.psb200_local_thickness_workspace_bytes(ctx.handle, nz, ny, nx, inlet_mode)
+    ws = ctx.workspace(nbytes)
+    T = np.ascontiguousarray(T, dtype=np.uint32)
+    _lib.check(ctx.lib.psb200_local_thickness_idx(
+        ctx.handle, ptr(d2), T.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(T), ptr(idx),
+        ptr(inlets_u8), inlet_mode, ndim, nz, ny, nx, flags, ptr(ws), ws.numel(), stream_ptr()))
+
+
+def expand_idx(ctx, idx, lut, out, merge=False):
+    lut = np.ascontiguousarray(lut, dtype=np.float64)
+    _lib.check(ctx.lib.psb200_expand_idx_f64(
+        ctx.handle, ptr(idx), lut.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(lut),
+        ptr(out), idx.numel(), _lib.FLAG_EXPAND_MERGE if merge else 0, stream_ptr()))
+
+
+def mark_written(ctx, out, idx):
+    _lib.check(ctx.lib.psb200_mark_written(ctx.handle, ptr(out), ptr(idx), idx.numel(), stream_ptr()))
+
+
+def flood(ctx, mask_u8, inlets_u8, conn, shape):
+    torch = _torch()
+    nz, ny, nx = shape3(shape)
+    out = torch.empty(nz * ny * nx, dtype=torch.uint8, device=mask_u8.device)
+    nbytes = ctx.lib.psb200_flood_workspace_bytes(ctx.handle, nz, ny, nx)
+    ws = ctx.workspace(nbytes)
+    _lib.check(ctx.lib.psb200_flood(ctx.handle, ptr(mask_u8), ptr(inlets_u8), ptr(out), conn,
+                                    nz, ny, nx, ptr(ws), ws.numel(), stream_ptr()))
+    return out

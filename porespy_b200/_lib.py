@@ -1,0 +1,151 @@
+"""ctypes binding of libpsb200.so (the C ABI declared in include/psb200.h).
+
+The product path has no CPU fallback: if the shared library is missing or no CUDA device is
+visible, every public entry point raises -- it never routes through `oracle/`.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpsb200.so")
+CSRC = os.path.join(_HERE, "csrc")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "psb200.h")
+
+OK = 0
+INLETS_NONE, INLETS_FACES, INLETS_MASK = 0, 1, 2
+ALGO_FAST, ALGO_GENERIC = 0, 1
+FLAG_IDX_PREINIT = 1
+FLAG_EXPAND_MERGE = 1
+MAX_THRESHOLDS = 253
+MAX_DIM = 32767
+INF_U32 = 0xFFFFFFFF
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+class Psb200Error(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/psb200.cu for sm_100a into porespy_b200/libpsb200.so (in-tree)."""
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [HEADER]
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, "psb200.cu"), "-o", LIB_PATH]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_c = ctypes
+_vp, _i64, _i32, _u32, _sz = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_uint32, _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/psb200.h one to one
+SIGNATURES = {
+    "psb200_version": (_i32, []),
+    "psb200_last_error": (_c.c_char_p, []),
+    "psb200_create": (_i32, [_i32, _c.POINTER(_vp)]),
+    "psb200_destroy": (_i32, [_vp]),
+    "psb200_set_option": (_i32, [_vp, _c.c_char_p, _i64]),
+    "psb200_launch_count": (_i64, [_vp]),
+    "psb200_edt_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
+    "psb200_edt_sq_u8": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "psb200_edt_pass": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "psb200_sqrt_f32": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "psb200_max_u32": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "psb200_local_thickness_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64, _i32]),
+    "psb200_local_thickness_idx": (_i32, [_vp, _vp, _c.POINTER(_u32), _i32, _vp, _vp, _i32, _i32,
+                                          _i64, _i64, _i64, _i32, _vp, _sz, _vp]),
+    "psb200_lt_classify": (_i32, [_vp, _vp, _c.POINTER(_u32), _i32, _vp, _i64, _vp]),
+    "psb200_lt_xy": (_i32, [_vp, _vp, _i32, _u32, _vp, _i64, _i64, _i64, _vp]),
+    "psb200_lt_z": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _u32, _i64, _i64, _i64, _vp]),
+    "psb200_expand_idx_f64": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _i32, _vp]),
+    "psb200_mark_written": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "psb200_flood_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
+    "psb200_flood": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """dlopen libpsb200.so and attach the prototypes.  Raises if the library is absent."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise Psb200Error(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                    f"g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        msg = load().psb200_last_error().decode("utf-8", "replace")
+        raise Psb200Error(f"psb200 error {rc}: {msg}")
+
+
+class Context:
+    """One psb200 context per CUDA device (per rank)."""
+
+    def __init__(self, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise Psb200Error("porespy_b200 needs a CUDA device (B200); there is no CPU fallback")
+        self.lib = load()
+        self.device = int(device)
+        self.handle = _vp()
+        check(self.lib.psb200_create(self.device, ctypes.byref(self.handle)))
+        self._ws = None
+
+    def set_algo(self, algo):
+        check(self.lib.psb200_set_option(self.handle, b"algo", int(algo)))
+
+    def launch_count(self):
+        return int(self.lib.psb200_launch_count(self.handle))
+
+    def workspace(self, nbytes):
+        """Grow-only device scratch buffer (a torch uint8 tensor used purely as an allocation)."""
+        import torch
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=f"cuda:{self.device}")
+        return self._ws
+
+    def release_workspace(self):
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.psb200_destroy(self.handle)
+                self.handle = _vp()
+        except Exception:
+            pass
+
+
+_contexts = {}
+
+
+def context(device=None):
+    import torch
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    device = int(device)
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]

@@ -1,0 +1,65 @@
+// common.cuh -- shared helpers for the psb200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PSB_INF 0xFFFFFFFFu
+
+// Class-map byte values (see lt_kernels.cuh)
+#define CLS_BG 255u        // background voxel (d2 == 0): never a seed, never filled
+#define CLS_NEVER 254u     // foreground voxel that is a seed for no threshold of this call
+// x-distance byte values inside the xy tile
+#define GX_BG 255u         // background voxel: output skipped
+#define GX_FAR 254u        // no seed within 253 voxels along x
+
+struct psb200_ctx {
+    int device;
+    int sm_count;
+    int max_smem_optin;
+    int algo;
+    long long launches;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ uint32_t byte_of(uint32_t v, int j) { return (v >> (8 * j)) & 0xFFu; }
+
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    return a | (b << 8) | (c << 16) | (d << 24);
+}
+
+// Load 4 consecutive bytes row[x..x+3] of a line of length nx; bytes outside [0,nx) read as
+// `fill`.  Uses one 32-bit load when the address is 4-byte aligned and fully inside.
+__device__ __forceinline__ uint32_t load4(const uint8_t *__restrict__ row, int x, int nx,
+                                          uint32_t fill)
+{
+    if (x >= 0 && x + 3 < nx && ((reinterpret_cast<uintptr_t>(row + x) & 3u) == 0))
+        return __ldg(reinterpret_cast<const uint32_t *>(row + x));
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int xx = x + j;
+        uint32_t b = (xx >= 0 && xx < nx) ? (uint32_t)__ldg(row + xx) : fill;
+        v |= b << (8 * j);
+    }
+    return v;
+}
+
+__device__ __forceinline__ void store4(uint8_t *__restrict__ row, int x, int nx, uint32_t v)
+{
+    if (x + 3 < nx && ((reinterpret_cast<uintptr_t>(row + x) & 3u) == 0)) {
+        *reinterpret_cast<uint32_t *>(row + x) = v;
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (x + j < nx) row[x + j] = (uint8_t)byte_of(v, j);
+}
+
+// ceil(sqrt(x)) for 1 <= x <= 65536 (exact: sqrtf is correctly rounded and the gap between
+// sqrt of a non-square and the next integer is > 1/(2*257) >> ulp).
+__device__ __forceinline__ uint32_t ceil_sqrt_small(uint32_t x)
+{
+    return (uint32_t)__float2int_ru(sqrtf((float)x));
+}

@@ -1,0 +1,553 @@
+// psb200.cu -- C-ABI entry points of libpsb200.so (see include/psb200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/psb200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "edt_kernels.cuh"
+#include "flood_kernels.cuh"
+#include "lt_kernels.cuh"
+
+// ------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(PSB200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                     \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                        \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                    \
+    do {                                                                                     \
+        (ctx)->launches++;                                                                   \
+        CUDA_TRY(cudaGetLastError());                                                        \
+    } while (0)
+
+extern "C" int psb200_version(void) { return PSB200_VERSION; }
+extern "C" const char *psb200_last_error(void) { return g_err; }
+
+extern "C" int psb200_create(int device, psb200_ctx **out)
+{
+    if (!out) return fail(PSB200_ERR_INVALID, "psb200_create: ctx pointer is NULL");
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count)
+        return fail(PSB200_ERR_INVALID, "psb200_create: device %d not in [0,%d)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    psb200_ctx *c = new psb200_ctx();
+    c->device = device;
+    c->algo = PSB200_ALGO_FAST;
+    c->launches = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CUDA_TRY(cudaFuncSetAttribute(lt_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_x_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_x_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    *out = c;
+    return PSB200_OK;
+}
+
+extern "C" int psb200_destroy(psb200_ctx *ctx)
+{
+    delete ctx;
+    return PSB200_OK;
+}
+
+extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name) return fail(PSB200_ERR_INVALID, "set_option: NULL argument");
+    if (!strcmp(name, "algo")) {
+        if (value != PSB200_ALGO_FAST && value != PSB200_ALGO_GENERIC)
+            return fail(PSB200_ERR_INVALID, "set_option: algo must be 0 (fast) or 1 (generic)");
+        ctx->algo = (int)value;
+        return PSB200_OK;
+    }
+    return fail(PSB200_ERR_INVALID, "set_option: unknown option '%s'", name);
+}
+
+extern "C" int64_t psb200_launch_count(const psb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// --------------------------------------------------------------------------- utilities
+static int check_dims(const char *who, int64_t nz, int64_t ny, int64_t nx)
+{
+    if (nz < 1 || ny < 1 || nx < 1)
+        return fail(PSB200_ERR_INVALID, "%s: empty volume (%lld,%lld,%lld)", who, (long long)nz,
+                    (long long)ny, (long long)nx);
+    if (nz > PSB200_MAX_DIM || ny > PSB200_MAX_DIM || nx > PSB200_MAX_DIM)
+        return fail(PSB200_ERR_UNSUPPORTED, "%s: dimension exceeds %d", who, PSB200_MAX_DIM);
+    return PSB200_OK;
+}
+
+struct Carver {
+    char *base;
+    size_t off;
+    template <typename T>
+    T *take(size_t count)
+    {
+        off = (off + 255) & ~(size_t)255;
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+static int grid_for(int64_t n, int block, int sm_count, int per_sm)
+{
+    int64_t g = (n + block - 1) / block;
+    int64_t cap = (int64_t)sm_count * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+#define COL_BLOCK 128
+#define COL_BLOCKS_PER_SM 8
+
+static int64_t col_threads(const psb200_ctx *ctx) { return (int64_t)ctx->sm_count * COL_BLOCKS_PER_SM * COL_BLOCK; }
+
+static size_t stack_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny)
+{
+    int64_t nmax = ny > nz ? ny : nz;
+    if (ny <= 1 && nz <= 1) return 0;
+    return (size_t)col_threads(ctx) * (size_t)nmax * sizeof(uint2);
+}
+
+// ---------------------------------------------------------------------------------- EDT
+extern "C" size_t psb200_edt_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx)
+{
+    (void)nx;
+    if (!ctx) return 0;
+    Carver c{nullptr, 0};
+    c.take<char>(stack_bytes(ctx, nz, ny));
+    return c.off + 256;
+}
+
+template <int SITE_MODE>
+static int launch_x(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2, int64_t nlines, int nx, int k,
+                    cudaStream_t st)
+{
+    const int nwords = (nx + 31) / 32;
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * 3 * nwords * 4 > 96 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * 3 * nwords * 4;
+    const int grid = grid_for(nlines, warps, ctx->sm_count, 16);
+    edt_x_kernel<SITE_MODE><<<grid, warps * 32, smem, st>>>(in, d2, nlines, nx, k);
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+// axis 1 (y) or 0 (z), in place on d2 unless a Store functor redirects the output
+template <typename Store>
+static int launch_col(psb200_ctx *ctx, int axis, const uint32_t *src, Store store, int64_t nz,
+                      int64_t ny, int64_t nx, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    const int64_t plane = ny * nx;
+    int64_t ncols, inner, outer, stride;
+    int n;
+    if (axis == 1) { ncols = nz * nx; inner = nx; outer = plane; stride = nx; n = (int)ny; }
+    else { ncols = plane; inner = plane; outer = 0; stride = plane; n = (int)nz; }
+    const int64_t need = (int64_t)col_threads(ctx) * n * (int64_t)sizeof(uint2);
+    if (!ws || (int64_t)ws_bytes < need)
+        return fail(PSB200_ERR_WORKSPACE, "column pass needs %lld workspace bytes, got %lld",
+                    (long long)need, (long long)ws_bytes);
+    const int grid = grid_for(ncols, COL_BLOCK, ctx->sm_count, COL_BLOCKS_PER_SM);
+    edt_col_kernel<Store><<<grid, COL_BLOCK, 0, st>>>(src, store, ncols, inner, outer, stride, n,
+                                                      reinterpret_cast<uint2 *>(ws));
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_edt_pass(psb200_ctx *ctx, int axis, const uint8_t *in, uint32_t *d2,
+                               int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
+                               psb200_stream stream)
+{
+    if (!ctx || !d2) return fail(PSB200_ERR_INVALID, "edt_pass: NULL argument");
+    int rc = check_dims("edt_pass", nz, ny, nx);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    void *wsa = ws ? (void *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
+    size_t wsb = ws ? ws_bytes - ((uintptr_t)wsa - (uintptr_t)ws) : 0;
+    if (axis == 2) {
+        if (!in) return fail(PSB200_ERR_INVALID, "edt_pass: x pass needs the input image");
+        return launch_x<0>(ctx, in, d2, nz * ny, (int)nx, 0, st);
+    }
+    if (axis == 1) {
+        if (ny == 1) return PSB200_OK;
+        return launch_col(ctx, 1, d2, EdtStoreU32{d2}, nz, ny, nx, wsa, wsb, st);
+    }
+    if (axis == 0) {
+        if (nz == 1) return PSB200_OK;
+        return launch_col(ctx, 0, d2, EdtStoreU32{d2}, nz, ny, nx, wsa, wsb, st);
+    }
+    return fail(PSB200_ERR_INVALID, "edt_pass: axis must be 0, 1 or 2");
+}
+
+extern "C" int psb200_edt_sq_u8(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2, int64_t nz,
+                                int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
+                                psb200_stream stream)
+{
+    if (!ctx || !in || !d2) return fail(PSB200_ERR_INVALID, "edt_sq_u8: NULL argument");
+    for (int axis = 2; axis >= 0; --axis) {
+        int rc = psb200_edt_pass(ctx, axis, in, d2, nz, ny, nx, ws, ws_bytes, stream);
+        if (rc) return rc;
+    }
+    return PSB200_OK;
+}
+
+extern "C" int psb200_sqrt_f32(psb200_ctx *ctx, const uint32_t *d2, float *out, int64_t n,
+                               psb200_stream stream)
+{
+    if (!ctx || !d2 || !out || n < 0) return fail(PSB200_ERR_INVALID, "sqrt_f32: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sqrt_f32_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, (cudaStream_t)stream>>>(d2, out, n);
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_max_u32(psb200_ctx *ctx, const uint32_t *d2, int64_t n, uint32_t *dev_out,
+                              psb200_stream stream)
+{
+    if (!ctx || !d2 || !dev_out || n < 0) return fail(PSB200_ERR_INVALID, "max_u32: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(dev_out, 0, sizeof(uint32_t), st));
+    if (n == 0) return PSB200_OK;
+    max_u32_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(d2, n, dev_out);
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+// ------------------------------------------------------------------ local thickness loop
+static uint32_t isqrt_u32(uint32_t v)
+{
+    uint32_t r = (uint32_t)__builtin_sqrt((double)v);
+    while ((uint64_t)r * r > v) --r;
+    while ((uint64_t)(r + 1) * (r + 1) <= v) ++r;
+    return r;
+}
+
+static int check_thresholds(const char *who, const uint32_t *T, int nT)
+{
+    if (nT < 0 || nT > PSB200_MAX_THRESHOLDS)
+        return fail(PSB200_ERR_INVALID, "%s: nT=%d outside [0,%d]", who, nT, PSB200_MAX_THRESHOLDS);
+    if (nT && !T) return fail(PSB200_ERR_INVALID, "%s: thresholds pointer is NULL", who);
+    for (int k = 0; k < nT; ++k) {
+        if (T[k] == 0) return fail(PSB200_ERR_INVALID, "%s: threshold %d is 0", who, k);
+        if (k && T[k] >= T[k - 1])
+            return fail(PSB200_ERR_INVALID, "%s: thresholds must be strictly descending", who);
+    }
+    return PSB200_OK;
+}
+
+struct LtWorkspace {
+    uint8_t *cls, *rcls, *reach;
+    uint32_t *parent;
+    int *gate;
+    uint32_t *gen_d2;     // generic algo: full u32 distance map of ~seeds
+    char *gen_stk;
+    size_t gen_stk_bytes;
+    size_t total;
+};
+
+static LtWorkspace carve_lt(const psb200_ctx *ctx, char *base, int64_t nz, int64_t ny, int64_t nx,
+                            int inlet_mode)
+{
+    const size_t n = (size_t)nz * ny * nx;
+    Carver c{base, 0};
+    LtWorkspace w{};
+    w.gate = c.take<int>(64);
+    w.cls = c.take<uint8_t>(n + 16);
+    w.reach = c.take<uint8_t>(n + 16);
+    if (inlet_mode != PSB200_INLETS_NONE) {
+        w.rcls = c.take<uint8_t>(n + 16);
+        w.parent = c.take<uint32_t>(n + 1);
+    }
+    if (ctx->algo == PSB200_ALGO_GENERIC) {
+        w.gen_d2 = c.take<uint32_t>(n);
+        w.gen_stk_bytes = stack_bytes(ctx, nz, ny);
+        w.gen_stk = c.take<char>(w.gen_stk_bytes);
+    }
+    w.total = c.off + 256;
+    return w;
+}
+
+extern "C" size_t psb200_local_thickness_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny,
+                                                         int64_t nx, int inlet_mode)
+{
+    if (!ctx) return 0;
+    return carve_lt(ctx, nullptr, nz, ny, nx, inlet_mode).total + 256;
+}
+
+extern "C" size_t psb200_flood_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx)
+{
+    if (!ctx) return 0;
+    psb200_ctx tmp = *ctx;
+    tmp.algo = PSB200_ALGO_FAST;
+    return carve_lt(&tmp, nullptr, nz, ny, nx, PSB200_INLETS_MASK).total + 256;
+}
+
+static int classify_impl(psb200_ctx *ctx, const uint32_t *d2, const uint32_t *T_host, int nT,
+                         uint8_t *cls, int64_t n, cudaStream_t st)
+{
+    TArg targ;
+    memset(&targ, 0, sizeof(targ));
+    for (int k = 0; k < nT; ++k) targ.t[k] = T_host[k];
+    lt_classify_kernel<<<grid_for((n + 3) / 4, 256, ctx->sm_count, 16), 256, 0, st>>>(d2, cls, n, targ, nT);
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_lt_classify(psb200_ctx *ctx, const uint32_t *d2, const uint32_t *T_host, int nT,
+                                  uint8_t *cls, int64_t n, psb200_stream stream)
+{
+    if (!ctx || !d2 || !cls || n < 0) return fail(PSB200_ERR_INVALID, "lt_classify: bad argument");
+    int rc = check_thresholds("lt_classify", T_host, nT);
+    if (rc) return rc;
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return classify_impl(ctx, d2, T_host, nT, cls, n, (cudaStream_t)stream);
+}
+
+static int lt_xy_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t *reach,
+                      int64_t nz, int64_t ny, int64_t nx, const int *gate, cudaStream_t st)
+{
+    const int W = (int)isqrt_u32(T - 1);
+    if (W > LT_MAX_W)
+        return fail(PSB200_ERR_UNSUPPORTED, "lt_xy: threshold %u exceeds the uint8 pipeline (r > 254)", T);
+    int Ly = ny < 64 ? (int)ny : 64;
+    const int HW = (W + 31) / 32, NW = 4 + 2 * HW;
+    size_t smem = (size_t)(Ly + 2 * W) * LT_XT + (size_t)LT_WARPS * NW * 4;
+    if ((int)smem > ctx->max_smem_optin)
+        return fail(PSB200_ERR_UNSUPPORTED, "lt_xy: tile needs %zu bytes of shared memory", smem);
+    dim3 grid((unsigned)((nx + LT_XT - 1) / LT_XT), (unsigned)((ny + Ly - 1) / Ly), (unsigned)nz);
+    lt_xy_kernel<<<grid, LT_WARPS * 32, smem, st>>>(cls, reach, (int)ny, (int)nx, k, T, W, Ly, gate);
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+#define LT_LZ 32
+
+static int lt_z_impl(psb200_ctx *ctx, const uint8_t *reach, const uint8_t *m_lo, int nlo,
+                     const uint8_t *m_hi, int nhi, uint8_t *idx, int k, uint32_t T, int64_t nz,
+                     int64_t ny, int64_t nx, const int *gate, cudaStream_t st)
+{
+    const int W = (int)isqrt_u32(T - 1);
+    const int64_t plane = ny * nx;
+    if (nlo > W) { m_lo += (int64_t)(nlo - W) * plane; nlo = W; }
+    if (nhi > W) nhi = W;
+    const bool vec4 = (plane % 4 == 0) && (((uintptr_t)reach | (uintptr_t)idx | (uintptr_t)m_lo | (uintptr_t)m_hi) % 4 == 0);
+    const unsigned gy = (unsigned)((nz + LT_LZ - 1) / LT_LZ);
+    if (vec4) {
+        dim3 grid((unsigned)((plane / 4 + 255) / 256), gy);
+        lt_z_kernel<LT_LZ, 4><<<grid, 256, 0, st>>>(reach, m_lo, nlo, m_hi, nhi, idx, (int)nz, plane, W,
+                                                   (uint32_t)(k + 1), gate);
+    } else {
+        dim3 grid((unsigned)((plane + 255) / 256), gy);
+        lt_z_kernel<LT_LZ, 1><<<grid, 256, 0, st>>>(reach, m_lo, nlo, m_hi, nhi, idx, (int)nz, plane, W,
+                                                   (uint32_t)(k + 1), gate);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_lt_xy(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t *reach,
+                            int64_t nz, int64_t ny, int64_t nx, psb200_stream stream)
+{
+    if (!ctx || !cls || !reach || T == 0 || k < 0 || k >= PSB200_MAX_THRESHOLDS)
+        return fail(PSB200_ERR_INVALID, "lt_xy: bad argument");
+    int rc = check_dims("lt_xy", nz, ny, nx);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return lt_xy_impl(ctx, cls, k, T, reach, nz, ny, nx, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int psb200_lt_z(psb200_ctx *ctx, const uint8_t *reach, const uint8_t *m_lo, int nlo,
+                           const uint8_t *m_hi, int nhi, uint8_t *idx, int k, uint32_t T, int64_t nz,
+                           int64_t ny, int64_t nx, psb200_stream stream)
+{
+    if (!ctx || !reach || !idx || T == 0 || k < 0 || k >= PSB200_MAX_THRESHOLDS || nlo < 0 || nhi < 0 ||
+        (nlo && !m_lo) || (nhi && !m_hi))
+        return fail(PSB200_ERR_INVALID, "lt_z: bad argument");
+    int rc = check_dims("lt_z", nz, ny, nx);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return lt_z_impl(ctx, reach, m_lo, nlo, m_hi, nhi, idx, k, T, nz, ny, nx, nullptr, (cudaStream_t)stream);
+}
+
+static int uf_step(psb200_ctx *ctx, LtWorkspace &w, const InletSpec &inl, int klo, int khi, int conn,
+                   int64_t nz, int64_t ny, int64_t nx, cudaStream_t st)
+{
+    const int64_t n = nz * ny * nx;
+    const int g = grid_for(n, 256, ctx->sm_count, 16);
+    uf_activate_kernel<<<g, 256, 0, st>>>(w.parent, w.cls, inl, klo, khi, conn, (int)nz, (int)ny, (int)nx);
+    LAUNCH_CHECK(ctx);
+    uf_mark_kernel<<<g, 256, 0, st>>>(w.parent, w.cls, w.rcls, khi, n, w.gate);
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, const uint32_t *T_host,
+                                          int nT, uint8_t *idx, const uint8_t *inlets, int inlet_mode,
+                                          int ndim, int64_t nz, int64_t ny, int64_t nx, int flags,
+                                          void *ws, size_t ws_bytes, psb200_stream stream)
+{
+    if (!ctx || !d2 || !idx) return fail(PSB200_ERR_INVALID, "local_thickness_idx: NULL argument");
+    int rc = check_dims("local_thickness_idx", nz, ny, nx);
+    if (rc) return rc;
+    rc = check_thresholds("local_thickness_idx", T_host, nT);
+    if (rc) return rc;
+    if (inlet_mode < PSB200_INLETS_NONE || inlet_mode > PSB200_INLETS_MASK)
+        return fail(PSB200_ERR_INVALID, "local_thickness_idx: bad inlet_mode %d", inlet_mode);
+    if (inlet_mode == PSB200_INLETS_MASK && !inlets)
+        return fail(PSB200_ERR_INVALID, "local_thickness_idx: inlet mask is NULL");
+    if (ndim < 1 || ndim > 3) return fail(PSB200_ERR_INVALID, "local_thickness_idx: ndim must be 1..3");
+    const int64_t n = nz * ny * nx;
+    if (inlet_mode != PSB200_INLETS_NONE && n > 0xFFFFFFF0LL)
+        return fail(PSB200_ERR_UNSUPPORTED, "access-limited flooding supports < 2^32 voxels per GPU");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    char *base = ws ? (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
+    LtWorkspace w = carve_lt(ctx, base, nz, ny, nx, inlet_mode);
+    if (!ws || w.total + 256 > ws_bytes)
+        return fail(PSB200_ERR_WORKSPACE, "local_thickness_idx needs %zu workspace bytes, got %zu",
+                    w.total + 256, ws_bytes);
+    if (!(flags & PSB200_FLAG_IDX_PREINIT)) CUDA_TRY(cudaMemsetAsync(idx, 0, (size_t)n, st));
+    if (nT == 0) return PSB200_OK;
+
+    rc = classify_impl(ctx, d2, T_host, nT, w.cls, n, st);
+    if (rc) return rc;
+
+    const bool al = inlet_mode != PSB200_INLETS_NONE;
+    InletSpec inl{inlet_mode, ndim, inlets};
+    const int g = grid_for(n, 256, ctx->sm_count, 16);
+    if (al) {
+        CUDA_TRY(cudaMemsetAsync(w.gate, 0, sizeof(int), st));
+        uf_rcls_init_kernel<<<g, 256, 0, st>>>(w.cls, w.rcls, n);
+        LAUNCH_CHECK(ctx);
+        uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx);
+        LAUNCH_CHECK(ctx);
+    }
+    const uint8_t *cmap = al ? w.rcls : w.cls;
+    const int *gate = al ? w.gate : nullptr;
+    for (int k = 0; k < nT; ++k) {
+        const uint32_t T = T_host[k];
+        if (al) {
+            rc = uf_step(ctx, w, inl, k - 1, k, 6, nz, ny, nx, st);
+            if (rc) return rc;
+        }
+        if (ctx->algo == PSB200_ALGO_GENERIC) {
+            // reference-shaped path: full EDT of ~seeds, then fill <=> d2' < T  (F:1191)
+            rc = launch_x<1>(ctx, cmap, w.gen_d2, nz * ny, (int)nx, k, st);
+            if (rc) return rc;
+            const EdtStoreFill fillst{idx, T, (uint8_t)(k + 1)};
+            if (nz > 1) {
+                if (ny > 1) {
+                    rc = launch_col(ctx, 1, w.gen_d2, EdtStoreU32{w.gen_d2}, nz, ny, nx, w.gen_stk, w.gen_stk_bytes, st);
+                    if (rc) return rc;
+                }
+                rc = launch_col(ctx, 0, w.gen_d2, fillst, nz, ny, nx, w.gen_stk, w.gen_stk_bytes, st);
+            } else if (ny > 1) {
+                rc = launch_col(ctx, 1, w.gen_d2, fillst, nz, ny, nx, w.gen_stk, w.gen_stk_bytes, st);
+            } else {
+                fill_from_d2_kernel<<<g, 256, 0, st>>>(w.gen_d2, fillst, n);
+                LAUNCH_CHECK(ctx);
+            }
+            if (rc) return rc;
+            continue;
+        }
+        if (T == 1) {
+            lt_point_kernel<<<g, 256, 0, st>>>(cmap, idx, n, k, (uint32_t)(k + 1), gate);
+            LAUNCH_CHECK(ctx);
+            continue;
+        }
+        rc = lt_xy_impl(ctx, cmap, k, T, w.reach, nz, ny, nx, gate, st);
+        if (rc) return rc;
+        rc = lt_z_impl(ctx, w.reach, nullptr, 0, nullptr, 0, idx, k, T, nz, ny, nx, gate, st);
+        if (rc) return rc;
+    }
+    return PSB200_OK;
+}
+
+extern "C" int psb200_expand_idx_f64(psb200_ctx *ctx, const uint8_t *idx, const double *lut_host, int nlut,
+                                     double *out, int64_t n, int flags, psb200_stream stream)
+{
+    if (!ctx || !idx || !lut_host || !out || nlut < 1 || nlut > 254 || n < 0)
+        return fail(PSB200_ERR_INVALID, "expand_idx_f64: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    LutArg lut;
+    memset(&lut, 0, sizeof(lut));
+    for (int i = 0; i < nlut; ++i) lut.v[i] = lut_host[i];
+    lt_expand_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(
+        idx, lut, nlut, out, n, (flags & PSB200_FLAG_EXPAND_MERGE) ? 1 : 0);
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_mark_written(psb200_ctx *ctx, const double *out, uint8_t *idx, int64_t n,
+                                   psb200_stream stream)
+{
+    if (!ctx || !out || !idx || n < 0) return fail(PSB200_ERR_INVALID, "mark_written: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    lt_mark_written_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, (cudaStream_t)stream>>>(out, idx, n);
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+// -------------------------------------------------------------------------------- flood
+extern "C" int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t *inlets, uint8_t *out,
+                            int conn, int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
+                            psb200_stream stream)
+{
+    if (!ctx || !mask || !inlets || !out) return fail(PSB200_ERR_INVALID, "flood: NULL argument");
+    int rc = check_dims("flood", nz, ny, nx);
+    if (rc) return rc;
+    int c3;
+    if (conn == 6 || conn == 4) c3 = 6;
+    else if (conn == 26 || conn == 8) c3 = 26;
+    else return fail(PSB200_ERR_INVALID, "flood: conn must be 4/8 (2-D) or 6/26 (3-D), got %d", conn);
+    if ((conn == 4 || conn == 8) && nz != 1)
+        return fail(PSB200_ERR_INVALID, "flood: conn %d is 2-D connectivity but nz=%lld", conn, (long long)nz);
+    const int64_t n = nz * ny * nx;
+    if (n > 0xFFFFFFF0LL) return fail(PSB200_ERR_UNSUPPORTED, "flood supports < 2^32 voxels per GPU");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    psb200_ctx tmp = *ctx;
+    tmp.algo = PSB200_ALGO_FAST;
+    char *base = ws ? (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
+    LtWorkspace w = carve_lt(&tmp, base, nz, ny, nx, PSB200_INLETS_MASK);
+    if (!ws || w.total + 256 > ws_bytes)
+        return fail(PSB200_ERR_WORKSPACE, "flood needs %zu workspace bytes, got %zu", w.total + 256, ws_bytes);
+    const int g = grid_for(n, 256, ctx->sm_count, 16);
+    InletSpec inl{PSB200_INLETS_MASK, 3, inlets};
+    CUDA_TRY(cudaMemsetAsync(w.gate, 0, sizeof(int), st));
+    flood_cls_kernel<<<g, 256, 0, st>>>(mask, w.cls, n);
+    LAUNCH_CHECK(ctx);
+    uf_rcls_init_kernel<<<g, 256, 0, st>>>(w.cls, w.rcls, n);
+    LAUNCH_CHECK(ctx);
+    uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx);
+    LAUNCH_CHECK(ctx);
+    rc = uf_step(ctx, w, inl, -1, 0, c3, nz, ny, nx, st);
+    if (rc) return rc;
+    flood_out_kernel<<<g, 256, 0, st>>>(w.rcls, out, n);
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}

@@ -1,0 +1,146 @@
+"""Drop-in replacements for the reference's hot-path filters, same signatures and results:
+
+* `porosimetry`             /root/reference/src/porespy/filters/_funcs.py:1032-1212
+* `local_thickness`         /root/reference/src/porespy/filters/_funcs.py:947-1029
+* `trim_disconnected_blobs` /root/reference/src/porespy/filters/_funcs.py:1215-1270
+
+Host code here only does what numpy does in the reference prologue (squeeze, radii, inlet
+validation); all voxel work runs in libpsb200.so on the GPU.  There is no CPU fallback.
+"""
+import logging
+
+import numpy as np
+
+from . import _device as dev
+from . import _host as host
+from . import _lib
+
+logger = logging.getLogger(__name__)
+
+__all__ = ["porosimetry", "local_thickness", "trim_disconnected_blobs"]
+
+
+def _result_for_no_background(shape, radii):
+    """Image without any background voxel: edt == +inf everywhere (black_border=False), so every
+    radius r with `inf >= r` seeds the whole image and `edt(all False) == 0 < r` fills it: the
+    first positive, non-NaN radius wins everywhere (parity unpinned upstream)."""
+    out = np.zeros(shape)
+    for r in radii:
+        if np.inf >= r and 0 < r:      # both False for NaN
+            out[...] = r
+            break
+    return out
+
+
+def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True):
+    """Device loop over the effective thresholds (in groups of <= 253) -> float64 radius map."""
+    torch = dev._torch()
+    n = int(np.prod(shape))
+    out = torch.empty(n, dtype=torch.float64, device=d2.device)
+    idx = torch.empty(n, dtype=torch.uint8, device=d2.device)
+    G = _lib.MAX_THRESHOLDS
+    ngroups = max(1, -(-len(T) // G))
+    for g in range(ngroups):
+        Tg, Rg = T[g * G:(g + 1) * G], R[g * G:(g + 1) * G]
+        flags = 0
+        if g > 0:
+            dev.mark_written(ctx, out, idx)
+            flags = _lib.FLAG_IDX_PREINIT
+        dev.local_thickness_idx(ctx, d2, Tg, idx, inlets_u8, inlet_mode, ndim, shape, flags)
+        lut = np.concatenate([[0.0], Rg])
+        dev.expand_idx(ctx, idx, lut, out, merge=(g > 0))
+    del idx
+    out = out.view(*shape) if len(shape) else out
+    if not as_numpy:
+        return out
+    res = out.cpu().numpy()
+    return res
+
+
+def porosimetry(im, sizes: int = 25, inlets=None, access_limited: bool = True,
+                mode: str = "hybrid", divs=1):
+    r"""Porosimetry simulation (sphere insertion from the inlets); see the reference docstring
+    (F:1040-1122) for the meaning of every argument -- they are unchanged.
+
+    `mode`: 'hybrid', 'dt' and 'mio' give identical results in the reference (its own tests
+    assert it, test/unit/test_filters.py:27-51); all three run the same exact integer
+    pipeline here.  `divs` is accepted for compatibility and ignored (the result of the
+    reference's chunked path is chunk-invariant by construction, F:1517-1520).
+    """
+    torch = dev._torch()
+    as_numpy = not isinstance(im, torch.Tensor)
+    if mode not in ("hybrid", "dt", "mio"):
+        raise Exception("Unrecognized mode " + mode)
+    if as_numpy:
+        im = np.squeeze(np.asarray(im))
+    else:
+        im = torch.squeeze(im)
+    shape = tuple(int(s) for s in im.shape)
+    ndim = len(shape)
+    if ndim == 0 or int(np.prod(shape)) == 0:
+        return np.zeros(shape)
+    ctx = _lib.context()
+    im_u8 = dev.to_device_u8(im, ctx)
+    d2 = dev.edt_sq(ctx, im_u8, shape)
+    del im_u8
+    max_d2 = dev.max_u32(ctx, d2)
+    radii = host.reference_sizes(sizes, max_d2)
+
+    inlet_mode, inlets_u8 = _lib.INLETS_NONE, None
+    if access_limited:
+        if inlets is None:
+            inlet_mode = _lib.INLETS_FACES
+        else:
+            if isinstance(inlets, torch.Tensor):
+                inlets = inlets.cpu().numpy()
+            mask = host.normalise_inlets(inlets, shape)
+            inlet_mode, inlets_u8 = _lib.INLETS_MASK, dev.to_device_u8(mask, ctx)
+
+    if max_d2 == host.INF_U32:
+        res = _result_for_no_background(shape, radii)
+        return res if as_numpy else torch.from_numpy(res).to(d2.device)
+    T, R = host.effective_thresholds(radii, max_d2)
+    return _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=as_numpy)
+
+
+def local_thickness(im, sizes: int = 25, mode: str = "hybrid", divs: int = 1):
+    r"""Radius of the largest sphere that covers each voxel and fits in the foreground.
+    Identical to `porosimetry(..., access_limited=False)` (F:1027-1029)."""
+    return porosimetry(im=im, sizes=sizes, access_limited=False, mode=mode, divs=divs)
+
+
+def trim_disconnected_blobs(im, inlets, strel=None):
+    r"""Removes foreground voxels not connected to the inlets (F:1215-1270).
+
+    `strel` is the connectivity neighbourhood.  The reference passes it to
+    `scipy.ndimage.label`; here the 3x3(x3) structuring elements PoreSpy itself uses are
+    recognised: the cross (`ball(1)`/`disk(1)`: 6-/4-connectivity) and the full cube
+    (`cube(3)`/`square(3)`: 26-/8-connectivity, the default).  Other shapes are rejected.
+    """
+    im = np.asarray(im)
+    if im.ndim not in (2, 3):
+        raise ValueError("trim_disconnected_blobs supports 2-D and 3-D images")
+    mask = host.normalise_inlets(inlets, im.shape)
+    full = 26 if im.ndim == 3 else 8
+    cross = 6 if im.ndim == 3 else 4
+    if strel is None:
+        conn = full
+    else:
+        s = np.asarray(strel) != 0
+        if s.shape != (3,) * im.ndim:
+            raise NotImplementedError("only 3x3(x3) connectivity structuring elements are supported")
+        grid = np.indices(s.shape) - 1
+        if np.array_equal(s, np.abs(grid).sum(axis=0) <= 1):
+            conn = cross
+        elif s.all():
+            conn = full
+        else:
+            raise NotImplementedError("strel must be the cross (ball(1)/disk(1)) or the full cube")
+    if im.size == 0:
+        return np.zeros(im.shape, dtype=im.dtype)
+    ctx = _lib.context()
+    fg = dev.to_device_u8(im > 0, ctx)
+    inl = dev.to_device_u8(mask, ctx)
+    shape3 = host.shape3(im.shape)
+    keep = dev.flood(ctx, fg, inl, conn, shape3).view(*im.shape).cpu().numpy().astype(bool)
+    return keep * im

@@ -1,0 +1,258 @@
+"""GPU suite (`-m gpu`): the CUDA path, called through the public API / C ABI, must be
+bit-exact against the CPU oracle and the reference-generated golden vectors."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cpu as oc                       # noqa: E402  (checker only)
+from tests.golden_io import sha                    # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def psb():
+    import torch
+    assert torch.cuda.is_available(), "GPU suite needs a CUDA device"
+    import porespy_b200 as psb
+    return psb
+
+
+def assert_same(got, want, what=""):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+    assert got.dtype == want.dtype, f"{what}: dtype {got.dtype} != {want.dtype}"
+    if np.array_equal(got, want):
+        return
+    bad = np.argwhere(got != want)
+    lines = [f"{what}: {len(bad)} of {got.size} voxels differ"]
+    for c in bad[:12]:
+        lines.append(f"  at {tuple(int(i) for i in c)}: got {got[tuple(c)]!r} want {want[tuple(c)]!r}")
+    lines.append(f"  got values {np.unique(got)[:20]}  want values {np.unique(want)[:20]}")
+    raise AssertionError("\n".join(lines))
+
+
+def set_algo(psb, name):
+    from porespy_b200 import _lib
+    _lib.context().set_algo(_lib.ALGO_GENERIC if name == "generic" else _lib.ALGO_FAST)
+
+
+def rand_image(shape, p, seed):
+    rng = np.random.default_rng(seed)
+    return rng.random(shape) < p
+
+
+# ---------------------------------------------------------------------------------- EDT
+EDT_CASES = [((37, 29, 41), 0.5), ((64, 64, 64), 0.97), ((13, 37, 101), 0.9), ((1, 50, 60), 0.8),
+             ((50, 1, 60), 0.8), ((50, 60, 1), 0.8), ((5, 1, 7), 0.6), ((17, 251), 0.9), ((129,), 0.95),
+             ((3, 300, 5), 0.99), ((127, 31, 33), 0.995), ((2, 2, 2), 0.5), ((1,), 1.0), ((70, 130), 0.999)]
+
+
+@pytest.mark.parametrize("shape,p", EDT_CASES)
+def test_edt_random(psb, shape, p):
+    im = rand_image(shape, p, seed=len(shape) * 1000 + shape[0])
+    from porespy_b200.edt import edt_sq_u32
+    assert_same(edt_sq_u32(im), oc.edt_sq(im), f"edt_sq {shape}")
+    dt = psb.edt(im)
+    assert dt.dtype == np.float32
+    assert_same(dt, oc.edt(im), f"edt {shape}")
+
+
+def test_edt_adversarial(psb):
+    from porespy_b200.edt import edt_sq_u32
+    one_bg = np.ones((33, 40, 47), bool)
+    one_bg[16, 20, 23] = False
+    assert_same(edt_sq_u32(one_bg), oc.edt_sq(one_bg), "single background voxel")
+    one_fg = np.zeros((33, 40, 47), bool)
+    one_fg[16, 20, 23] = True
+    assert_same(edt_sq_u32(one_fg), oc.edt_sq(one_fg), "single foreground voxel")
+    z, y, x = np.indices((24, 24, 24))
+    checker = ((z + y + x) % 2).astype(bool)
+    assert_same(edt_sq_u32(checker), oc.edt_sq(checker), "checkerboard")
+    empty = np.zeros((9, 10, 11), bool)
+    assert np.all(psb.edt(empty) == 0)
+    full = np.ones((9, 10, 11), bool)
+    assert np.all(edt_sq_u32(full) == 0xFFFFFFFF)
+    assert np.all(np.isinf(psb.edt(full)))              # black_border=False, note N8
+    corner = np.ones((40, 41, 300), bool)
+    corner[0, 0, 0] = False                             # long distances, 299^2+40^2+39^2
+    assert_same(edt_sq_u32(corner), oc.edt_sq(corner), "far corner")
+    # kwargs PoreSpy passes (F:1186-1189, _snows.py:600-607)
+    assert_same(psb.edt(data=one_bg, parallel=0), oc.edt(one_bg), "kwargs")
+    assert_same(psb.edtsq(one_bg), oc.edt_sq(one_bg).astype(np.float32), "edtsq")
+    with pytest.raises(NotImplementedError):
+        psb.edt(one_bg, black_border=True)
+
+
+def test_edt_golden_blobs100(psb, golden):
+    from porespy_b200.edt import edt_sq_u32
+    g = golden.blobs100
+    d2 = edt_sq_u32(g.mask("im"))
+    assert sha(d2) == str(g.raw("d2_sha"))
+    assert_same(d2[:, :, 50], g.raw("d2_slice50"), "d2 slice")
+
+
+def test_edt_config1_shape_sample(psb):
+    """BASELINE config 1 at a size the oracle finishes in seconds (256^3 of the 512^3 recipe)."""
+    from porespy_b200.edt import edt_sq_u32
+    im = oc.blobs([256, 256, 256], porosity=0.6, blobiness=2, seed=0)
+    assert_same(edt_sq_u32(im), oc.edt_sq(im), "blobs 256^3")
+
+
+# ------------------------------------------------------------------- local thickness
+LT_CASES = [((40, 36, 44), 12, 0.6), ((48, 52), 9, 0.6), ((30, 30, 30), [5, 3.5, 2, 1.2], 0.6),
+            ((33, 31, 29), np.arange(8, 1, -1), 0.5), ((61, 67, 131), 25, 0.7), ((1, 90, 140), 10, 0.6),
+            ((150, 3, 40), 6, 0.8), ((64, 200), 25, 0.75), ((257,), 5, 0.9)]
+
+
+@pytest.mark.parametrize("algo", ["fast", "generic"])
+@pytest.mark.parametrize("shape,sizes,por", LT_CASES)
+def test_local_thickness_vs_oracle(psb, algo, shape, sizes, por):
+    set_algo(psb, algo)
+    try:
+        if len(shape) == 1:
+            im = rand_image(shape, por, 5)
+            im[::17] = False
+        else:
+            im = oc.blobs(list(shape), porosity=por, blobiness=1.5, seed=7)
+        got = psb.filters.local_thickness(im, sizes=sizes, mode="dt")
+        want = oc.local_thickness(im, sizes=sizes, mode="dt")
+        assert got.dtype == np.float64
+        assert_same(got, want, f"local_thickness {algo} {shape}")
+    finally:
+        set_algo(psb, "fast")
+
+
+@pytest.mark.parametrize("algo", ["fast", "generic"])
+def test_local_thickness_goldens(psb, golden, algo):
+    set_algo(psb, algo)
+    try:
+        g = golden.blobs100
+        im = g.mask("im")
+        lt = psb.filters.local_thickness(im, mode="dt")
+        assert_same(lt, g.rmap("lt_dt_25"), "lt_dt_25")
+        np.testing.assert_almost_equal(lt.max(), psb.edt(im).max(), decimal=6)        # TF:266-272
+        assert_same(psb.filters.local_thickness(im, mode="hybrid"), g.rmap("lt_dt_25"), "hybrid")
+        assert_same(psb.filters.local_thickness(im[:, :, 50]), g.rmap("lt_2d_25"), "lt_2d_25")
+        assert_same(psb.filters.local_thickness(im, sizes=[6, 4.5, 3, 2, 1]), g.rmap("lt_list_sizes"),
+                    "lt_list_sizes")
+        assert_same(psb.filters.porosimetry(im[:, :, 50], sizes=9, access_limited=False),
+                    g.rmap("poro_2d_noaccess"), "poro_2d_noaccess")
+        m = golden.misc2d
+        lt = psb.filters.local_thickness(m.mask("rsa"), sizes=[20, 10])
+        assert np.all(np.unique(lt) == [0, 10, 20])                                   # TF:274-279
+        assert_same(lt, m.rmap("lt_rsa"), "lt_rsa")
+        drn = m.mask("drn")
+        lt = psb.filters.local_thickness(drn)
+        assert_same(lt, m.rmap("lt_drn"), "lt_drn")
+        assert (lt > 25).sum() / drn.sum() == 0.34427115020497745                    # test_drainage.py:49
+    finally:
+        set_algo(psb, "fast")
+
+
+def test_input_not_mutated_and_quirks(psb, golden):
+    im = golden.blobs100.mask("im")[:50, :50, :50].copy()
+    keep = im.copy()
+    a = psb.filters.local_thickness(im, sizes=np.int64(2))      # numpy int scalar: ONE radius (App. B1)
+    assert np.array_equal(im, keep) and a is not im
+    assert set(np.unique(a)) <= {0.0, 2.0}
+    assert_same(a, oc.local_thickness(im, sizes=np.int64(2), mode="dt"), "np.int64 sizes")
+    b = psb.filters.local_thickness(im[None, :, :, None, :1].repeat(1, axis=0), sizes=5)   # squeeze
+    assert b.shape == (50, 50)
+    with pytest.raises(Exception, match="Unrecognized mode"):
+        psb.filters.local_thickness(im, mode="nope")
+    assert np.all(psb.filters.local_thickness(np.zeros((8, 9, 10), bool)) == 0)      # all background
+    full = psb.filters.local_thickness(np.ones((6, 7, 8), bool), sizes=[3, 2])
+    assert np.all(full == 3.0)                                                       # no background (N8)
+    neg = psb.filters.local_thickness(im, sizes=[2.5, 0, -1])
+    assert_same(neg, oc.local_thickness(im, sizes=[2.5, 0, -1], mode="dt"), "non-positive radii")
+
+
+def test_many_thresholds_grouping(psb):
+    """more than 253 distinct thresholds -> several device calls chained through idx KEEP marks"""
+    im = oc.blobs([70, 60, 50], porosity=0.75, blobiness=0.6, seed=3)
+    dmax = float(oc.edt(im).max())
+    sizes = np.linspace(1.0, dmax, 900)
+    got = psb.filters.local_thickness(im, sizes=sizes)
+    want = oc.local_thickness(im, sizes=sizes, mode="dt")
+    assert_same(got, want, "900 radii")
+
+
+# ------------------------------------------------------------------------ porosimetry
+@pytest.mark.parametrize("algo", ["fast", "generic"])
+def test_porosimetry_goldens(psb, golden, algo):
+    set_algo(psb, algo)
+    try:
+        g = golden.blobs100
+        im = g.mask("im")
+        mip = psb.filters.porosimetry(im=im, sizes=10)
+        ans = np.array([0.00000000, 1.00000000, 1.37871571, 1.61887041, 1.90085700, 2.23196205,
+                        2.62074139, 3.07724114, 3.61325732])                          # TF:39-41
+        assert np.allclose(np.unique(mip), ans)
+        assert_same(mip, g.rmap("poro_hybrid_sizes10"), "poro sizes=10")
+        sizes = np.arange(25, 1, -1)
+        for mode in ("hybrid", "dt", "mio"):                                         # TF:44-51
+            assert_same(psb.filters.porosimetry(im, sizes=sizes, mode=mode), g.rmap("poro_dt_arange_3d"),
+                        f"3d {mode}")
+        assert_same(psb.filters.porosimetry(im[:, :, 50], sizes=sizes, mode="dt"),
+                    g.rmap("poro_dt_arange_2d"), "2d")                               # TF:27-34
+        s = np.logspace(0.01, 0.6, 5)
+        mip = psb.filters.porosimetry(im=im, sizes=s)
+        assert np.allclose(np.unique(mip)[1:], s)                                    # TF:53-56
+        assert_same(mip, g.rmap("poro_logsizes"), "logsizes")
+        inlets = np.zeros_like(im)
+        inlets[0, ...] = True
+        assert_same(psb.filters.porosimetry(im, sizes=12, inlets=inlets, mode="dt"),
+                    g.rmap("poro_inlet0_dt_12"), "inlet0")
+    finally:
+        set_algo(psb, "fast")
+
+
+@pytest.mark.parametrize("shape,por", [((44, 40, 36), 0.55), ((90, 110), 0.6), ((31, 64, 129), 0.5)])
+def test_porosimetry_vs_oracle(psb, shape, por):
+    im = oc.blobs(list(shape), porosity=por, blobiness=1.5, seed=11)
+    assert_same(psb.filters.porosimetry(im, sizes=10), oc.porosimetry(im, sizes=10, mode="dt"), "faces")
+    inlets = np.zeros(shape, dtype=int)
+    inlets[..., 0] = 1
+    assert_same(psb.filters.porosimetry(im, sizes=8, inlets=inlets),
+                oc.porosimetry(im, sizes=8, inlets=inlets, mode="dt"), "x-face inlet")
+    inlets = np.zeros(shape, dtype=bool)
+    inlets[tuple(s // 2 for s in shape)] = True                                     # a single (maybe solid) voxel
+    assert_same(psb.filters.porosimetry(im, sizes=6, inlets=inlets),
+                oc.porosimetry(im, sizes=6, inlets=inlets, mode="dt"), "point inlet")
+    with pytest.raises(Exception, match="inlets not valid"):
+        psb.filters.porosimetry(im, inlets=np.zeros(shape))
+
+
+def test_trim_disconnected_blobs(psb, golden):
+    g = golden.trim
+    im, inl = g.mask("im2d"), g.mask("inlets2d")
+    assert_same(psb.filters.trim_disconnected_blobs(im, inl), g.mask("out8"), "8-conn")   # TF:201-210
+    assert_same(psb.filters.trim_disconnected_blobs(im, inl, strel=oc._cross(2)), g.mask("out4"), "4-conn")
+    im, inl = g.mask("im3d"), g.mask("inlets3d")
+    assert_same(psb.filters.trim_disconnected_blobs(im, inl), g.mask("out26"), "26-conn")
+    assert_same(psb.filters.trim_disconnected_blobs(im, inl, strel=oc._cross(3)), g.mask("out6"), "6-conn")
+    rng = np.random.default_rng(0)
+    im = rng.random((40, 50, 60)) < 0.35                                             # near percolation
+    inl = np.zeros_like(im)
+    inl[:, :, -1] = True
+    for strel in (None, oc._cross(3)):
+        assert_same(psb.filters.trim_disconnected_blobs(im, inl, strel=strel),
+                    oc.trim_disconnected_blobs(im, inl, strel=strel), "random")
+
+
+def test_config0_golden(psb, golden):
+    """BASELINE config 0: 200^3 blobs(0.6, 2), sizes=25 -- reference output pinned by SHA-256."""
+    g = golden.config0
+    im = oc.blobs([200, 200, 200], porosity=0.6, blobiness=2, seed=0)
+    assert sha(im) == str(g.raw("im_sha"))
+    from porespy_b200.edt import edt_sq_u32
+    assert sha(edt_sq_u32(im)) == str(g.raw("d2_sha"))
+    assert sha(psb.edt(im)) == str(g.raw("dt_sha"))
+    lt = psb.filters.local_thickness(im, sizes=25)
+    v, c = np.unique(lt, return_counts=True)
+    assert np.array_equal(v, g.raw("lt_values")) and np.array_equal(c, g.raw("lt_counts"))
+    assert sha(lt) == str(g.raw("lt_sha"))
+    assert sha(psb.filters.porosimetry(im, sizes=25)) == str(g.raw("poro_faces_sha"))
+    inl = np.zeros_like(im)
+    inl[0, ...] = True
+    assert sha(psb.filters.porosimetry(im, sizes=25, inlets=inl)) == str(g.raw("poro_inlet0_sha"))

@@ -1,0 +1,153 @@
+"""CPU suite: host-side logic of the product (thresholds, radii, inlets), the numpy model of the
+bounded pipeline against the oracle, and the C-ABI surface (symbols only, no compute)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import cpu as oc
+from porespy_b200 import _host as host
+from porespy_b200 import _lib
+from tests import model_fast as mf
+
+
+def test_threshold_examples():
+    # r = 4.2426405 -> T = 18, r = 3.9947 -> T = 16
+    assert host.threshold_of(np.float32(4.2426405)) == 18
+    assert host.threshold_of(np.float32(3.9947)) == 16
+    assert host.threshold_of(np.int64(20)) == 400
+    assert host.threshold_of(3.0) == 9
+    assert host.threshold_of(1.0) == 1
+    assert host.threshold_of(0.0) == 0 and host.threshold_of(-2.5) == 0
+    assert host.threshold_of(np.nan) is None and host.threshold_of(np.inf) is None
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_threshold_matches_float_comparison(dtype):
+    rng = np.random.default_rng(3)
+    d2 = np.arange(0, 5000, dtype=np.uint32)
+    dt = np.sqrt(d2.astype(np.float32))
+    radii = np.concatenate([rng.uniform(0.5, 70, 200), np.sqrt(np.arange(1, 60))]).astype(dtype)
+    for r in radii:
+        T = host.threshold_of(r)
+        assert np.array_equal(dt >= r, d2 >= T), r
+        assert np.array_equal(dt < r, d2 < T), r
+
+
+def test_reference_sizes_dtype_and_values():
+    r = host.reference_sizes(25, 86)
+    assert r.dtype == np.float32 and len(r) == 25 and r[-1] == 1.0     # NEP 50 trap (note N1)
+    T, R = host.effective_thresholds(r, 86)
+    assert list(T) == [86, 72, 60, 50, 41, 34, 29, 24, 20, 17, 14, 12, 10, 8, 7, 6, 5, 4, 3, 2, 1]
+    assert R[0] == float(r[0]) and R[-1] == 1.0
+    r = host.reference_sizes([20, 10], 1000)
+    assert r.dtype.kind == "i" and list(r) == [20, 10]
+    r = host.reference_sizes(np.int64(7), 1000)           # numpy integer scalar: ONE radius
+    assert list(r) == [7]
+    T, R = host.effective_thresholds(host.reference_sizes([3, 2, 0, -1, 50], 30), 30)
+    assert list(T) == [9, 4] and list(R) == [3.0, 2.0]
+
+
+def test_all_background_yields_no_thresholds():
+    r = host.reference_sizes(10, 0)
+    T, R = host.effective_thresholds(r, 0)
+    assert len(T) == 0
+
+
+def test_normalise_inlets():
+    m = np.zeros((4, 5), bool)
+    m[0] = True
+    assert np.array_equal(host.normalise_inlets(m.astype(int), (4, 5)), m)
+    with pytest.raises(Exception, match="inlets not valid"):
+        host.normalise_inlets(np.zeros((4, 5)), (4, 5))
+    with pytest.raises(Exception, match="inlets not valid"):
+        host.normalise_inlets(m, (5, 4))
+    # tuple inlets follow the reference's own idiom literally (np.copy of the tuple becomes a
+    # 2-D integer array that indexes axis 0, F:1252-1255) -- quirk preserved, not "fixed"
+    where = (np.array([0, 0, 1]), np.array([1, 2, 3]))
+    ref = np.zeros((4, 5), bool)
+    ref[np.copy(where)] = True
+    assert np.array_equal(host.normalise_inlets(where, (4, 5)), ref)
+
+
+def _idx_to_map(idx, R):
+    return np.concatenate([[0.0], R])[idx]
+
+
+@pytest.mark.parametrize("shape,sizes", [((40, 36, 44), 12), ((48, 52), 9), ((30, 30, 30), [5, 3.5, 2, 1.2]),
+                                         ((33, 31, 29), np.arange(8, 1, -1))])
+def test_model_matches_oracle_local_thickness(shape, sizes):
+    im = oc.blobs(list(shape), porosity=0.6, blobiness=1.5, seed=7)
+    d2 = oc.edt_sq(im)
+    radii = host.reference_sizes(sizes, int(d2.max()))
+    T, R = host.effective_thresholds(radii, int(d2.max()))
+    got = _idx_to_map(mf.lt_idx(d2, T).reshape(shape), R)
+    want = oc.local_thickness(im, sizes=sizes, mode="dt")
+    assert np.array_equal(got, want)
+
+
+def test_model_matches_oracle_porosimetry():
+    shape = (36, 40, 32)
+    im = oc.blobs(list(shape), porosity=0.55, blobiness=1.5, seed=11)
+    d2 = oc.edt_sq(im)
+    inlets = np.zeros(shape, bool)
+    inlets[0] = True
+    radii = host.reference_sizes(10, int(d2.max()))
+    T, R = host.effective_thresholds(radii, int(d2.max()))
+
+    def trim(k, seeds):
+        return oc.trim_disconnected_blobs(seeds, inlets, strel=oc._cross(3))
+    got = _idx_to_map(mf.lt_idx(d2, T, seeds_filter=trim).reshape(shape), R)
+    want = oc.porosimetry(im, sizes=10, inlets=inlets, mode="dt")
+    assert np.array_equal(got, want)
+
+
+def test_model_golden(golden):
+    g = golden.blobs100
+    im = g.mask("im")[:60, :60, :60]
+    d2 = oc.edt_sq(im)
+    radii = host.reference_sizes(25, int(d2.max()))
+    T, R = host.effective_thresholds(radii, int(d2.max()))
+    got = _idx_to_map(mf.lt_idx(d2, T).reshape(im.shape), R)
+    assert np.array_equal(got, oc.local_thickness(im, mode="dt"))
+
+
+# ------------------------------------------------------------------------------ C ABI
+def _declared_symbols():
+    text = open(_lib.HEADER).read()
+    return sorted(set(re.findall(r"\b(psb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == sorted(_lib.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _declared_symbols():
+        assert hasattr(lib, name), name
+    lib.psb200_version.restype = ctypes.c_int
+    assert lib.psb200_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import porespy_b200 as psb
+    with pytest.raises(Exception):
+        psb.filters.local_thickness(np.ones((8, 8, 8), bool))
+    with pytest.raises(Exception):
+        psb.edt(np.ones((8, 8), bool))
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.abspath(_lib.__file__))
+    for fn in os.listdir(root):
+        if fn.endswith(".py"):
+            src = open(os.path.join(root, fn)).read()
+            assert "oracle" not in src.replace("no CPU fallback", "").lower() or fn == "_lib.py", fn
