@@ -68,10 +68,17 @@ const char *psb200_last_error(void);
 /* One context per device (per rank).  Selects the device for subsequent calls. */
 int psb200_create(int device, psb200_ctx **ctx);
 int psb200_destroy(psb200_ctx *ctx);
-/* name: "algo" (PSB200_ALGO_*).  Returns PSB200_ERR_INVALID for unknown names. */
+/* name: "algo" (PSB200_ALGO_*), "profile" (0/1: record a cudaEvent pair around every kernel
+ * launch).  Returns PSB200_ERR_INVALID for unknown names. */
 int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t value);
 /* Number of kernel launches issued through this ctx since creation (bench bookkeeping). */
 int64_t psb200_launch_count(const psb200_ctx *ctx);
+/* Per-kernel-family device time measured with CUDA events on the launching stream while the
+ * "profile" option is on.  psb200_profile_read synchronises, fills two arrays of
+ * psb200_profile_kernels() entries (milliseconds, launch counts) and clears the records. */
+int psb200_profile_kernels(void);
+const char *psb200_profile_name(int kernel_id);
+int psb200_profile_read(psb200_ctx *ctx, double *ms_total, int64_t *launches);
 
 /* ---------------------------------------------------------------- exact squared EDT
  * Replaces edt.edt(data) at F:1126 / F:1191 / T:1153 (black_border=False, isotropic,

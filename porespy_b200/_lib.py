@@ -55,6 +55,9 @@ SIGNATURES = {
     "psb200_destroy": (_i32, [_vp]),
     "psb200_set_option": (_i32, [_vp, _c.c_char_p, _i64]),
     "psb200_launch_count": (_i64, [_vp]),
+    "psb200_profile_kernels": (_i32, []),
+    "psb200_profile_name": (_c.c_char_p, [_i32]),
+    "psb200_profile_read": (_i32, [_vp, _c.POINTER(_c.c_double), _c.POINTER(_i64)]),
     "psb200_edt_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
     "psb200_edt_sq_u8": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_edt_pass": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
@@ -114,6 +117,17 @@ class Context:
 
     def set_algo(self, algo):
         check(self.lib.psb200_set_option(self.handle, b"algo", int(algo)))
+
+    def set_profile(self, on):
+        check(self.lib.psb200_set_option(self.handle, b"profile", 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel family: (total ms, launches)} since the last read (device-synchronising)."""
+        n = self.lib.psb200_profile_kernels()
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        check(self.lib.psb200_profile_read(self.handle, ms, cnt))
+        return {self.lib.psb200_profile_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}
 
     def launch_count(self):
         return int(self.lib.psb200_launch_count(self.handle))

@@ -12,12 +12,20 @@
 #define GX_BG 255u         // background voxel: output skipped
 #define GX_FAR 254u        // no seed within 253 voxels along x
 
+#include <vector>
+struct ProfRec {
+    int kid;
+    cudaEvent_t a, b;
+};
+
 struct psb200_ctx {
     int device;
     int sm_count;
     int max_smem_optin;
     int algo;
+    int profile;
     long long launches;
+    std::vector<ProfRec> prof;
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "edt_kernels.cuh"
@@ -37,6 +38,37 @@ static int fail(int code, const char *fmt, ...)
         CUDA_TRY(cudaGetLastError());                                                        \
     } while (0)
 
+// ---------------------------------------------------------------------------- profiling
+// Optional (ctx option "profile"): a cudaEvent pair around every kernel launch, on the
+// launching stream, summed per kernel family by psb200_profile_read().
+enum KernelId {
+    K_EDT_X = 0, K_EDT_Y, K_EDT_Z, K_SQRT, K_MAX, K_CLASSIFY, K_LT_XY, K_LT_Z, K_LT_POINT, K_EXPAND,
+    K_MARK_WRITTEN, K_UF_INIT, K_UF_ACTIVATE, K_UF_MARK, K_FLOOD_MISC, K_GEN_X, K_GEN_Y, K_GEN_Z, K_COUNT
+};
+static const char *const kKernelNames[K_COUNT] = {
+    "edt_x", "edt_y", "edt_z", "sqrt_f32", "max_u32", "lt_classify", "lt_xy", "lt_z", "lt_point",
+    "lt_expand", "lt_mark_written", "uf_init", "uf_activate", "uf_mark", "flood_misc",
+    "generic_x", "generic_y", "generic_z"};
+
+struct ProfScope {
+    psb200_ctx *c;
+    cudaStream_t st;
+    int kid;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(psb200_ctx *c_, cudaStream_t st_, int kid_) : c(c_), st(st_), kid(kid_)
+    {
+        if (!c->profile) return;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+        cudaEventRecord(a, st);
+    }
+    ~ProfScope()
+    {
+        if (!c->profile || !a || !b) return;
+        cudaEventRecord(b, st);
+        c->prof.push_back(ProfRec{kid, a, b});
+    }
+};
+
 extern "C" int psb200_version(void) { return PSB200_VERSION; }
 extern "C" const char *psb200_last_error(void) { return g_err; }
 
@@ -52,6 +84,7 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->device = device;
     c->algo = PSB200_ALGO_FAST;
     c->launches = 0;
+    c->profile = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_TRY(cudaFuncSetAttribute(lt_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
@@ -76,10 +109,39 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
         ctx->algo = (int)value;
         return PSB200_OK;
     }
+    if (!strcmp(name, "profile")) {
+        ctx->profile = value ? 1 : 0;
+        return PSB200_OK;
+    }
     return fail(PSB200_ERR_INVALID, "set_option: unknown option '%s'", name);
 }
 
 extern "C" int64_t psb200_launch_count(const psb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int psb200_profile_kernels(void) { return K_COUNT; }
+extern "C" const char *psb200_profile_name(int kernel_id)
+{
+    return (kernel_id >= 0 && kernel_id < K_COUNT) ? kKernelNames[kernel_id] : "";
+}
+
+// Synchronises on the recorded events.  ms_total / launches: arrays of psb200_profile_kernels()
+// entries (summed per kernel family since the last reset).  Clears the records.
+extern "C" int psb200_profile_read(psb200_ctx *ctx, double *ms_total, int64_t *launches)
+{
+    if (!ctx || !ms_total || !launches) return fail(PSB200_ERR_INVALID, "profile_read: NULL argument");
+    for (int i = 0; i < K_COUNT; ++i) { ms_total[i] = 0.0; launches[i] = 0; }
+    for (ProfRec &r : ctx->prof) {
+        CUDA_TRY(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_total[r.kid] += ms;
+        launches[r.kid] += 1;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+    return PSB200_OK;
+}
 
 // --------------------------------------------------------------------------- utilities
 static int check_dims(const char *who, int64_t nz, int64_t ny, int64_t nx)
@@ -145,7 +207,10 @@ static int launch_x(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2, int64_t nl
     while (warps > 1 && (size_t)warps * 3 * nwords * 4 > 96 * 1024) warps >>= 1;
     const size_t smem = (size_t)warps * 3 * nwords * 4;
     const int grid = grid_for(nlines, warps, ctx->sm_count, 16);
-    edt_x_kernel<SITE_MODE><<<grid, warps * 32, smem, st>>>(in, d2, nlines, nx, k);
+    {
+        ProfScope ps__(ctx, st, SITE_MODE == 0 ? K_EDT_X : K_GEN_X);
+        edt_x_kernel<SITE_MODE><<<grid, warps * 32, smem, st>>>(in, d2, nlines, nx, k);
+    }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
@@ -153,8 +218,10 @@ static int launch_x(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2, int64_t nl
 // axis 1 (y) or 0 (z), in place on d2 unless a Store functor redirects the output
 template <typename Store>
 static int launch_col(psb200_ctx *ctx, int axis, const uint32_t *src, Store store, int64_t nz,
-                      int64_t ny, int64_t nx, void *ws, size_t ws_bytes, cudaStream_t st)
+                      int64_t ny, int64_t nx, void *ws, size_t ws_bytes, cudaStream_t st,
+                      int prof_kid = -1)
 {
+    if (prof_kid < 0) prof_kid = axis == 1 ? K_EDT_Y : K_EDT_Z;
     const int64_t plane = ny * nx;
     int64_t ncols, inner, outer, stride;
     int n;
@@ -165,8 +232,11 @@ static int launch_col(psb200_ctx *ctx, int axis, const uint32_t *src, Store stor
         return fail(PSB200_ERR_WORKSPACE, "column pass needs %lld workspace bytes, got %lld",
                     (long long)need, (long long)ws_bytes);
     const int grid = grid_for(ncols, COL_BLOCK, ctx->sm_count, COL_BLOCKS_PER_SM);
-    edt_col_kernel<Store><<<grid, COL_BLOCK, 0, st>>>(src, store, ncols, inner, outer, stride, n,
-                                                      reinterpret_cast<uint2 *>(ws));
+    {
+        ProfScope ps__(ctx, st, prof_kid);
+        edt_col_kernel<Store><<<grid, COL_BLOCK, 0, st>>>(src, store, ncols, inner, outer, stride, n,
+                                                          reinterpret_cast<uint2 *>(ws));
+    }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
@@ -215,7 +285,10 @@ extern "C" int psb200_sqrt_f32(psb200_ctx *ctx, const uint32_t *d2, float *out, 
     if (!ctx || !d2 || !out || n < 0) return fail(PSB200_ERR_INVALID, "sqrt_f32: bad argument");
     if (n == 0) return PSB200_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    sqrt_f32_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, (cudaStream_t)stream>>>(d2, out, n);
+    {
+        ProfScope ps__(ctx, (cudaStream_t)stream, K_SQRT);
+        sqrt_f32_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, (cudaStream_t)stream>>>(d2, out, n);
+    }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
@@ -228,7 +301,10 @@ extern "C" int psb200_max_u32(psb200_ctx *ctx, const uint32_t *d2, int64_t n, ui
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(dev_out, 0, sizeof(uint32_t), st));
     if (n == 0) return PSB200_OK;
-    max_u32_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(d2, n, dev_out);
+    {
+        ProfScope ps__(ctx, st, K_MAX);
+        max_u32_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(d2, n, dev_out);
+    }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
@@ -308,7 +384,10 @@ static int classify_impl(psb200_ctx *ctx, const uint32_t *d2, const uint32_t *T_
     TArg targ;
     memset(&targ, 0, sizeof(targ));
     for (int k = 0; k < nT; ++k) targ.t[k] = T_host[k];
-    lt_classify_kernel<<<grid_for((n + 3) / 4, 256, ctx->sm_count, 16), 256, 0, st>>>(d2, cls, n, targ, nT);
+    {
+        ProfScope ps__(ctx, st, K_CLASSIFY);
+        lt_classify_kernel<<<grid_for((n + 3) / 4, 256, ctx->sm_count, 16), 256, 0, st>>>(d2, cls, n, targ, nT);
+    }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
@@ -336,7 +415,10 @@ static int lt_xy_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, ui
     if ((int)smem > ctx->max_smem_optin)
         return fail(PSB200_ERR_UNSUPPORTED, "lt_xy: tile needs %zu bytes of shared memory", smem);
     dim3 grid((unsigned)((nx + LT_XT - 1) / LT_XT), (unsigned)((ny + Ly - 1) / Ly), (unsigned)nz);
-    lt_xy_kernel<<<grid, LT_WARPS * 32, smem, st>>>(cls, reach, (int)ny, (int)nx, k, T, W, Ly, gate);
+    {
+        ProfScope ps__(ctx, st, K_LT_XY);
+        lt_xy_kernel<<<grid, LT_WARPS * 32, smem, st>>>(cls, reach, (int)ny, (int)nx, k, T, W, Ly, gate);
+    }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
@@ -355,12 +437,18 @@ static int lt_z_impl(psb200_ctx *ctx, const uint8_t *reach, const uint8_t *m_lo,
     const unsigned gy = (unsigned)((nz + LT_LZ - 1) / LT_LZ);
     if (vec4) {
         dim3 grid((unsigned)((plane / 4 + 255) / 256), gy);
-        lt_z_kernel<LT_LZ, 4><<<grid, 256, 0, st>>>(reach, m_lo, nlo, m_hi, nhi, idx, (int)nz, plane, W,
-                                                   (uint32_t)(k + 1), gate);
+        {
+            ProfScope ps__(ctx, st, K_LT_Z);
+            lt_z_kernel<LT_LZ, 4><<<grid, 256, 0, st>>>(reach, m_lo, nlo, m_hi, nhi, idx, (int)nz, plane, W,
+                                                       (uint32_t)(k + 1), gate);
+        }
     } else {
         dim3 grid((unsigned)((plane + 255) / 256), gy);
-        lt_z_kernel<LT_LZ, 1><<<grid, 256, 0, st>>>(reach, m_lo, nlo, m_hi, nhi, idx, (int)nz, plane, W,
-                                                   (uint32_t)(k + 1), gate);
+        {
+            ProfScope ps__(ctx, st, K_LT_Z);
+            lt_z_kernel<LT_LZ, 1><<<grid, 256, 0, st>>>(reach, m_lo, nlo, m_hi, nhi, idx, (int)nz, plane, W,
+                                                       (uint32_t)(k + 1), gate);
+        }
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
@@ -395,9 +483,15 @@ static int uf_step(psb200_ctx *ctx, LtWorkspace &w, const InletSpec &inl, int kl
 {
     const int64_t n = nz * ny * nx;
     const int g = grid_for(n, 256, ctx->sm_count, 16);
-    uf_activate_kernel<<<g, 256, 0, st>>>(w.parent, w.cls, inl, klo, khi, conn, (int)nz, (int)ny, (int)nx);
+    {
+        ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+        uf_activate_kernel<<<g, 256, 0, st>>>(w.parent, w.cls, inl, klo, khi, conn, (int)nz, (int)ny, (int)nx);
+    }
     LAUNCH_CHECK(ctx);
-    uf_mark_kernel<<<g, 256, 0, st>>>(w.parent, w.cls, w.rcls, khi, n, w.gate);
+    {
+        ProfScope ps__(ctx, st, K_UF_MARK);
+        uf_mark_kernel<<<g, 256, 0, st>>>(w.parent, w.cls, w.rcls, khi, n, w.gate);
+    }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
@@ -438,9 +532,15 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
     const int g = grid_for(n, 256, ctx->sm_count, 16);
     if (al) {
         CUDA_TRY(cudaMemsetAsync(w.gate, 0, sizeof(int), st));
-        uf_rcls_init_kernel<<<g, 256, 0, st>>>(w.cls, w.rcls, n);
+        {
+            ProfScope ps__(ctx, st, K_UF_INIT);
+            uf_rcls_init_kernel<<<g, 256, 0, st>>>(w.cls, w.rcls, n);
+        }
         LAUNCH_CHECK(ctx);
-        uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx);
+        {
+            ProfScope ps__(ctx, st, K_UF_INIT);
+            uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx);
+        }
         LAUNCH_CHECK(ctx);
     }
     const uint8_t *cmap = al ? w.rcls : w.cls;
@@ -458,21 +558,27 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
             const EdtStoreFill fillst{idx, T, (uint8_t)(k + 1)};
             if (nz > 1) {
                 if (ny > 1) {
-                    rc = launch_col(ctx, 1, w.gen_d2, EdtStoreU32{w.gen_d2}, nz, ny, nx, w.gen_stk, w.gen_stk_bytes, st);
+                    rc = launch_col(ctx, 1, w.gen_d2, EdtStoreU32{w.gen_d2}, nz, ny, nx, w.gen_stk, w.gen_stk_bytes, st, K_GEN_Y);
                     if (rc) return rc;
                 }
-                rc = launch_col(ctx, 0, w.gen_d2, fillst, nz, ny, nx, w.gen_stk, w.gen_stk_bytes, st);
+                rc = launch_col(ctx, 0, w.gen_d2, fillst, nz, ny, nx, w.gen_stk, w.gen_stk_bytes, st, K_GEN_Z);
             } else if (ny > 1) {
-                rc = launch_col(ctx, 1, w.gen_d2, fillst, nz, ny, nx, w.gen_stk, w.gen_stk_bytes, st);
+                rc = launch_col(ctx, 1, w.gen_d2, fillst, nz, ny, nx, w.gen_stk, w.gen_stk_bytes, st, K_GEN_Y);
             } else {
-                fill_from_d2_kernel<<<g, 256, 0, st>>>(w.gen_d2, fillst, n);
+                {
+                    ProfScope ps__(ctx, st, K_GEN_Z);
+                    fill_from_d2_kernel<<<g, 256, 0, st>>>(w.gen_d2, fillst, n);
+                }
                 LAUNCH_CHECK(ctx);
             }
             if (rc) return rc;
             continue;
         }
         if (T == 1) {
-            lt_point_kernel<<<g, 256, 0, st>>>(cmap, idx, n, k, (uint32_t)(k + 1), gate);
+            {
+                ProfScope ps__(ctx, st, K_LT_POINT);
+                lt_point_kernel<<<g, 256, 0, st>>>(cmap, idx, n, k, (uint32_t)(k + 1), gate);
+            }
             LAUNCH_CHECK(ctx);
             continue;
         }
@@ -495,8 +601,11 @@ extern "C" int psb200_expand_idx_f64(psb200_ctx *ctx, const uint8_t *idx, const 
     LutArg lut;
     memset(&lut, 0, sizeof(lut));
     for (int i = 0; i < nlut; ++i) lut.v[i] = lut_host[i];
-    lt_expand_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(
-        idx, lut, nlut, out, n, (flags & PSB200_FLAG_EXPAND_MERGE) ? 1 : 0);
+    {
+        ProfScope ps__(ctx, st, K_EXPAND);
+        lt_expand_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(
+            idx, lut, nlut, out, n, (flags & PSB200_FLAG_EXPAND_MERGE) ? 1 : 0);
+    }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
@@ -507,7 +616,10 @@ extern "C" int psb200_mark_written(psb200_ctx *ctx, const double *out, uint8_t *
     if (!ctx || !out || !idx || n < 0) return fail(PSB200_ERR_INVALID, "mark_written: bad argument");
     if (n == 0) return PSB200_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    lt_mark_written_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, (cudaStream_t)stream>>>(out, idx, n);
+    {
+        ProfScope ps__(ctx, (cudaStream_t)stream, K_MARK_WRITTEN);
+        lt_mark_written_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, (cudaStream_t)stream>>>(out, idx, n);
+    }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
@@ -539,15 +651,27 @@ extern "C" int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t 
     const int g = grid_for(n, 256, ctx->sm_count, 16);
     InletSpec inl{PSB200_INLETS_MASK, 3, inlets};
     CUDA_TRY(cudaMemsetAsync(w.gate, 0, sizeof(int), st));
-    flood_cls_kernel<<<g, 256, 0, st>>>(mask, w.cls, n);
+    {
+        ProfScope ps__(ctx, st, K_FLOOD_MISC);
+        flood_cls_kernel<<<g, 256, 0, st>>>(mask, w.cls, n);
+    }
     LAUNCH_CHECK(ctx);
-    uf_rcls_init_kernel<<<g, 256, 0, st>>>(w.cls, w.rcls, n);
+    {
+        ProfScope ps__(ctx, st, K_UF_INIT);
+        uf_rcls_init_kernel<<<g, 256, 0, st>>>(w.cls, w.rcls, n);
+    }
     LAUNCH_CHECK(ctx);
-    uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx);
+    {
+        ProfScope ps__(ctx, st, K_UF_INIT);
+        uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx);
+    }
     LAUNCH_CHECK(ctx);
     rc = uf_step(ctx, w, inl, -1, 0, c3, nz, ny, nx, st);
     if (rc) return rc;
-    flood_out_kernel<<<g, 256, 0, st>>>(w.rcls, out, n);
+    {
+        ProfScope ps__(ctx, st, K_FLOOD_MISC);
+        flood_out_kernel<<<g, 256, 0, st>>>(w.rcls, out, n);
+    }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
