@@ -79,6 +79,8 @@ int64_t psb200_launch_count(const psb200_ctx *ctx);
 int psb200_profile_kernels(void);
 const char *psb200_profile_name(int kernel_id);
 int psb200_profile_read(psb200_ctx *ctx, double *ms_total, int64_t *launches);
+/* Per-launch records in launch order; returns how many exist (at most `max` are written). */
+int psb200_profile_records(psb200_ctx *ctx, int *kernel_ids, float *ms, int max);
 
 /* ---------------------------------------------------------------- exact squared EDT
  * Replaces edt.edt(data) at F:1126 / F:1191 / T:1153 (black_border=False, isotropic,
@@ -131,8 +133,10 @@ int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2,
 int psb200_lt_classify(psb200_ctx *ctx, const uint32_t *d2, const uint32_t *T_host, int nT,
                        uint8_t *cls, int64_t n, psb200_stream stream);
 int psb200_lt_xy(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t *reach,
-                 int64_t nz, int64_t ny, int64_t nx, psb200_stream stream);
-int psb200_lt_z(psb200_ctx *ctx, const uint8_t *reach, const uint8_t *m_lo, int nlo,
+                 int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
+                 psb200_stream stream);      /* ws: >= nz*ny*nx + 256 bytes of scratch */
+/* reach is overwritten (forward cone values) by the call */
+int psb200_lt_z(psb200_ctx *ctx, uint8_t *reach, const uint8_t *m_lo, int nlo,
                 const uint8_t *m_hi, int nhi, uint8_t *idx, int k, uint32_t T,
                 int64_t nz, int64_t ny, int64_t nx, psb200_stream stream);
 

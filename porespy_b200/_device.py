@@ -21,18 +21,21 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def to_device_u8(arr, ctx, nonzero=True):
-    """Host array (bool / any numeric) or torch tensor -> contiguous uint8 device tensor (1 = non-zero)."""
+def to_device_u8(arr, ctx):
+    """Host array or torch tensor -> contiguous uint8 device tensor whose non-zero bytes mark the
+    foreground (the kernels test `byte != 0`, so bool / uint8 data is passed through as is)."""
     torch = _torch()
     dev = f"cuda:{ctx.device}"
     if isinstance(arr, torch.Tensor):
         t = arr.to(dev)
-        return (t != 0).to(torch.uint8).contiguous() if t.dtype != torch.uint8 or nonzero else t.contiguous()
+        if t.dtype == torch.bool:
+            return t.contiguous().view(torch.uint8)
+        if t.dtype == torch.uint8:
+            return t.contiguous()
+        return (t != 0).to(torch.uint8).contiguous()
     a = np.asarray(arr)
-    if a.dtype == np.bool_:
+    if a.dtype == np.bool_ or a.dtype == np.uint8:
         a = np.ascontiguousarray(a).view(np.uint8)
-    elif a.dtype == np.uint8 and not nonzero:
-        a = np.ascontiguousarray(a)
     else:
         a = np.ascontiguousarray(a != 0).view(np.uint8)
     return torch.from_numpy(a).to(dev, non_blocking=False)

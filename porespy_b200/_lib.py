@@ -58,6 +58,7 @@ SIGNATURES = {
     "psb200_profile_kernels": (_i32, []),
     "psb200_profile_name": (_c.c_char_p, [_i32]),
     "psb200_profile_read": (_i32, [_vp, _c.POINTER(_c.c_double), _c.POINTER(_i64)]),
+    "psb200_profile_records": (_i32, [_vp, _c.POINTER(_i32), _c.POINTER(_c.c_float), _i32]),
     "psb200_edt_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
     "psb200_edt_sq_u8": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_edt_pass": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
@@ -67,7 +68,7 @@ SIGNATURES = {
     "psb200_local_thickness_idx": (_i32, [_vp, _vp, _c.POINTER(_u32), _i32, _vp, _vp, _i32, _i32,
                                           _i64, _i64, _i64, _i32, _vp, _sz, _vp]),
     "psb200_lt_classify": (_i32, [_vp, _vp, _c.POINTER(_u32), _i32, _vp, _i64, _vp]),
-    "psb200_lt_xy": (_i32, [_vp, _vp, _i32, _u32, _vp, _i64, _i64, _i64, _vp]),
+    "psb200_lt_xy": (_i32, [_vp, _vp, _i32, _u32, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_lt_z": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _u32, _i64, _i64, _i64, _vp]),
     "psb200_expand_idx_f64": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _i32, _vp]),
     "psb200_mark_written": (_i32, [_vp, _vp, _vp, _i64, _vp]),
@@ -128,6 +129,13 @@ class Context:
         cnt = (ctypes.c_int64 * n)()
         check(self.lib.psb200_profile_read(self.handle, ms, cnt))
         return {self.lib.psb200_profile_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}
+
+    def profile_records(self, max_records=4096):
+        """[(kernel family, ms)] per launch, in launch order (call before profile_read)."""
+        ids = (ctypes.c_int * max_records)()
+        ms = (ctypes.c_float * max_records)()
+        n = min(self.lib.psb200_profile_records(self.handle, ids, ms, max_records), max_records)
+        return [(self.lib.psb200_profile_name(ids[i]).decode(), float(ms[i])) for i in range(n)]
 
     def launch_count(self):
         return int(self.lib.psb200_launch_count(self.handle))

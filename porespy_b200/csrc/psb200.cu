@@ -42,11 +42,11 @@ static int fail(int code, const char *fmt, ...)
 // Optional (ctx option "profile"): a cudaEvent pair around every kernel launch, on the
 // launching stream, summed per kernel family by psb200_profile_read().
 enum KernelId {
-    K_EDT_X = 0, K_EDT_Y, K_EDT_Z, K_SQRT, K_MAX, K_CLASSIFY, K_LT_XY, K_LT_Z, K_LT_POINT, K_EXPAND,
+    K_EDT_X = 0, K_EDT_Y, K_EDT_Z, K_SQRT, K_MAX, K_CLASSIFY, K_LT_XY, K_LT_X, K_LT_Y, K_LT_Z, K_LT_POINT, K_EXPAND,
     K_MARK_WRITTEN, K_UF_INIT, K_UF_ACTIVATE, K_UF_MARK, K_FLOOD_MISC, K_GEN_X, K_GEN_Y, K_GEN_Z, K_COUNT
 };
 static const char *const kKernelNames[K_COUNT] = {
-    "edt_x", "edt_y", "edt_z", "sqrt_f32", "max_u32", "lt_classify", "lt_xy", "lt_z", "lt_point",
+    "edt_x", "edt_y", "edt_z", "sqrt_f32", "max_u32", "lt_classify", "lt_xy", "lt_x", "lt_y", "lt_z", "lt_point",
     "lt_expand", "lt_mark_written", "uf_init", "uf_activate", "uf_mark", "flood_misc",
     "generic_x", "generic_y", "generic_z"};
 
@@ -88,6 +88,8 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_TRY(cudaFuncSetAttribute(lt_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(lt_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(lt_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_x_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_x_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     *out = c;
@@ -122,6 +124,23 @@ extern "C" int psb200_profile_kernels(void) { return K_COUNT; }
 extern "C" const char *psb200_profile_name(int kernel_id)
 {
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? kKernelNames[kernel_id] : "";
+}
+
+// Per-launch records in launch order (kernel id, milliseconds); returns the number of records
+// available (<= max written).  Does not clear.
+extern "C" int psb200_profile_records(psb200_ctx *ctx, int *kernel_ids, float *ms, int max)
+{
+    if (!ctx) return 0;
+    int i = 0;
+    for (ProfRec &r : ctx->prof) {
+        if (i < max && kernel_ids && ms) {
+            if (cudaEventSynchronize(r.b) != cudaSuccess) break;
+            kernel_ids[i] = r.kid;
+            if (cudaEventElapsedTime(&ms[i], r.a, r.b) != cudaSuccess) ms[i] = -1.f;
+        }
+        ++i;
+    }
+    return i;
 }
 
 // Synchronises on the recorded events.  ms_total / launches: arrays of psb200_profile_kernels()
@@ -332,7 +351,7 @@ static int check_thresholds(const char *who, const uint32_t *T, int nT)
 }
 
 struct LtWorkspace {
-    uint8_t *cls, *rcls, *reach;
+    uint8_t *cls, *rcls, *reach, *gx;
     uint32_t *parent;
     int *gate;
     uint32_t *gen_d2;     // generic algo: full u32 distance map of ~seeds
@@ -350,6 +369,7 @@ static LtWorkspace carve_lt(const psb200_ctx *ctx, char *base, int64_t nz, int64
     w.gate = c.take<int>(64);
     w.cls = c.take<uint8_t>(n + 16);
     w.reach = c.take<uint8_t>(n + 16);
+    w.gx = c.take<uint8_t>(n + 16);
     if (inlet_mode != PSB200_INLETS_NONE) {
         w.rcls = c.take<uint8_t>(n + 16);
         w.parent = c.take<uint32_t>(n + 1);
@@ -454,18 +474,84 @@ static int lt_z_impl(psb200_ctx *ctx, const uint8_t *reach, const uint8_t *m_lo,
     return PSB200_OK;
 }
 
+// streaming three-kernel form (nx % 16 == 0): x-distance, y tile scan, in-place z sweeps
+static bool streaming_ok(int64_t ny, int64_t nx, const void *a, const void *b, const void *c)
+{
+    (void)ny;
+    return (nx % 16 == 0) && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15u) == 0);
+}
+
+static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t *gx,
+                             uint8_t *reach, int64_t nz, int64_t ny, int64_t nx, const int *gate,
+                             cudaStream_t st)
+{
+    const int W = (int)isqrt_u32(T - 1);
+    if (W > LT_MAX_W)
+        return fail(PSB200_ERR_UNSUPPORTED, "lt_xy: threshold %u exceeds the uint8 pipeline (r > 254)", T);
+    {   // x pass
+        const int nch = (int)(nx / 16);
+        int warps = 8;
+        while (warps > 1 && (size_t)warps * 3 * nch * 4 > 64 * 1024) warps >>= 1;
+        const size_t smem = (size_t)warps * 3 * nch * 4;
+        const int grid = grid_for(nz * ny, warps, ctx->sm_count, 32);
+        {
+            ProfScope ps__(ctx, st, K_LT_X);
+            lt_x_kernel<<<grid, warps * 32, smem, st>>>(cls, gx, nz * ny, (int)nx, k, gate);
+        }
+        LAUNCH_CHECK(ctx);
+    }
+    {   // y pass
+        int Ly = W <= 16 ? 128 : 256;
+        if (ny < Ly) Ly = (int)ny;
+        const int rows = Ly + 2 * W;
+        const size_t smem = (size_t)rows * LT_XT + (size_t)((rows + 31) / 32) * 4 + 16;
+        if ((int)smem > ctx->max_smem_optin)
+            return fail(PSB200_ERR_UNSUPPORTED, "lt_y: tile needs %zu bytes of shared memory", smem);
+        dim3 grid((unsigned)((nx + LT_XT - 1) / LT_XT), (unsigned)((ny + Ly - 1) / Ly), (unsigned)nz);
+        {
+            ProfScope ps__(ctx, st, K_LT_Y);
+            lt_y_kernel<<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate);
+        }
+        LAUNCH_CHECK(ctx);
+    }
+    return PSB200_OK;
+}
+
+static int lt_z_stream_impl(psb200_ctx *ctx, uint8_t *reach, const uint8_t *m_lo, int nlo,
+                            const uint8_t *m_hi, int nhi, uint8_t *idx, int k, uint32_t T, int64_t nz,
+                            int64_t ny, int64_t nx, const int *gate, cudaStream_t st)
+{
+    const int W = (int)isqrt_u32(T - 1);
+    const int64_t plane = ny * nx;
+    if (nlo > W) { m_lo += (int64_t)(nlo - W) * plane; nlo = W; }
+    if (nhi > W) nhi = W;
+    const unsigned grid = (unsigned)((plane / 4 + 255) / 256);
+    {
+        ProfScope ps__(ctx, st, K_LT_Z);
+        lt_zsweep_kernel<<<grid, 256, 0, st>>>(reach, m_lo, nlo, m_hi, nhi, idx, (int)nz, plane,
+                                               (uint32_t)(k + 1), gate);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
 extern "C" int psb200_lt_xy(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t *reach,
-                            int64_t nz, int64_t ny, int64_t nx, psb200_stream stream)
+                            int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
+                            psb200_stream stream)
 {
     if (!ctx || !cls || !reach || T == 0 || k < 0 || k >= PSB200_MAX_THRESHOLDS)
         return fail(PSB200_ERR_INVALID, "lt_xy: bad argument");
     int rc = check_dims("lt_xy", nz, ny, nx);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    uint8_t *gx = ws ? (uint8_t *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
+    const size_t need = (size_t)(nz * ny * nx) + 256;
+    if (gx && ws_bytes >= need && streaming_ok(ny, nx, cls, reach, gx))
+        return lt_xy_stream_impl(ctx, cls, k, T, gx, reach, nz, ny, nx, nullptr, (cudaStream_t)stream);
     return lt_xy_impl(ctx, cls, k, T, reach, nz, ny, nx, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int psb200_lt_z(psb200_ctx *ctx, const uint8_t *reach, const uint8_t *m_lo, int nlo,
+extern "C" int psb200_lt_z(psb200_ctx *ctx, uint8_t *reach, const uint8_t *m_lo, int nlo,
                            const uint8_t *m_hi, int nhi, uint8_t *idx, int k, uint32_t T, int64_t nz,
                            int64_t ny, int64_t nx, psb200_stream stream)
 {
@@ -475,6 +561,9 @@ extern "C" int psb200_lt_z(psb200_ctx *ctx, const uint8_t *reach, const uint8_t 
     int rc = check_dims("lt_z", nz, ny, nx);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    if (streaming_ok(ny, nx, reach, idx, nullptr) && ((((uintptr_t)m_lo | (uintptr_t)m_hi) & 3u) == 0))
+        return lt_z_stream_impl(ctx, reach, m_lo, nlo, m_hi, nhi, idx, k, T, nz, ny, nx, nullptr,
+                                (cudaStream_t)stream);
     return lt_z_impl(ctx, reach, m_lo, nlo, m_hi, nhi, idx, k, T, nz, ny, nx, nullptr, (cudaStream_t)stream);
 }
 
@@ -582,9 +671,15 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
             LAUNCH_CHECK(ctx);
             continue;
         }
-        rc = lt_xy_impl(ctx, cmap, k, T, w.reach, nz, ny, nx, gate, st);
-        if (rc) return rc;
-        rc = lt_z_impl(ctx, w.reach, nullptr, 0, nullptr, 0, idx, k, T, nz, ny, nx, gate, st);
+        if (streaming_ok(ny, nx, cmap, w.reach, w.gx) && (((uintptr_t)idx & 15u) == 0)) {
+            rc = lt_xy_stream_impl(ctx, cmap, k, T, w.gx, w.reach, nz, ny, nx, gate, st);
+            if (rc) return rc;
+            rc = lt_z_stream_impl(ctx, w.reach, nullptr, 0, nullptr, 0, idx, k, T, nz, ny, nx, gate, st);
+        } else {
+            rc = lt_xy_impl(ctx, cmap, k, T, w.reach, nz, ny, nx, gate, st);
+            if (rc) return rc;
+            rc = lt_z_impl(ctx, w.reach, nullptr, 0, nullptr, 0, idx, k, T, nz, ny, nx, gate, st);
+        }
         if (rc) return rc;
     }
     return PSB200_OK;

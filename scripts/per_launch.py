@@ -1,0 +1,30 @@
+"""Dev tool: per-launch kernel times of one local_thickness call (CUDA events via the ABI)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+import porespy_b200 as psb
+from porespy_b200 import _lib, _host
+
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+dev = torch.device("cuda", 0)
+im = bench.device_blobs((size,) * 3, 0.6, 2, 0, dev)
+ctx = _lib.context(0)
+for _ in range(2):
+    psb.filters.local_thickness(im, sizes=25)
+torch.cuda.synchronize()
+ctx.set_profile(True); ctx.profile_read()
+psb.filters.local_thickness(im, sizes=25)
+recs = ctx.profile_records()
+from porespy_b200 import _device as d
+d2 = d.edt_sq(ctx, im, im.shape); mx = d.max_u32(ctx, d2)
+T, R = _host.effective_thresholds(_host.reference_sizes(25, mx), mx)
+print("max d2", mx, "T", list(T))
+k = 0
+for name, ms in recs:
+    tag = ""
+    if name in ("lt_xy", "lt_point"):
+        tag = f"k={k} T={T[k]} W={int(np.sqrt(T[k]-1))}"; 
+    if name in ("lt_z", "lt_point"):
+        k += 1
+    print(f"{name:14s} {ms:8.3f} ms {tag}")

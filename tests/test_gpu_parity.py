@@ -101,7 +101,10 @@ def test_edt_config1_shape_sample(psb):
 # ------------------------------------------------------------------- local thickness
 LT_CASES = [((40, 36, 44), 12, 0.6), ((48, 52), 9, 0.6), ((30, 30, 30), [5, 3.5, 2, 1.2], 0.6),
             ((33, 31, 29), np.arange(8, 1, -1), 0.5), ((61, 67, 131), 25, 0.7), ((1, 90, 140), 10, 0.6),
-            ((150, 3, 40), 6, 0.8), ((64, 200), 25, 0.75), ((257,), 5, 0.9)]
+            ((150, 3, 40), 6, 0.8), ((64, 200), 25, 0.75), ((257,), 5, 0.9),
+            # nx % 16 == 0: the streaming three-kernel path
+            ((45, 70, 64), 25, 0.6), ((130, 140, 160), 25, 0.65), ((300, 256), 25, 0.7),
+            ((300, 1, 32), 8, 0.8), ((20, 300, 16), 12, 0.7), ((256,), 6, 0.9), ((9, 520, 144), 30, 0.8)]
 
 
 @pytest.mark.parametrize("algo", ["fast", "generic"])
@@ -207,7 +210,8 @@ def test_porosimetry_goldens(psb, golden, algo):
         set_algo(psb, "fast")
 
 
-@pytest.mark.parametrize("shape,por", [((44, 40, 36), 0.55), ((90, 110), 0.6), ((31, 64, 129), 0.5)])
+@pytest.mark.parametrize("shape,por", [((44, 40, 36), 0.55), ((90, 110), 0.6), ((31, 64, 129), 0.5),
+                                       ((44, 40, 48), 0.55), ((90, 112), 0.6), ((131, 64, 128), 0.5)])
 def test_porosimetry_vs_oracle(psb, shape, por):
     im = oc.blobs(list(shape), porosity=por, blobiness=1.5, seed=11)
     assert_same(psb.filters.porosimetry(im, sizes=10), oc.porosimetry(im, sizes=10, mode="dt"), "faces")
