@@ -39,8 +39,8 @@ UNIT = "voxels/s"
 
 # algorithmic bytes per voxel per launch of each kernel family (SURVEY.md 8(d) pass model)
 ALG_BYTES = {
-    "edt_x": 5, "edt_y": 8, "edt_z": 8,              # 1+4, 4+4, 4+4  (B_edt = 21)
-    "lt_xy": 16, "lt_z": 6, "lt_point": 22,          # x(4+4) + y(4+4); z(4+1+1)  (B_rad = 22)
+    "edt_x": 5, "edt_y": 8, "edt_z": 8, "edt_fh_x": 5, "edt_fh_y": 8, "edt_fh_z": 8,              # 1+4, 4+4, 4+4  (B_edt = 21)
+    "lt_xy": 16, "lt_x": 8, "lt_y": 8, "lt_z": 6, "lt_point": 22,         # x(4+4) + y(4+4); z(4+1+1)  (B_rad = 22)
     "lt_expand": 9, "lt_classify": 5,
     "generic_x": 8, "generic_y": 8, "generic_z": 6,
 }
@@ -298,7 +298,7 @@ def run_ours(args):
         tot_ms, cnt = fam[dom]
         avg_s = tot_ms / cnt * 1e-3
         achieved = ALG_BYTES[dom] * per_voxels / avg_s / 1e9
-        n_eff = sum(c for k, (m, c) in prof.items() if k in ("lt_xy", "lt_point")) / args.steps
+        n_eff = sum(c for k, (m, c) in prof.items() if k in ("lt_xy", "lt_y", "lt_point")) / args.steps
         path_bytes = (21 + 22 * n_eff + 9) * nvox
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -92,6 +92,14 @@ int psb200_edt_sq_u8(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2_out,
                      int64_t nz, int64_t ny, int64_t nx,
                      void *ws, size_t ws_bytes, psb200_stream stream);
 
+/* Same transform with the epilogues fused into the last pass: out_kind 0 -> uint32 squared
+ * distances (as above), 1 -> float32 distances (exactly what edt.edt returns: IEEE sqrt of the
+ * exact integer, +inf when the image has no zero).  max_out (device uint32, may be NULL)
+ * receives max(d2) -- np.amax(dt) at F:1132 without another pass over the volume. */
+int psb200_edt_u8(psb200_ctx *ctx, const uint8_t *in, void *out, int out_kind,
+                  uint32_t *max_out, int64_t nz, int64_t ny, int64_t nx,
+                  void *ws, size_t ws_bytes, psb200_stream stream);
+
 /* Single passes of the separable transform, exposed for z-slab sharded volumes
  * (SURVEY 8(e)): x and y passes run on the local slab, the z pass on the pencil
  * layout [nz][ny/P][nx] after the all-to-all.  axis: 2 = x (reads `in`, writes d2),

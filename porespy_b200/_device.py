@@ -41,16 +41,25 @@ def to_device_u8(arr, ctx):
     return torch.from_numpy(a).to(dev, non_blocking=False)
 
 
-def edt_sq(ctx, im_u8, shape):
-    """uint8 device volume -> uint32 squared distances (device tensor)."""
+def edt_run(ctx, im_u8, shape, as_f32=False, want_max=False):
+    """uint8 device volume -> (uint32 squared distances | float32 distances, max d2 or None).
+    One call of psb200_edt_u8: sqrt and max are fused into the last pass."""
     torch = _torch()
     nz, ny, nx = shape3(shape)
-    d2 = torch.empty(nz * ny * nx, dtype=torch.int32, device=im_u8.device)
+    out = torch.empty(nz * ny * nx, dtype=torch.float32 if as_f32 else torch.int32, device=im_u8.device)
+    mx = torch.empty(1, dtype=torch.int32, device=im_u8.device) if want_max else None
     nbytes = ctx.lib.psb200_edt_workspace_bytes(ctx.handle, nz, ny, nx)
     ws = ctx.workspace(nbytes)
-    _lib.check(ctx.lib.psb200_edt_sq_u8(ctx.handle, ptr(im_u8), ptr(d2), nz, ny, nx, ptr(ws),
-                                        ws.numel(), stream_ptr()))
-    return d2
+    _lib.check(ctx.lib.psb200_edt_u8(ctx.handle, ptr(im_u8), ptr(out), 1 if as_f32 else 0, ptr(mx),
+                                     nz, ny, nx, ptr(ws), ws.numel(), stream_ptr()))
+    if want_max:
+        return out, int(mx.cpu().numpy().view(np.uint32)[0])
+    return out, None
+
+
+def edt_sq(ctx, im_u8, shape):
+    """uint8 device volume -> uint32 squared distances (device tensor)."""
+    return edt_run(ctx, im_u8, shape)[0]
 
 
 def max_u32(ctx, d2):

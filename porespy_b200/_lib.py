@@ -61,6 +61,7 @@ SIGNATURES = {
     "psb200_profile_records": (_i32, [_vp, _c.POINTER(_i32), _c.POINTER(_c.c_float), _i32]),
     "psb200_edt_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
     "psb200_edt_sq_u8": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "psb200_edt_u8": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_edt_pass": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_sqrt_f32": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "psb200_max_u32": (_i32, [_vp, _vp, _i64, _vp, _vp]),

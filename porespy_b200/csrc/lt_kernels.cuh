@@ -293,233 +293,13 @@ lt_mark_written_kernel(const double *__restrict__ out, uint8_t *__restrict__ idx
 }
 
 // =========================================================================================
-// Streaming three-kernel form of one radius (used when nx % 16 == 0; the fused lt_xy_kernel
-// above stays as the any-shape path).  Every kernel issues all of its global loads up front
-// (16-byte vectors), so it runs at memory speed instead of at load latency.
-//
-//   lt_x_kernel : class map -> x-distance bytes (GX_* encoding), one warp per line
-//   lt_y_kernel : x-distance tile (+/- W halo rows) -> reach bytes
-//   lt_zsweep_kernel : in-place forward cone sweep over whole z columns, then the backward
-//                 sweep combined with the radius-index write
+// Streaming three-kernel form of one radius (used when nx % 16 == 0 and T <= 32767; the fused
+// lt_xy_kernel above stays as the any-shape path):
+//   xdist_kernel<XD_LT> (xdist_kernels.cuh) : class map -> x-distance bytes min(d, W + 1)
+//   lt_y2_kernel (minplus_kernels.cuh)      : x-distance tile (+/- W halo rows) -> reach bytes
+//   lt_zsweep_kernel (below)                : in-place forward cone sweep over whole z columns,
+//                 then the backward sweep combined with the radius-index write
 // =========================================================================================
-
-// ------------------------------------------------------------------------------ x pass
-// One warp per line; a lane owns 16-voxel chunks (one uint4).  smem per warp: 3 ints per chunk.
-__global__ void __launch_bounds__(256)
-lt_x_kernel(const uint8_t *__restrict__ cls, uint8_t *__restrict__ gx, int64_t nlines, int nx, int k,
-            const int *__restrict__ gate)
-{
-    if (gate && *gate == 0) return;
-    extern __shared__ int ltx_smem[];
-    const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = lane_id();
-    const int nch = nx >> 4;
-    int *words = ltx_smem + (size_t)wid * 3 * nch;   // seed mask | background mask << 16
-    int *lastp = words + nch;                         // position of the last seed at or before chunk end
-    int *firstp = lastp + nch;                        // position of the first seed at or after chunk start
-    const int NONE_L = -100000, NONE_R = 100000;
-
-    for (int64_t line = (int64_t)blockIdx.x * warps + wid; line < nlines; line += (int64_t)gridDim.x * warps) {
-        const uint4 *row = reinterpret_cast<const uint4 *>(cls + line * nx);
-        for (int c = lane; c < nch; c += 32) {
-            const uint4 v = __ldg(row + c);
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-            uint32_t mk = 0, bg = 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t by = byte_of(w4[q], b);
-                    mk |= (by <= (uint32_t)k ? 1u : 0u) << (4 * q + b);
-                    bg |= (by == CLS_BG ? 1u : 0u) << (4 * q + b);
-                }
-            words[c] = (int)(mk | (bg << 16));
-            lastp[c] = mk ? 16 * c + 31 - __clz(mk) : NONE_L;
-            firstp[c] = mk ? 16 * c + __ffs(mk) - 1 : NONE_R;
-        }
-        __syncwarp();
-        int carry = NONE_L;
-        for (int base = 0; base < nch; base += 32) {
-            const int c = base + lane;
-            int v = (c < nch) ? lastp[c] : NONE_L;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int t = __shfl_up_sync(0xFFFFFFFFu, v, off);
-                if (lane >= off) v = max(v, t);
-            }
-            v = max(v, carry);
-            if (c < nch) lastp[c] = v;
-            carry = __shfl_sync(0xFFFFFFFFu, v, 31);
-        }
-        carry = NONE_R;
-        for (int base = ((nch - 1) / 32) * 32; base >= 0; base -= 32) {
-            const int c = base + lane;
-            int v = (c < nch) ? firstp[c] : NONE_R;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int t = __shfl_down_sync(0xFFFFFFFFu, v, off);
-                if (lane + off < 32) v = min(v, t);
-            }
-            v = min(v, carry);
-            if (c < nch) firstp[c] = v;
-            carry = __shfl_sync(0xFFFFFFFFu, v, 0);
-        }
-        __syncwarp();
-        uint4 *orow = reinterpret_cast<uint4 *>(gx + line * nx);
-        for (int c = lane; c < nch; c += 32) {
-            const uint32_t w = (uint32_t)words[c];
-            const uint32_t mk = w & 0xFFFFu, bg = w >> 16;
-            const int Lpos = c > 0 ? lastp[c - 1] : NONE_L;
-            const int Rpos = c + 1 < nch ? firstp[c + 1] : NONE_R;
-            int d[16];
-            int run = min(16 * c - 1 - Lpos, (int)GX_FAR);       // distance of the voxel just left of the chunk
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                run = ((mk >> j) & 1u) ? 0 : min(run + 1, (int)GX_FAR);
-                d[j] = run;
-            }
-            run = min(Rpos - (16 * c + 16), (int)GX_FAR);
-#pragma unroll
-            for (int j = 15; j >= 0; --j) {
-                run = ((mk >> j) & 1u) ? 0 : min(run + 1, (int)GX_FAR);
-                d[j] = min(d[j], run);
-                if ((bg >> j) & 1u) d[j] = GX_BG;
-            }
-            uint4 o;
-            o.x = pack4(d[0], d[1], d[2], d[3]);
-            o.y = pack4(d[4], d[5], d[6], d[7]);
-            o.z = pack4(d[8], d[9], d[10], d[11]);
-            o.w = pack4(d[12], d[13], d[14], d[15]);
-            orow[c] = o;
-        }
-        __syncwarp();
-    }
-}
-
-// ------------------------------------------------------------------------------ y pass
-// grid = (ceil(nx/128), ceil(ny/Ly), nz), block = 256, dyn smem = (Ly+2W)*128 + 4*ceil(rows/32) + 16.
-__device__ __forceinline__ int rowmask_prev(const uint32_t *mask, int pos)
-{   // largest set index <= pos, or -1
-    if (pos < 0) return -1;
-    int w = pos >> 5;
-    uint32_t m = mask[w] & (0xFFFFFFFFu >> (31 - (pos & 31)));
-    while (true) {
-        if (m) return (w << 5) + 31 - __clz(m);
-        if (--w < 0) return -1;
-        m = mask[w];
-    }
-}
-
-__device__ __forceinline__ int rowmask_next(const uint32_t *mask, int pos, int rows)
-{   // smallest set index >= pos, or rows
-    if (pos >= rows) return rows;
-    const int nw = (rows + 31) >> 5;
-    int w = pos >> 5;
-    uint32_t m = mask[w] & (0xFFFFFFFFu << (pos & 31));
-    while (true) {
-        if (m) return (w << 5) + __ffs(m) - 1;
-        if (++w >= nw) return rows;
-        m = mask[w];
-    }
-}
-
-__global__ void __launch_bounds__(256)
-lt_y_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny, int nx, uint32_t T,
-            int W, int Ly, const int *__restrict__ gate)
-{
-    if (gate && *gate == 0) return;
-    extern __shared__ uint32_t lty_smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
-    const int rows = Ly + 2 * W;
-    const int nmw = (rows + 31) >> 5;
-    uint32_t *tile = lty_smem;                       // [rows][32] u32
-    uint32_t *rowmask = lty_smem + (size_t)rows * 32;   // bit r: row r holds a finite x-distance
-    const int x0 = blockIdx.x * LT_XT, y0 = blockIdx.y * Ly;
-    const int64_t zoff = (int64_t)blockIdx.z * ny;
-
-    for (int i = tid; i < nmw; i += blockDim.x) rowmask[i] = 0u;
-    __syncthreads();
-    const uint32_t FAR4 = GX_FAR * 0x01010101u;
-    for (int i0 = 0; i0 < rows * 8; i0 += blockDim.x) {      // uniform trip count (ballot inside)
-        const int i = i0 + tid;
-        const bool valid = i < rows * 8;
-        const int r = i >> 3, ch = i & 7;
-        const int y = y0 - W + r, x = x0 + 16 * ch;
-        uint4 v = make_uint4(FAR4, FAR4, FAR4, FAR4);
-        if (valid && y >= 0 && y < ny && x < nx)
-            v = __ldg(reinterpret_cast<const uint4 *>(gx + (zoff + y) * nx + x));
-        if (valid) reinterpret_cast<uint4 *>(tile)[i] = v;
-        const uint32_t one = 0x01010101u;
-        const bool has = valid && ((v.x | one) & (v.y | one) & (v.z | one) & (v.w | one)) != 0xFFFFFFFFu;
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
-        if (valid && (lane & 7) == 0 && ((bal >> lane) & 0xFFu)) atomicOr(&rowmask[r >> 5], 1u << (r & 31));
-    }
-    __syncthreads();
-    int nflag = 0;
-    for (int i = 0; i < nmw; ++i) nflag += __popc(rowmask[i]);
-    const bool dense = (nflag == rows);
-
-    for (int ry = warp; ry < Ly; ry += 8) {
-        const int y = y0 + ry;
-        if (y >= ny) break;
-        uint32_t outv = 0;
-        if (nflag) {
-            const int r = ry + W;
-            const uint32_t v = tile[r * 32 + lane];
-            uint32_t best[4];
-            bool bg[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t a = byte_of(v, j);
-                bg[j] = (a == GX_BG);
-                best[j] = bg[j] ? 0u : min(T, a * a);
-            }
-            uint32_t bmax = max(max(best[0], best[1]), max(best[2], best[3]));
-            if (dense) {
-                for (int dy = 1; (uint32_t)(dy * dy) < bmax; ++dy) {
-                    const uint32_t up = tile[(r - dy) * 32 + lane];
-                    const uint32_t dn = tile[(r + dy) * 32 + lane];
-                    const uint32_t dy2 = (uint32_t)(dy * dy);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t cu = byte_of(up, j), cd = byte_of(dn, j);
-                        best[j] = min(best[j], min(cu * cu, cd * cd) + dy2);
-                    }
-                    bmax = max(max(best[0], best[1]), max(best[2], best[3]));
-                }
-            } else {
-                uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, bmax);
-                int cu = rowmask_prev(rowmask, r - 1), cd = rowmask_next(rowmask, r + 1, rows);
-                while (true) {
-                    const int du = cu >= 0 ? r - cu : 0x7FFF, dd = cd < rows ? cd - r : 0x7FFF;
-                    const int d = min(du, dd);
-                    if ((uint32_t)(d * d) >= wmax) break;
-                    const uint32_t d2 = (uint32_t)(d * d);
-                    if (du == d) {
-                        const uint32_t t = tile[cu * 32 + lane];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { const uint32_t c = byte_of(t, j); best[j] = min(best[j], c * c + d2); }
-                        cu = rowmask_prev(rowmask, cu - 1);
-                    }
-                    if (dd == d) {
-                        const uint32_t t = tile[cd * 32 + lane];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { const uint32_t c = byte_of(t, j); best[j] = min(best[j], c * c + d2); }
-                        cd = rowmask_next(rowmask, cd + 1, rows);
-                    }
-                    bmax = max(max(best[0], best[1]), max(best[2], best[3]));
-                    wmax = __reduce_max_sync(0xFFFFFFFFu, bmax);
-                }
-            }
-            uint32_t m[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                m[j] = (bg[j] || best[j] >= T) ? 0u : ceil_sqrt_small(T - best[j]);
-            outv = pack4(m[0], m[1], m[2], m[3]);
-        }
-        const int x = x0 + 4 * lane;
-        if (x < nx) *reinterpret_cast<uint32_t *>(reach + (zoff + y) * nx + x) = outv;
-    }
-}
 
 // ------------------------------------------------------------------------------ z sweeps
 // Thread = 4 adjacent columns of the [nz][plane] view.  Forward sweep rewrites reach in place

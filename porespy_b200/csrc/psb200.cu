@@ -11,6 +11,8 @@
 #include "edt_kernels.cuh"
 #include "flood_kernels.cuh"
 #include "lt_kernels.cuh"
+#include "minplus_kernels.cuh"
+#include "xdist_kernels.cuh"
 
 // ------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -43,12 +45,13 @@ static int fail(int code, const char *fmt, ...)
 // launching stream, summed per kernel family by psb200_profile_read().
 enum KernelId {
     K_EDT_X = 0, K_EDT_Y, K_EDT_Z, K_SQRT, K_MAX, K_CLASSIFY, K_LT_XY, K_LT_X, K_LT_Y, K_LT_Z, K_LT_POINT, K_EXPAND,
-    K_MARK_WRITTEN, K_UF_INIT, K_UF_ACTIVATE, K_UF_MARK, K_FLOOD_MISC, K_GEN_X, K_GEN_Y, K_GEN_Z, K_COUNT
+    K_MARK_WRITTEN, K_UF_INIT, K_UF_ACTIVATE, K_UF_MARK, K_FLOOD_MISC, K_GEN_X, K_GEN_Y, K_GEN_Z,
+    K_FH_X, K_FH_Y, K_FH_Z, K_COUNT
 };
 static const char *const kKernelNames[K_COUNT] = {
     "edt_x", "edt_y", "edt_z", "sqrt_f32", "max_u32", "lt_classify", "lt_xy", "lt_x", "lt_y", "lt_z", "lt_point",
     "lt_expand", "lt_mark_written", "uf_init", "uf_activate", "uf_mark", "flood_misc",
-    "generic_x", "generic_y", "generic_z"};
+    "generic_x", "generic_y", "generic_z", "edt_fh_x", "edt_fh_y", "edt_fh_z"};
 
 struct ProfScope {
     psb200_ctx *c;
@@ -88,8 +91,13 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_TRY(cudaFuncSetAttribute(lt_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
-    CUDA_TRY(cudaFuncSetAttribute(lt_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
-    CUDA_TRY(cudaFuncSetAttribute(lt_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(lt_y2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(xdist_kernel<XD_EDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(xdist_kernel<XD_LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_x_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_x_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     *out = c;
@@ -208,13 +216,18 @@ static size_t stack_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny)
 }
 
 // ---------------------------------------------------------------------------------- EDT
+// Fast path: xdist (u16) -> bounded min-plus y pass -> bounded min-plus z pass.
+// Workspace: [u16 x-distances: n][u32 intermediate: n (only when both ny > 1 and nz > 1)].
+// ALGO_GENERIC: the lower-envelope (Felzenszwalb / Meijster) kernels, in place on d2.
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
 extern "C" size_t psb200_edt_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx)
 {
-    (void)nx;
     if (!ctx) return 0;
-    Carver c{nullptr, 0};
-    c.take<char>(stack_bytes(ctx, nz, ny));
-    return c.off + 256;
+    const size_t n = (size_t)nz * ny * nx;
+    size_t fast = align256(n * 2) + align256(n * 4) + 512;
+    size_t fh = stack_bytes(ctx, nz, ny) + 512;
+    return fast > fh ? fast : fh;
 }
 
 template <int SITE_MODE>
@@ -227,7 +240,7 @@ static int launch_x(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2, int64_t nl
     const size_t smem = (size_t)warps * 3 * nwords * 4;
     const int grid = grid_for(nlines, warps, ctx->sm_count, 16);
     {
-        ProfScope ps__(ctx, st, SITE_MODE == 0 ? K_EDT_X : K_GEN_X);
+        ProfScope ps__(ctx, st, SITE_MODE == 0 ? K_FH_X : K_GEN_X);
         edt_x_kernel<SITE_MODE><<<grid, warps * 32, smem, st>>>(in, d2, nlines, nx, k);
     }
     LAUNCH_CHECK(ctx);
@@ -240,7 +253,7 @@ static int launch_col(psb200_ctx *ctx, int axis, const uint32_t *src, Store stor
                       int64_t ny, int64_t nx, void *ws, size_t ws_bytes, cudaStream_t st,
                       int prof_kid = -1)
 {
-    if (prof_kid < 0) prof_kid = axis == 1 ? K_EDT_Y : K_EDT_Z;
+    if (prof_kid < 0) prof_kid = axis == 1 ? K_FH_Y : K_FH_Z;
     const int64_t plane = ny * nx;
     int64_t ncols, inner, outer, stride;
     int n;
@@ -258,6 +271,74 @@ static int launch_col(psb200_ctx *ctx, int axis, const uint32_t *src, Store stor
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
+}
+
+// x-distance pass (xdist_kernel): one warp per line
+template <int MODE>
+static int launch_xdist(psb200_ctx *ctx, const uint8_t *in, void *out, int64_t nlines, int nx, int k, int cap,
+                        const int *gate, cudaStream_t st)
+{
+    const int nch = (nx + 15) / 16;
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * 2 * nch * 4 > 64 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * 2 * nch * 4;
+    const int grid = grid_for(nlines, warps, ctx->sm_count, 32);
+    {
+        ProfScope ps__(ctx, st, MODE == XD_EDT ? K_EDT_X : K_LT_X);
+        xdist_kernel<MODE><<<grid, warps * 32, smem, st>>>(in, out, nlines, nx, k, cap, gate);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+// bounded min-plus pass along y (axis 1) or z (axis 0); out_kind 0: u32 squared, 1: f32 sqrt
+template <typename Src>
+static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src, void *dst, int out_kind,
+                          uint32_t *gmax, int64_t nz, int64_t ny, int64_t nx, cudaStream_t st)
+{
+    const int64_t plane = ny * nx;
+    int n;
+    int64_t rstride, nxc, ostride, nouter;
+    if (axis == 1) { n = (int)ny; rstride = nx; nxc = nx; ostride = plane; nouter = nz; }
+    else { n = (int)nz; rstride = plane; nxc = plane; ostride = 0; nouter = 1; }
+    int L, H;
+    if (n <= 128) { L = n; H = 0; }
+    else { L = 64; H = 32; }
+    const size_t smem = (size_t)(L + 2 * H) * 512;
+    const int vec = (nxc % 4 == 0) && (rstride % 4 == 0) && (ostride % 4 == 0) &&
+                    ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0);
+    const int64_t gx = ((nxc + MP_TX - 1) / MP_TX) * ((n + L - 1) / L);
+    if (gx > 0x7FFFFFFFLL || nouter > 65535)
+        return fail(PSB200_ERR_UNSUPPORTED, "edt pass: volume too large for one launch");
+    dim3 grid((unsigned)gx, (unsigned)nouter);
+    {
+        ProfScope ps__(ctx, st, axis == 1 ? K_EDT_Y : K_EDT_Z);
+        if (out_kind == 0)
+            edt_minplus_kernel<Src, 0><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax);
+        else
+            edt_minplus_kernel<Src, 1><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+static int edt_fast(psb200_ctx *ctx, const uint8_t *in, void *out, int out_kind, uint32_t *gmax,
+                    int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    const size_t n = (size_t)nz * ny * nx;
+    char *base = ws ? (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
+    const size_t need = align256(n * 2) + ((nz > 1) ? align256(n * 4) : 0) + 256;
+    if (!base || ws_bytes < need + (size_t)(base - (char *)ws))
+        return fail(PSB200_ERR_WORKSPACE, "edt needs %zu workspace bytes, got %zu", need + 256, ws_bytes);
+    uint16_t *dx = reinterpret_cast<uint16_t *>(base);
+    uint32_t *mid = reinterpret_cast<uint32_t *>(base + align256(n * 2));
+    if (gmax) CUDA_TRY(cudaMemsetAsync(gmax, 0, sizeof(uint32_t), st));
+    int rc = launch_xdist<XD_EDT>(ctx, in, dx, nz * ny, (int)nx, 0, 0, nullptr, st);
+    if (rc) return rc;
+    if (nz == 1) return launch_minplus<MpSrcU16>(ctx, 1, dx, out, out_kind, gmax, nz, ny, nx, st);
+    rc = launch_minplus<MpSrcU16>(ctx, 1, dx, mid, 0, nullptr, nz, ny, nx, st);
+    if (rc) return rc;
+    return launch_minplus<MpSrcU32>(ctx, 0, mid, out, out_kind, gmax, nz, ny, nx, st);
 }
 
 extern "C" int psb200_edt_pass(psb200_ctx *ctx, int axis, const uint8_t *in, uint32_t *d2,
@@ -286,16 +367,39 @@ extern "C" int psb200_edt_pass(psb200_ctx *ctx, int axis, const uint8_t *in, uin
     return fail(PSB200_ERR_INVALID, "edt_pass: axis must be 0, 1 or 2");
 }
 
+extern "C" int psb200_edt_u8(psb200_ctx *ctx, const uint8_t *in, void *out, int out_kind,
+                             uint32_t *max_out, int64_t nz, int64_t ny, int64_t nx, void *ws,
+                             size_t ws_bytes, psb200_stream stream)
+{
+    if (!ctx || !in || !out) return fail(PSB200_ERR_INVALID, "edt_u8: NULL argument");
+    if (out_kind != 0 && out_kind != 1) return fail(PSB200_ERR_INVALID, "edt_u8: out_kind must be 0 (u32 d2) or 1 (f32)");
+    int rc = check_dims("edt_u8", nz, ny, nx);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->algo == PSB200_ALGO_GENERIC) {
+        // lower-envelope kernels; u32 in place, then the pointwise epilogues
+        uint32_t *d2 = reinterpret_cast<uint32_t *>(out);      // float32 and uint32 have the same size
+        for (int axis = 2; axis >= 0; --axis) {
+            rc = psb200_edt_pass(ctx, axis, in, d2, nz, ny, nx, ws, ws_bytes, stream);
+            if (rc) return rc;
+        }
+        const int64_t n = nz * ny * nx;
+        if (max_out) {
+            rc = psb200_max_u32(ctx, d2, n, max_out, stream);
+            if (rc) return rc;
+        }
+        if (out_kind == 1) return psb200_sqrt_f32(ctx, d2, reinterpret_cast<float *>(out), n, stream);
+        return PSB200_OK;
+    }
+    return edt_fast(ctx, in, out, out_kind, max_out, nz, ny, nx, ws, ws_bytes, st);
+}
+
 extern "C" int psb200_edt_sq_u8(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2, int64_t nz,
                                 int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
                                 psb200_stream stream)
 {
-    if (!ctx || !in || !d2) return fail(PSB200_ERR_INVALID, "edt_sq_u8: NULL argument");
-    for (int axis = 2; axis >= 0; --axis) {
-        int rc = psb200_edt_pass(ctx, axis, in, d2, nz, ny, nx, ws, ws_bytes, stream);
-        if (rc) return rc;
-    }
-    return PSB200_OK;
+    return psb200_edt_u8(ctx, in, d2, 0, nullptr, nz, ny, nx, ws, ws_bytes, stream);
 }
 
 extern "C" int psb200_sqrt_f32(psb200_ctx *ctx, const uint32_t *d2, float *out, int64_t n,
@@ -474,11 +578,11 @@ static int lt_z_impl(psb200_ctx *ctx, const uint8_t *reach, const uint8_t *m_lo,
     return PSB200_OK;
 }
 
-// streaming three-kernel form (nx % 16 == 0): x-distance, y tile scan, in-place z sweeps
-static bool streaming_ok(int64_t ny, int64_t nx, const void *a, const void *b, const void *c)
+// streaming three-kernel form (nx % 16 == 0, T <= 32767): x-distance, y tile scan, in-place z sweeps
+static bool streaming_ok(int64_t ny, int64_t nx, uint32_t T, const void *a, const void *b, const void *c)
 {
     (void)ny;
-    return (nx % 16 == 0) && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15u) == 0);
+    return (nx % 16 == 0) && T <= 32767u && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15u) == 0);
 }
 
 static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t *gx,
@@ -486,31 +590,18 @@ static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_
                              cudaStream_t st)
 {
     const int W = (int)isqrt_u32(T - 1);
-    if (W > LT_MAX_W)
-        return fail(PSB200_ERR_UNSUPPORTED, "lt_xy: threshold %u exceeds the uint8 pipeline (r > 254)", T);
-    {   // x pass
-        const int nch = (int)(nx / 16);
-        int warps = 8;
-        while (warps > 1 && (size_t)warps * 3 * nch * 4 > 64 * 1024) warps >>= 1;
-        const size_t smem = (size_t)warps * 3 * nch * 4;
-        const int grid = grid_for(nz * ny, warps, ctx->sm_count, 32);
-        {
-            ProfScope ps__(ctx, st, K_LT_X);
-            lt_x_kernel<<<grid, warps * 32, smem, st>>>(cls, gx, nz * ny, (int)nx, k, gate);
-        }
-        LAUNCH_CHECK(ctx);
-    }
+    int rc = launch_xdist<XD_LT>(ctx, cls, gx, nz * ny, (int)nx, k, W + 1, gate, st);
+    if (rc) return rc;
     {   // y pass
-        int Ly = W <= 16 ? 128 : 256;
-        if (ny < Ly) Ly = (int)ny;
+        int Ly = ny < 128 ? (int)ny : 128;
         const int rows = Ly + 2 * W;
-        const size_t smem = (size_t)rows * LT_XT + (size_t)((rows + 31) / 32) * 4 + 16;
+        const size_t smem = (size_t)rows * 256 + 16;
         if ((int)smem > ctx->max_smem_optin)
             return fail(PSB200_ERR_UNSUPPORTED, "lt_y: tile needs %zu bytes of shared memory", smem);
-        dim3 grid((unsigned)((nx + LT_XT - 1) / LT_XT), (unsigned)((ny + Ly - 1) / Ly), (unsigned)nz);
+        dim3 grid((unsigned)((nx + MP_TX - 1) / MP_TX), (unsigned)((ny + Ly - 1) / Ly), (unsigned)nz);
         {
             ProfScope ps__(ctx, st, K_LT_Y);
-            lt_y_kernel<<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate);
+            lt_y2_kernel<<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate);
         }
         LAUNCH_CHECK(ctx);
     }
@@ -546,7 +637,7 @@ extern "C" int psb200_lt_xy(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t
     CUDA_TRY(cudaSetDevice(ctx->device));
     uint8_t *gx = ws ? (uint8_t *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
     const size_t need = (size_t)(nz * ny * nx) + 256;
-    if (gx && ws_bytes >= need && streaming_ok(ny, nx, cls, reach, gx))
+    if (gx && ws_bytes >= need && streaming_ok(ny, nx, T, cls, reach, gx))
         return lt_xy_stream_impl(ctx, cls, k, T, gx, reach, nz, ny, nx, nullptr, (cudaStream_t)stream);
     return lt_xy_impl(ctx, cls, k, T, reach, nz, ny, nx, nullptr, (cudaStream_t)stream);
 }
@@ -561,7 +652,7 @@ extern "C" int psb200_lt_z(psb200_ctx *ctx, uint8_t *reach, const uint8_t *m_lo,
     int rc = check_dims("lt_z", nz, ny, nx);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    if (streaming_ok(ny, nx, reach, idx, nullptr) && ((((uintptr_t)m_lo | (uintptr_t)m_hi) & 3u) == 0))
+    if (streaming_ok(ny, nx, 1, reach, idx, nullptr) && ((((uintptr_t)m_lo | (uintptr_t)m_hi) & 3u) == 0))
         return lt_z_stream_impl(ctx, reach, m_lo, nlo, m_hi, nhi, idx, k, T, nz, ny, nx, nullptr,
                                 (cudaStream_t)stream);
     return lt_z_impl(ctx, reach, m_lo, nlo, m_hi, nhi, idx, k, T, nz, ny, nx, nullptr, (cudaStream_t)stream);
@@ -671,7 +762,7 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
             LAUNCH_CHECK(ctx);
             continue;
         }
-        if (streaming_ok(ny, nx, cmap, w.reach, w.gx) && (((uintptr_t)idx & 15u) == 0)) {
+        if (streaming_ok(ny, nx, T, cmap, w.reach, w.gx) && (((uintptr_t)idx & 15u) == 0)) {
             rc = lt_xy_stream_impl(ctx, cmap, k, T, w.gx, w.reach, nz, ny, nx, gate, st);
             if (rc) return rc;
             rc = lt_z_stream_impl(ctx, w.reach, nullptr, 0, nullptr, 0, idx, k, T, nz, ny, nx, gate, st);

@@ -35,14 +35,14 @@ def _run(data, squared):
         raise ValueError("edt supports 1-D, 2-D and 3-D arrays")
     ctx = _lib.context()
     im_u8 = dev.to_device_u8(data, ctx)
-    d2 = dev.edt_sq(ctx, im_u8, shape)
     if squared:
         # squared distances are exact integers < 2^24 for every supported volume of edge
         # <= 2048; returned as float32 like edt.edtsq
+        d2 = dev.edt_sq(ctx, im_u8, shape)
         out = d2.view(torch.int32).to(torch.float32)
         out = torch.where(d2 == -1, torch.full_like(out, float("inf")), out)
     else:
-        out = dev.sqrt_f32(ctx, d2)
+        out = dev.edt_run(ctx, im_u8, shape, as_f32=True)[0]      # sqrt fused into the last pass
     out = out.view(*shape)
     return out.cpu().numpy() if as_numpy else out
 

@@ -81,9 +81,8 @@ def porosimetry(im, sizes: int = 25, inlets=None, access_limited: bool = True,
         return np.zeros(shape)
     ctx = _lib.context()
     im_u8 = dev.to_device_u8(im, ctx)
-    d2 = dev.edt_sq(ctx, im_u8, shape)
+    d2, max_d2 = dev.edt_run(ctx, im_u8, shape, want_max=True)    # max fused into the last pass
     del im_u8
-    max_d2 = dev.max_u32(ctx, d2)
     radii = host.reference_sizes(sizes, max_d2)
 
     inlet_mode, inlets_u8 = _lib.INLETS_NONE, None

@@ -1,0 +1,23 @@
+"""ncu target: one local_thickness(sizes=25) on a device-generated blobs volume (no warm-up,
+no timing -- numbers printed under a profiler are never bench values)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+import porespy_b200 as psb
+
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+mode = sys.argv[2] if len(sys.argv) > 2 else "lt"
+im = bench.device_blobs((size,) * 3, bench.POROSITY, bench.BLOBINESS, 0, torch.device("cuda", 0))
+torch.cuda.synchronize()
+if mode == "lt":
+    out = psb.filters.local_thickness(im, sizes=bench.SIZES)
+elif mode == "poro":
+    out = psb.filters.porosimetry(im, sizes=bench.SIZES)
+elif mode == "edt":
+    out = psb.edt(im)
+torch.cuda.synchronize()
+print("done", tuple(out.shape))
