@@ -69,7 +69,8 @@ const char *psb200_last_error(void);
 int psb200_create(int device, psb200_ctx **ctx);
 int psb200_destroy(psb200_ctx *ctx);
 /* name: "algo" (PSB200_ALGO_*), "profile" (0/1: record a cudaEvent pair around every kernel
- * launch).  Returns PSB200_ERR_INVALID for unknown names. */
+ * launch), "bit_tmax" (thresholds T <= bit_tmax take the bit-parallel dilation kernels, 0 turns
+ * them off; default 200).  Returns PSB200_ERR_INVALID for unknown names. */
 int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t value);
 /* Number of kernel launches issued through this ctx since creation (bench bookkeeping). */
 int64_t psb200_launch_count(const psb200_ctx *ctx);

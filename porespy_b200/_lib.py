@@ -120,6 +120,10 @@ class Context:
     def set_algo(self, algo):
         check(self.lib.psb200_set_option(self.handle, b"algo", int(algo)))
 
+    def set_bit_tmax(self, tmax):
+        """Thresholds T <= tmax run the bit-parallel dilation kernels (0 = never)."""
+        check(self.lib.psb200_set_option(self.handle, b"bit_tmax", int(tmax)))
+
     def set_profile(self, on):
         check(self.lib.psb200_set_option(self.handle, b"profile", 1 if on else 0))
 

@@ -24,6 +24,7 @@ struct psb200_ctx {
     int max_smem_optin;
     int algo;
     int profile;
+    int bit_tmax;      // thresholds T <= bit_tmax use the bit-parallel dilation (0: never)
     long long launches;
     std::vector<ProfRec> prof;
 };

@@ -13,6 +13,7 @@
 #include "lt_kernels.cuh"
 #include "minplus_kernels.cuh"
 #include "xdist_kernels.cuh"
+#include "bitball_kernels.cuh"
 
 // ------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -46,12 +47,12 @@ static int fail(int code, const char *fmt, ...)
 enum KernelId {
     K_EDT_X = 0, K_EDT_Y, K_EDT_Z, K_SQRT, K_MAX, K_CLASSIFY, K_LT_XY, K_LT_X, K_LT_Y, K_LT_Z, K_LT_POINT, K_EXPAND,
     K_MARK_WRITTEN, K_UF_INIT, K_UF_ACTIVATE, K_UF_MARK, K_FLOOD_MISC, K_GEN_X, K_GEN_Y, K_GEN_Z,
-    K_FH_X, K_FH_Y, K_FH_Z, K_COUNT
+    K_FH_X, K_FH_Y, K_FH_Z, K_LT_PACK, K_LT_BITBALL, K_LT_WMASK, K_COUNT
 };
 static const char *const kKernelNames[K_COUNT] = {
     "edt_x", "edt_y", "edt_z", "sqrt_f32", "max_u32", "lt_classify", "lt_xy", "lt_x", "lt_y", "lt_z", "lt_point",
     "lt_expand", "lt_mark_written", "uf_init", "uf_activate", "uf_mark", "flood_misc",
-    "generic_x", "generic_y", "generic_z", "edt_fh_x", "edt_fh_y", "edt_fh_z"};
+    "generic_x", "generic_y", "generic_z", "edt_fh_x", "edt_fh_y", "edt_fh_z", "lt_pack", "lt_bitball", "lt_wmask"};
 
 struct ProfScope {
     psb200_ctx *c;
@@ -88,6 +89,7 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->algo = PSB200_ALGO_FAST;
     c->launches = 0;
     c->profile = 0;
+    c->bit_tmax = 200;
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_TRY(cudaFuncSetAttribute(lt_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
@@ -117,6 +119,11 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
         if (value != PSB200_ALGO_FAST && value != PSB200_ALGO_GENERIC)
             return fail(PSB200_ERR_INVALID, "set_option: algo must be 0 (fast) or 1 (generic)");
         ctx->algo = (int)value;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "bit_tmax")) {
+        if (value < 0 || value > 400) return fail(PSB200_ERR_INVALID, "set_option: bit_tmax must be in [0,400]");
+        ctx->bit_tmax = (int)value;
         return PSB200_OK;
     }
     if (!strcmp(name, "profile")) {
@@ -456,6 +463,7 @@ static int check_thresholds(const char *who, const uint32_t *T, int nT)
 
 struct LtWorkspace {
     uint8_t *cls, *rcls, *reach, *gx;
+    uint32_t *seedbits, *written;   // bit path: one bit per voxel
     uint32_t *parent;
     int *gate;
     uint32_t *gen_d2;     // generic algo: full u32 distance map of ~seeds
@@ -474,6 +482,8 @@ static LtWorkspace carve_lt(const psb200_ctx *ctx, char *base, int64_t nz, int64
     w.cls = c.take<uint8_t>(n + 16);
     w.reach = c.take<uint8_t>(n + 16);
     w.gx = c.take<uint8_t>(n + 16);
+    w.seedbits = c.take<uint32_t>(n / 32 + 4);
+    w.written = c.take<uint32_t>(n / 32 + 4);
     if (inlet_mode != PSB200_INLETS_NONE) {
         w.rcls = c.take<uint8_t>(n + 16);
         w.parent = c.take<uint32_t>(n + 1);
@@ -676,6 +686,55 @@ static int uf_step(psb200_ctx *ctx, LtWorkspace &w, const InletSpec &inl, int kl
     return PSB200_OK;
 }
 
+
+// (dy,dz) offsets of the digital ball {o : |o|^2 < T}, grouped by x-allowance (bitball_kernels.cuh)
+static bool build_ball_pairs(uint32_t T, int64_t ny, int64_t nw, BallPairs &bp)
+{
+    const int W = (int)isqrt_u32(T - 1);
+    if (W > 31) return false;
+    bp.W = W;
+    int cnt = 0;
+    for (int a = W; a >= 0; --a) {
+        for (int dz = -W; dz <= W; ++dz)
+            for (int dy = -W; dy <= W; ++dy) {
+                const int64_t rem = (int64_t)T - 1 - (int64_t)dy * dy - (int64_t)dz * dz;
+                if (rem < 0) continue;
+                if ((int)isqrt_u32((uint32_t)rem) != a) continue;
+                if (cnt >= BB_MAX_PAIRS) return false;
+                bp.e[cnt].x = (int)((dz * ny + dy) * nw);
+                bp.e[cnt].y = (int)(((uint32_t)dy & 0xFFFFu) | ((uint32_t)dz << 16));
+                ++cnt;
+            }
+        bp.ring_end[a] = (unsigned short)cnt;
+    }
+    bp.ring_end[W + 1] = 0;
+    return true;
+}
+
+static int lt_bit_step(psb200_ctx *ctx, LtWorkspace &w, const uint8_t *cmap, uint8_t *idx, int k, uint32_t T,
+                       int64_t nz, int64_t ny, int64_t nx, const int *gate, cudaStream_t st)
+{
+    static thread_local BallPairs bp;
+    memset(&bp, 0, sizeof(int) + sizeof(bp.ring_end));
+    if (!build_ball_pairs(T, ny, nx / 32, bp)) return fail(PSB200_ERR_UNSUPPORTED, "bit path: threshold %u too large", T);
+    const int64_t nwords = nz * ny * nx / 32;
+    {
+        ProfScope ps__(ctx, st, K_LT_PACK);
+        lt_pack_kernel<<<grid_for(nwords, 256, ctx->sm_count, 16), 256, 0, st>>>(cmap, w.seedbits, nwords, k, gate);
+    }
+    LAUNCH_CHECK(ctx);
+    const int nw = (int)(nx / 32);
+    const int seg = nw <= 32 ? 32 : 30;
+    dim3 grid((unsigned)((nw + seg - 1) / seg), (unsigned)((ny + BB_TY - 1) / BB_TY), (unsigned)((nz + BB_TZ - 1) / BB_TZ));
+    {
+        ProfScope ps__(ctx, st, K_LT_BITBALL);
+        lt_bitball_kernel<<<grid, 1024, 0, st>>>(w.seedbits, w.written, idx, (int)nz, (int)ny, nw, seg, bp,
+                                                (uint32_t)(k + 1), gate);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
 extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, const uint32_t *T_host,
                                           int nT, uint8_t *idx, const uint8_t *inlets, int inlet_mode,
                                           int ndim, int64_t nz, int64_t ny, int64_t nx, int flags,
@@ -725,11 +784,33 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
     }
     const uint8_t *cmap = al ? w.rcls : w.cls;
     const int *gate = al ? w.gate : nullptr;
+    const bool bit_ok = ctx->algo == PSB200_ALGO_FAST && ctx->bit_tmax > 0 && (nx % 32 == 0) && nz <= 65535 && n < (1LL << 35) &&
+                        ((((uintptr_t)idx | (uintptr_t)cmap) & 15u) == 0);
+    bool wmask_ready = false;
     for (int k = 0; k < nT; ++k) {
         const uint32_t T = T_host[k];
         if (al) {
             rc = uf_step(ctx, w, inl, k - 1, k, 6, nz, ny, nx, st);
             if (rc) return rc;
+        }
+        if (bit_ok && T <= (uint32_t)ctx->bit_tmax) {
+            // small radii: bit-parallel ball dilation (thresholds descend: every later radius too)
+            if (!wmask_ready) {
+                const int64_t nwords = n / 32;
+                if (k == 0 && !(flags & PSB200_FLAG_IDX_PREINIT))
+                    CUDA_TRY(cudaMemsetAsync(w.written, 0, (size_t)nwords * 4, st));
+                else {
+                    {
+                        ProfScope ps__(ctx, st, K_LT_WMASK);
+                        lt_wmask_kernel<<<grid_for(nwords, 256, ctx->sm_count, 16), 256, 0, st>>>(idx, w.written, nwords);
+                    }
+                    LAUNCH_CHECK(ctx);
+                }
+                wmask_ready = true;
+            }
+            rc = lt_bit_step(ctx, w, cmap, idx, k, T, nz, ny, nx, gate, st);
+            if (rc) return rc;
+            continue;
         }
         if (ctx->algo == PSB200_ALGO_GENERIC) {
             // reference-shaped path: full EDT of ~seeds, then fill <=> d2' < T  (F:1191)

@@ -10,6 +10,8 @@ size = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 dev = torch.device("cuda", 0)
 im = bench.device_blobs((size,) * 3, 0.6, 2, 0, dev)
 ctx = _lib.context(0)
+if os.environ.get("BIT_TMAX"):
+    ctx.set_bit_tmax(int(os.environ["BIT_TMAX"]))
 for _ in range(2):
     psb.filters.local_thickness(im, sizes=25)
 torch.cuda.synchronize()

@@ -32,8 +32,12 @@ def assert_same(got, want, what=""):
 
 
 def set_algo(psb, name):
+    """fast: default (bit-parallel kernels for T <= 200, byte pipeline above); nobit: byte pipeline
+    only; allbit: bit-parallel kernels up to T = 400; generic: full lower-envelope EDT per radius."""
     from porespy_b200 import _lib
-    _lib.context().set_algo(_lib.ALGO_GENERIC if name == "generic" else _lib.ALGO_FAST)
+    ctx = _lib.context()
+    ctx.set_algo(_lib.ALGO_GENERIC if name == "generic" else _lib.ALGO_FAST)
+    ctx.set_bit_tmax({"nobit": 0, "allbit": 400}.get(name, 200))
 
 
 def rand_image(shape, p, seed):
@@ -104,10 +108,13 @@ LT_CASES = [((40, 36, 44), 12, 0.6), ((48, 52), 9, 0.6), ((30, 30, 30), [5, 3.5,
             ((150, 3, 40), 6, 0.8), ((64, 200), 25, 0.75), ((257,), 5, 0.9),
             # nx % 16 == 0: the streaming three-kernel path
             ((45, 70, 64), 25, 0.6), ((130, 140, 160), 25, 0.65), ((300, 256), 25, 0.7),
-            ((300, 1, 32), 8, 0.8), ((20, 300, 16), 12, 0.7), ((256,), 6, 0.9), ((9, 520, 144), 30, 0.8)]
+            ((300, 1, 32), 8, 0.8), ((20, 300, 16), 12, 0.7), ((256,), 6, 0.9), ((9, 520, 144), 30, 0.8),
+            # nx % 32 == 0: bit-parallel kernels (incl. rows longer than 1024 voxels: 30-word segments)
+            ((40, 50, 96), 20, 0.6), ((3, 40, 1120), 14, 0.7), ((5, 4, 2048), [9, 4, 2.5, 1], 0.8),
+            ((70, 2080), 16, 0.7)]
 
 
-@pytest.mark.parametrize("algo", ["fast", "generic"])
+@pytest.mark.parametrize("algo", ["fast", "nobit", "allbit", "generic"])
 @pytest.mark.parametrize("shape,sizes,por", LT_CASES)
 def test_local_thickness_vs_oracle(psb, algo, shape, sizes, por):
     set_algo(psb, algo)
@@ -211,8 +218,18 @@ def test_porosimetry_goldens(psb, golden, algo):
 
 
 @pytest.mark.parametrize("shape,por", [((44, 40, 36), 0.55), ((90, 110), 0.6), ((31, 64, 129), 0.5),
-                                       ((44, 40, 48), 0.55), ((90, 112), 0.6), ((131, 64, 128), 0.5)])
-def test_porosimetry_vs_oracle(psb, shape, por):
+                                       ((44, 40, 48), 0.55), ((90, 112), 0.6), ((131, 64, 128), 0.5),
+                                       ((36, 44, 64), 0.6), ((90, 96), 0.6)])
+@pytest.mark.parametrize("algo", ["fast", "nobit"])
+def test_porosimetry_vs_oracle(psb, algo, shape, por):
+    set_algo(psb, algo)
+    try:
+        _porosimetry_vs_oracle(psb, shape, por)
+    finally:
+        set_algo(psb, "fast")
+
+
+def _porosimetry_vs_oracle(psb, shape, por):
     im = oc.blobs(list(shape), porosity=por, blobiness=1.5, seed=11)
     assert_same(psb.filters.porosimetry(im, sizes=10), oc.porosimetry(im, sizes=10, mode="dt"), "faces")
     inlets = np.zeros(shape, dtype=int)
