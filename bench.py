@@ -56,7 +56,7 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------ inputs
-def device_blobs(shape, porosity, blobiness, seed, device):
+def device_blobs(shape, porosity, blobiness, seed, device, sigma_shape=None):
     """Device-side look-alike of ps.generators.blobs (generators/_imgen.py:1023-1051): uniform
     noise -> separable gaussian blur (sigma = mean(shape)/(40*blobiness), reflect borders) ->
     erfc uniformisation -> `< porosity`.  float32 and a different RNG, so not bit-equal to the
@@ -66,7 +66,7 @@ def device_blobs(shape, porosity, blobiness, seed, device):
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     f = torch.rand(tuple(shape), generator=g, device=device, dtype=torch.float32)
-    sigma = float(np.mean(shape)) / (40.0 * blobiness)
+    sigma = float(np.mean(sigma_shape if sigma_shape is not None else shape)) / (40.0 * blobiness)
     rad = int(4.0 * sigma + 0.5)
     x = torch.arange(-rad, rad + 1, device=device, dtype=torch.float32)
     w = torch.exp(-0.5 * (x / sigma) ** 2)
@@ -226,7 +226,9 @@ def run_ours(args):
     else:
         from porespy_b200 import sharded
         job = sharded.ShardedVolume(shape, ctx)
-        im = device_blobs(job.local_shape_with_seed_halo(), POROSITY, BLOBINESS, seed=rank, device=device)
+        # every rank generates its own slab (independent noise per slab: it is only an input)
+        im = device_blobs(job.local_shape, POROSITY, BLOBINESS, seed=rank, device=device,
+                          sigma_shape=shape)
 
         def step():
             return job.local_thickness(im, sizes=SIZES)

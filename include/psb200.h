@@ -109,6 +109,20 @@ int psb200_edt_pass(psb200_ctx *ctx, int axis, const uint8_t *in, uint32_t *d2,
                     int64_t nz, int64_t ny, int64_t nx,
                     void *ws, size_t ws_bytes, psb200_stream stream);
 
+/* The same transform for a volume sharded into z-slabs over several GPUs.
+ * psb200_edt_xy_u8: x and y passes of the local slab [nz][ny][nx] -> 2-D squared distances.
+ *   ysplit = 0: h_out is [nz][ny][nx].  ysplit > 0: h_out is written in the send layout of the
+ *   slab->pencil all-to-all, [dest d][nz][rows of d][nx] with dest d owning rows
+ *   [d*ysplit, min(ny,(d+1)*ysplit)) -- the pack is fused into the store.
+ * psb200_edt_z_u32: z pass on a pencil [nz][ny_local][nx] (all planes, a range of rows);
+ *   out_kind / max_out as in psb200_edt_u8.  out may not alias h. */
+int psb200_edt_xy_u8(psb200_ctx *ctx, const uint8_t *in, uint32_t *h_out,
+                     int64_t nz, int64_t ny, int64_t nx, int64_t ysplit,
+                     void *ws, size_t ws_bytes, psb200_stream stream);
+int psb200_edt_z_u32(psb200_ctx *ctx, const uint32_t *h, void *out, int out_kind,
+                     uint32_t *max_out, int64_t nz, int64_t ny, int64_t nx,
+                     psb200_stream stream);
+
 /* out[i] = float32(sqrt(d2[i])) (IEEE, correctly rounded == np.sqrt(float32));
  * PSB200_INF_U32 -> +inf.  This is the float32 array edt.edt returns. */
 int psb200_sqrt_f32(psb200_ctx *ctx, const uint32_t *d2, float *out, int64_t n,
@@ -148,6 +162,21 @@ int psb200_lt_xy(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t
 int psb200_lt_z(psb200_ctx *ctx, uint8_t *reach, const uint8_t *m_lo, int nlo,
                 const uint8_t *m_hi, int nhi, uint8_t *idx, int k, uint32_t T,
                 int64_t nz, int64_t ny, int64_t nx, psb200_stream stream);
+
+/* Bit-parallel form of the same step for small radii (nx % 32 == 0; buffers 16-byte aligned):
+ *   psb200_lt_pack    : bits[v/32] bit v%32 = (cls[v] <= k)                 (seeds, F:1180)
+ *   psb200_lt_wmask   : written[v/32] bit   = (idx[v] != 0)
+ *   psb200_lt_bitball : fill = dilation of the seed bits by {o : |o|^2 < T} (F:1191 == F:1207);
+ *                       idx[v] = k+1 where fill and not yet written (F:1192); written |= fill.
+ * seedbits holds nz_src planes; output plane z reads seed plane z + z_off, so a z-slab shard
+ * puts the W = ceil(sqrt(T))-1 halo planes of its neighbours in front of / behind its own. */
+int psb200_lt_pack(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t *bits,
+                   int64_t nz, int64_t ny, int64_t nx, psb200_stream stream);
+int psb200_lt_wmask(psb200_ctx *ctx, const uint8_t *idx, uint32_t *written,
+                    int64_t nz, int64_t ny, int64_t nx, psb200_stream stream);
+int psb200_lt_bitball(psb200_ctx *ctx, const uint32_t *seedbits, int64_t nz_src, int64_t z_off,
+                      uint32_t *written, uint8_t *idx, int k, uint32_t T,
+                      int64_t nz, int64_t ny, int64_t nx, psb200_stream stream);
 
 /* out[i] = lut_host[idx[i]] as float64 (np.zeros(shape) + radii, F:1178, F:1192, F:1212).
  * lut_host has nlut entries (entry 0 must be 0.0).  With PSB200_FLAG_EXPAND_MERGE only

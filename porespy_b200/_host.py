@@ -18,6 +18,12 @@ def shape3(shape):
     raise ValueError(f"only 1-D, 2-D and 3-D images are supported, got shape {shape}")
 
 
+def isqrt(v):
+    """floor(sqrt(v)) for a non-negative integer (reach of a ball: W = isqrt(T - 1))."""
+    import math
+    return math.isqrt(int(v))
+
+
 def dt_max_f32(max_d2):
     """np.amax(edt(im)) as the float32 scalar the reference sees (F:1132)."""
     if max_d2 == INF_U32:

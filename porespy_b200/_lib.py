@@ -62,6 +62,8 @@ SIGNATURES = {
     "psb200_edt_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
     "psb200_edt_sq_u8": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_edt_u8": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "psb200_edt_xy_u8": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "psb200_edt_z_u32": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i64, _vp]),
     "psb200_edt_pass": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_sqrt_f32": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "psb200_max_u32": (_i32, [_vp, _vp, _i64, _vp, _vp]),
@@ -71,6 +73,9 @@ SIGNATURES = {
     "psb200_lt_classify": (_i32, [_vp, _vp, _c.POINTER(_u32), _i32, _vp, _i64, _vp]),
     "psb200_lt_xy": (_i32, [_vp, _vp, _i32, _u32, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_lt_z": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _u32, _i64, _i64, _i64, _vp]),
+    "psb200_lt_pack": (_i32, [_vp, _vp, _i32, _vp, _i64, _i64, _i64, _vp]),
+    "psb200_lt_wmask": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "psb200_lt_bitball": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _u32, _i64, _i64, _i64, _vp]),
     "psb200_expand_idx_f64": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _i32, _vp]),
     "psb200_mark_written": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "psb200_flood_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),

@@ -68,13 +68,16 @@ lt_wmask_kernel(const uint8_t *__restrict__ idx, uint32_t *__restrict__ written,
 }
 
 // ------------------------------------------------------------------------------ dilation
-// seeds / written: [nz][ny][nw] words (nw = nx / 32).  idx: [nz][ny][nx] bytes.
+// seeds: [nz_src][ny][nw] words (nw = nx / 32); output plane z reads seed plane z + z_off, so a
+// z-slab shard passes its slab with the neighbours' halo planes in front / behind (single GPU:
+// nz_src = nz, z_off = 0).  written: [nz][ny][nw].  idx: [nz][ny][nx] bytes.
 // grid = (nseg, ceil(ny / 8), ceil(nz / 4)), block = 1024 (8 x 4 rows: the source rows of a
 // block, (8 + 2W) x (4 + 2W) x 128 bytes, stay in L1).  seg_words = 32 (nw <= 32) or 30.
 __global__ void __launch_bounds__(1024)
 lt_bitball_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ written,
                   uint8_t *__restrict__ idx, int nz, int ny, int nw, int seg_words,
-                  const __grid_constant__ BallPairs bp, uint32_t val, const int *__restrict__ gate)
+                  const __grid_constant__ BallPairs bp, uint32_t val, const int *__restrict__ gate,
+                  int nz_src, int z_off)
 {
     if (gate && *gate == 0) return;
     const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -85,10 +88,11 @@ lt_bitball_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ wri
     const int w = blockIdx.x * seg_words + lane - halo;
     const bool inrow = w >= 0 && w < nw;
     const uint32_t inmask = inrow ? 0xFFFFFFFFu : 0u;
-    const uint32_t *base = seeds + ((int64_t)z * ny + y) * nw + (inrow ? w : 0);
+    const int zs = z + z_off;             // plane of this row inside the seed buffer (z halo planes first)
+    const uint32_t *base = seeds + ((int64_t)zs * ny + y) * nw + (inrow ? w : 0);
     asm volatile("" : "+l"(base));        // keep it one pointer: base + offset is then a single IMAD.WIDE
     const int W = bp.W;
-    const bool interior = y - W >= 0 && y + W < ny && z - W >= 0 && z + W < nz;
+    const bool interior = y - W >= 0 && y + W < ny && zs - W >= 0 && zs + W < nz_src;
 
     uint32_t A = 0;
     int p = 0;
@@ -110,8 +114,8 @@ lt_bitball_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ wri
         } else {
             for (; p < pend; ++p) {
                 const int2 e = bp.e[p];
-                const int yy = y + (int)(short)(e.y & 0xFFFF), zz = z + (e.y >> 16);
-                if ((unsigned)yy < (unsigned)ny && (unsigned)zz < (unsigned)nz) A |= __ldg(base + e.x) & inmask;
+                const int yy = y + (int)(short)(e.y & 0xFFFF), zz = zs + (e.y >> 16);
+                if ((unsigned)yy < (unsigned)ny && (unsigned)zz < (unsigned)nz_src) A |= __ldg(base + e.x) & inmask;
             }
         }
     }

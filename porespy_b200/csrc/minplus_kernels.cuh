@@ -62,13 +62,15 @@ __device__ __forceinline__ uint4 mp_load_row(const typename Src::T *row, int x, 
 // contiguous elements.  Outer slices (blockIdx.y): `ostride` elements apart.
 //   y pass: n = ny, rstride = nx,    nxc = nx,    outer = nz (ostride = ny*nx)
 //   z pass: n = nz, rstride = ny*nx, nxc = ny*nx, outer = 1
+// split > 0 (y pass of a z-slab shard only): rows are scattered into the send layout of the
+// slab -> pencil all-to-all, so no separate pack pass is needed.
 // grid.x = ceil(nxc/128) * ceil(n/L)  (row tiles fastest: neighbours share halo rows in L2).
 // OUT 0: uint32 squared distance (PSB_INF when infinite); OUT 1: float32 sqrt (edt.edt's result).
 template <typename Src, int OUT>
 __global__ void __launch_bounds__(MP_WARPS * 32)
 edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ dst, int n,
                    int64_t rstride, int64_t nxc, int64_t ostride, int L, int H, int vec,
-                   uint32_t *__restrict__ gmax)
+                   uint32_t *__restrict__ gmax, int split)
 {
     extern __shared__ uint4 mp_tile[];                     // [L + 2H][32]
     const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -127,7 +129,14 @@ edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ d
             if (o[j] >= MP_INF) o[j] = PSB_INF;
             if (xl + j < valid) lmax = max(lmax, o[j]);
         }
-        const int64_t oi = (int64_t)blockIdx.y * ostride + x0 + (int64_t)gr * rstride + xl;
+        int64_t oi = (int64_t)blockIdx.y * ostride + x0 + (int64_t)gr * rstride + xl;
+        if (split > 0) {
+            // y pass of a z-slab: store in all-to-all send layout [dest d][z][y - d*split][x]
+            // (dest d owns rows [d*split, min(n, (d+1)*split)) of the pencil decomposition)
+            const int d = gr / split, yy = gr - d * split;
+            const int nyd = min(split, n - d * split);
+            oi = ((int64_t)d * split * gridDim.y + (int64_t)blockIdx.y * nyd + yy) * rstride + x0 + xl;
+        }
         if (OUT == 0) {
             uint32_t *orow = reinterpret_cast<uint32_t *>(dst) + oi;
             if (vec && xl + 3 < valid) *reinterpret_cast<uint4 *>(orow) = make_uint4(o[0], o[1], o[2], o[3]);

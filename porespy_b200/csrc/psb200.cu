@@ -301,7 +301,7 @@ static int launch_xdist(psb200_ctx *ctx, const uint8_t *in, void *out, int64_t n
 // bounded min-plus pass along y (axis 1) or z (axis 0); out_kind 0: u32 squared, 1: f32 sqrt
 template <typename Src>
 static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src, void *dst, int out_kind,
-                          uint32_t *gmax, int64_t nz, int64_t ny, int64_t nx, cudaStream_t st)
+                          uint32_t *gmax, int64_t nz, int64_t ny, int64_t nx, cudaStream_t st, int split = 0)
 {
     const int64_t plane = ny * nx;
     int n;
@@ -321,9 +321,9 @@ static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src,
     {
         ProfScope ps__(ctx, st, axis == 1 ? K_EDT_Y : K_EDT_Z);
         if (out_kind == 0)
-            edt_minplus_kernel<Src, 0><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax);
+            edt_minplus_kernel<Src, 0><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax, split);
         else
-            edt_minplus_kernel<Src, 1><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax);
+            edt_minplus_kernel<Src, 1><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax, split);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
@@ -407,6 +407,41 @@ extern "C" int psb200_edt_sq_u8(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2
                                 psb200_stream stream)
 {
     return psb200_edt_u8(ctx, in, d2, 0, nullptr, nz, ny, nx, ws, ws_bytes, stream);
+}
+
+// ---- z-slab sharded EDT: x and y passes on the local slab, z pass on the pencil
+extern "C" int psb200_edt_xy_u8(psb200_ctx *ctx, const uint8_t *in, uint32_t *h_out, int64_t nz,
+                                int64_t ny, int64_t nx, int64_t ysplit, void *ws, size_t ws_bytes,
+                                psb200_stream stream)
+{
+    if (!ctx || !in || !h_out) return fail(PSB200_ERR_INVALID, "edt_xy_u8: NULL argument");
+    int rc = check_dims("edt_xy_u8", nz, ny, nx);
+    if (rc) return rc;
+    if (ysplit < 0 || ysplit > ny) return fail(PSB200_ERR_INVALID, "edt_xy_u8: ysplit outside [0, ny]");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)nz * ny * nx;
+    char *base = ws ? (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
+    if (!base || ws_bytes < align256(n * 2) + 512)
+        return fail(PSB200_ERR_WORKSPACE, "edt_xy_u8 needs %zu workspace bytes, got %zu", align256(n * 2) + 512, ws_bytes);
+    uint16_t *dx = reinterpret_cast<uint16_t *>(base);
+    rc = launch_xdist<XD_EDT>(ctx, in, dx, nz * ny, (int)nx, 0, 0, nullptr, st);
+    if (rc) return rc;
+    return launch_minplus<MpSrcU16>(ctx, 1, dx, h_out, 0, nullptr, nz, ny, nx, st, (int)ysplit);
+}
+
+extern "C" int psb200_edt_z_u32(psb200_ctx *ctx, const uint32_t *h, void *out, int out_kind,
+                                uint32_t *max_out, int64_t nz, int64_t ny, int64_t nx,
+                                psb200_stream stream)
+{
+    if (!ctx || !h || !out || h == out) return fail(PSB200_ERR_INVALID, "edt_z_u32: bad argument");
+    if (out_kind != 0 && out_kind != 1) return fail(PSB200_ERR_INVALID, "edt_z_u32: out_kind must be 0 or 1");
+    int rc = check_dims("edt_z_u32", nz, ny, nx);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (max_out) CUDA_TRY(cudaMemsetAsync(max_out, 0, sizeof(uint32_t), st));
+    return launch_minplus<MpSrcU32>(ctx, 0, h, out, out_kind, max_out, nz, ny, nx, st);
 }
 
 extern "C" int psb200_sqrt_f32(psb200_ctx *ctx, const uint32_t *d2, float *out, int64_t n,
@@ -711,28 +746,97 @@ static bool build_ball_pairs(uint32_t T, int64_t ny, int64_t nw, BallPairs &bp)
     return true;
 }
 
-static int lt_bit_step(psb200_ctx *ctx, LtWorkspace &w, const uint8_t *cmap, uint8_t *idx, int k, uint32_t T,
-                       int64_t nz, int64_t ny, int64_t nx, const int *gate, cudaStream_t st)
+static int lt_pack_impl(psb200_ctx *ctx, const uint8_t *cmap, int k, uint32_t *bits, int64_t nwords,
+                        const int *gate, cudaStream_t st)
+{
+    {
+        ProfScope ps__(ctx, st, K_LT_PACK);
+        lt_pack_kernel<<<grid_for(nwords, 256, ctx->sm_count, 16), 256, 0, st>>>(cmap, bits, nwords, k, gate);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+static int lt_bitball_impl(psb200_ctx *ctx, const uint32_t *seedbits, int64_t nz_src, int64_t z_off,
+                           uint32_t *written, uint8_t *idx, int k, uint32_t T, int64_t nz, int64_t ny,
+                           int64_t nx, const int *gate, cudaStream_t st)
 {
     static thread_local BallPairs bp;
     memset(&bp, 0, sizeof(int) + sizeof(bp.ring_end));
     if (!build_ball_pairs(T, ny, nx / 32, bp)) return fail(PSB200_ERR_UNSUPPORTED, "bit path: threshold %u too large", T);
-    const int64_t nwords = nz * ny * nx / 32;
-    {
-        ProfScope ps__(ctx, st, K_LT_PACK);
-        lt_pack_kernel<<<grid_for(nwords, 256, ctx->sm_count, 16), 256, 0, st>>>(cmap, w.seedbits, nwords, k, gate);
-    }
-    LAUNCH_CHECK(ctx);
     const int nw = (int)(nx / 32);
     const int seg = nw <= 32 ? 32 : 30;
     dim3 grid((unsigned)((nw + seg - 1) / seg), (unsigned)((ny + BB_TY - 1) / BB_TY), (unsigned)((nz + BB_TZ - 1) / BB_TZ));
     {
         ProfScope ps__(ctx, st, K_LT_BITBALL);
-        lt_bitball_kernel<<<grid, 1024, 0, st>>>(w.seedbits, w.written, idx, (int)nz, (int)ny, nw, seg, bp,
-                                                (uint32_t)(k + 1), gate);
+        lt_bitball_kernel<<<grid, 1024, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, nw, seg, bp,
+                                                 (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
+}
+
+static int lt_wmask_impl(psb200_ctx *ctx, const uint8_t *idx, uint32_t *written, int64_t nwords, cudaStream_t st)
+{
+    {
+        ProfScope ps__(ctx, st, K_LT_WMASK);
+        lt_wmask_kernel<<<grid_for(nwords, 256, ctx->sm_count, 16), 256, 0, st>>>(idx, written, nwords);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+static int lt_bit_step(psb200_ctx *ctx, LtWorkspace &w, const uint8_t *cmap, uint8_t *idx, int k, uint32_t T,
+                       int64_t nz, int64_t ny, int64_t nx, const int *gate, cudaStream_t st)
+{
+    int rc = lt_pack_impl(ctx, cmap, k, w.seedbits, nz * ny * nx / 32, gate, st);
+    if (rc) return rc;
+    return lt_bitball_impl(ctx, w.seedbits, nz, 0, w.written, idx, k, T, nz, ny, nx, gate, st);
+}
+
+// step-level entry points of the bit path (z-slab shards exchange seed-bit halo planes between them)
+static int bit_shape_ok(const char *who, int64_t nx, const void *a, const void *b)
+{
+    if (nx % 32 != 0) return fail(PSB200_ERR_UNSUPPORTED, "%s: the bit path needs nx %% 32 == 0", who);
+    if ((((uintptr_t)a | (uintptr_t)b) & 15u) != 0) return fail(PSB200_ERR_INVALID, "%s: buffers must be 16-byte aligned", who);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_lt_pack(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t *bits, int64_t nz,
+                              int64_t ny, int64_t nx, psb200_stream stream)
+{
+    if (!ctx || !cls || !bits || k < 0 || k >= PSB200_MAX_THRESHOLDS) return fail(PSB200_ERR_INVALID, "lt_pack: bad argument");
+    int rc = check_dims("lt_pack", nz, ny, nx);
+    if (!rc) rc = bit_shape_ok("lt_pack", nx, cls, bits);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return lt_pack_impl(ctx, cls, k, bits, nz * ny * nx / 32, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int psb200_lt_wmask(psb200_ctx *ctx, const uint8_t *idx, uint32_t *written, int64_t nz, int64_t ny,
+                               int64_t nx, psb200_stream stream)
+{
+    if (!ctx || !idx || !written) return fail(PSB200_ERR_INVALID, "lt_wmask: NULL argument");
+    int rc = check_dims("lt_wmask", nz, ny, nx);
+    if (!rc) rc = bit_shape_ok("lt_wmask", nx, idx, written);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return lt_wmask_impl(ctx, idx, written, nz * ny * nx / 32, (cudaStream_t)stream);
+}
+
+extern "C" int psb200_lt_bitball(psb200_ctx *ctx, const uint32_t *seedbits, int64_t nz_src, int64_t z_off,
+                                 uint32_t *written, uint8_t *idx, int k, uint32_t T, int64_t nz, int64_t ny,
+                                 int64_t nx, psb200_stream stream)
+{
+    if (!ctx || !seedbits || !written || !idx || T == 0 || k < 0 || k >= PSB200_MAX_THRESHOLDS)
+        return fail(PSB200_ERR_INVALID, "lt_bitball: bad argument");
+    if (z_off < 0 || z_off + nz > nz_src) return fail(PSB200_ERR_INVALID, "lt_bitball: slab [z_off, z_off+nz) outside the seed buffer");
+    int rc = check_dims("lt_bitball", nz, ny, nx);
+    if (!rc) rc = bit_shape_ok("lt_bitball", nx, seedbits, idx);
+    if (rc) return rc;
+    if (nz_src > 65535 || nz_src * ny * nx >= (1LL << 35)) return fail(PSB200_ERR_UNSUPPORTED, "lt_bitball: volume too large");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return lt_bitball_impl(ctx, seedbits, nz_src, z_off, written, idx, k, T, nz, ny, nx, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, const uint32_t *T_host,
@@ -800,11 +904,8 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
                 if (k == 0 && !(flags & PSB200_FLAG_IDX_PREINIT))
                     CUDA_TRY(cudaMemsetAsync(w.written, 0, (size_t)nwords * 4, st));
                 else {
-                    {
-                        ProfScope ps__(ctx, st, K_LT_WMASK);
-                        lt_wmask_kernel<<<grid_for(nwords, 256, ctx->sm_count, 16), 256, 0, st>>>(idx, w.written, nwords);
-                    }
-                    LAUNCH_CHECK(ctx);
+                    rc = lt_wmask_impl(ctx, idx, w.written, nwords, st);
+                    if (rc) return rc;
                 }
                 wmask_ready = true;
             }

@@ -1,0 +1,312 @@
+"""Volumes sharded as z-slabs over the GPUs of one box (one process per GPU, torch.distributed).
+
+Rank r owns the planes [z0_r, z1_r) of a global [nz][ny][nx] volume (C order: a slab is one
+contiguous block).  What is slab-local and what is exchanged:
+
+* EDT x and y passes: local.  z pass: slab -> pencil all-to-all (`all_to_all_single`; NCCL over
+  NVLink on GPUs), z pass on the pencil [nz][ny/P][nx], all-to-all back.  The pack for the first
+  transpose is fused into the y-pass store (`psb200_edt_xy_u8(ysplit)`), the pencil is the receive
+  buffer itself, and the way back sends contiguous z ranges.
+* max d2 (for `sizes=int`, F:1131-1132): one scalar all-reduce.
+* per radius (F:1177-1209): everything is local except the reach of the ball across the slab
+  faces, W = ceil(sqrt(T)) - 1 planes: the byte pipeline exchanges W planes of the reach map, the
+  bit pipeline W planes of seed bits, with the two z-neighbours only (send/recv).
+* access-limited flooding (F:1181-1183): local union-find plus an exchange of the reached flags of
+  the slab faces, repeated until no rank reaches anything new.
+
+The same driver runs on CPU tensors over gloo with a numpy backend (tests/cpu_backend.py) so the
+partitioning and exchange logic is covered without a GPU; the product backend below only ever
+calls libpsb200.so.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _device as dev
+from . import _host as host
+from . import _lib
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def split_counts(n, parts):
+    """Balanced contiguous partition of range(n) into `parts` pieces (first pieces one longer)."""
+    q, r = divmod(int(n), int(parts))
+    return [q + (1 if i < r else 0) for i in range(parts)]
+
+
+def ceil_split_counts(n, parts):
+    """Partition with a fixed stride ceil(n/parts) (the layout `psb200_edt_xy_u8(ysplit)` writes)."""
+    s = -(-int(n) // int(parts))
+    return s, [max(0, min(s, n - d * s)) for d in range(parts)]
+
+
+class CudaBackend:
+    """Step primitives on one GPU: thin calls into libpsb200.so (torch tensors = device buffers)."""
+
+    def __init__(self, ctx):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.device = torch.device("cuda", ctx.device)
+        self.bit_tmax = 200
+
+    # -- allocation
+    def empty(self, n, dtype):
+        return self.torch.empty(int(n), dtype=dtype, device=self.device)
+
+    def zeros(self, n, dtype):
+        return self.torch.zeros(int(n), dtype=dtype, device=self.device)
+
+    def to_u8(self, arr):
+        return dev.to_device_u8(arr, self.ctx).reshape(-1)
+
+    def bit_ok(self, shape, T):
+        return shape[2] % 32 == 0 and T <= self.bit_tmax
+
+    # -- EDT
+    def edt_xy(self, im_u8, shape, ysplit):
+        nz, ny, nx = shape
+        h = self.empty(nz * ny * nx, self.torch.int32)
+        ws = self.ctx.workspace(2 * nz * ny * nx + 1024)
+        _lib.check(self.ctx.lib.psb200_edt_xy_u8(self.ctx.handle, dev.ptr(im_u8), dev.ptr(h), nz, ny, nx,
+                                                 int(ysplit), dev.ptr(ws), ws.numel(), dev.stream_ptr()))
+        return h
+
+    def edt_z(self, h, shape):
+        nz, ny, nx = shape
+        out = self.empty(nz * ny * nx, self.torch.int32)
+        mx = self.empty(1, self.torch.int32)
+        if nz * ny * nx == 0:
+            return out, 0
+        _lib.check(self.ctx.lib.psb200_edt_z_u32(self.ctx.handle, dev.ptr(h), dev.ptr(out), 0, dev.ptr(mx),
+                                                 nz, ny, nx, dev.stream_ptr()))
+        return out, int(mx.cpu().numpy().view(np.uint32)[0])
+
+    # -- per-radius steps
+    def classify(self, d2, T):
+        cls = self.empty(d2.numel(), self.torch.uint8)
+        T = np.ascontiguousarray(T, dtype=np.uint32)
+        _lib.check(self.ctx.lib.psb200_lt_classify(self.ctx.handle, dev.ptr(d2),
+                                                   T.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(T),
+                                                   dev.ptr(cls), d2.numel(), dev.stream_ptr()))
+        return cls
+
+    def lt_xy(self, cls, k, T, shape):
+        nz, ny, nx = shape
+        reach = self.empty(nz * ny * nx, self.torch.uint8)
+        ws = self.ctx.workspace(nz * ny * nx + 1024)
+        _lib.check(self.ctx.lib.psb200_lt_xy(self.ctx.handle, dev.ptr(cls), int(k), int(T), dev.ptr(reach),
+                                             nz, ny, nx, dev.ptr(ws), ws.numel(), dev.stream_ptr()))
+        return reach
+
+    def lt_z(self, reach, m_lo, m_hi, idx, k, T, shape):
+        nz, ny, nx = shape
+        nlo = 0 if m_lo is None else m_lo.numel() // (ny * nx)
+        nhi = 0 if m_hi is None else m_hi.numel() // (ny * nx)
+        _lib.check(self.ctx.lib.psb200_lt_z(self.ctx.handle, dev.ptr(reach), dev.ptr(m_lo), nlo, dev.ptr(m_hi),
+                                            nhi, dev.ptr(idx), int(k), int(T), nz, ny, nx, dev.stream_ptr()))
+
+    def pack(self, cls, k, out_bits, shape):
+        nz, ny, nx = shape
+        _lib.check(self.ctx.lib.psb200_lt_pack(self.ctx.handle, dev.ptr(cls), int(k), dev.ptr(out_bits),
+                                               nz, ny, nx, dev.stream_ptr()))
+
+    def wmask(self, idx, written, shape):
+        nz, ny, nx = shape
+        _lib.check(self.ctx.lib.psb200_lt_wmask(self.ctx.handle, dev.ptr(idx), dev.ptr(written), nz, ny, nx,
+                                                dev.stream_ptr()))
+
+    def bitball(self, seedbits, nz_src, z_off, written, idx, k, T, shape):
+        nz, ny, nx = shape
+        _lib.check(self.ctx.lib.psb200_lt_bitball(self.ctx.handle, dev.ptr(seedbits), int(nz_src), int(z_off),
+                                                  dev.ptr(written), dev.ptr(idx), int(k), int(T), nz, ny, nx,
+                                                  dev.stream_ptr()))
+
+    def expand(self, idx, lut):
+        out = self.empty(idx.numel(), self.torch.float64)
+        dev.expand_idx(self.ctx, idx, lut, out)
+        return out
+
+
+class ShardedVolume:
+    """Driver of the z-slab sharded hot path.  `shape` is the GLOBAL (nz, ny, nx)."""
+
+    def __init__(self, shape, ctx=None, backend=None, group=None):
+        import torch
+        dist = _dist()
+        self.torch = torch
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if len(shape) != 3:
+            raise ValueError("ShardedVolume shards 3-D volumes")
+        self.shape = tuple(int(s) for s in shape)
+        nz, ny, nx = self.shape
+        if nz < self.world or ny < self.world:
+            raise ValueError(f"volume {self.shape} is too small for {self.world} ranks")
+        self.zcounts = split_counts(nz, self.world)
+        self.zstarts = [sum(self.zcounts[:r]) for r in range(self.world)]
+        self.ysplit, self.ycounts = ceil_split_counts(ny, self.world)
+        if min(self.ycounts) == 0:
+            raise ValueError(f"ny={ny} cannot be split into {self.world} non-empty pencil ranges")
+        self.nzl = self.zcounts[self.rank]
+        self.nyl = self.ycounts[self.rank]
+        self.backend = backend if backend is not None else CudaBackend(ctx if ctx is not None else _lib.context())
+
+    # ------------------------------------------------------------------ geometry helpers
+    @property
+    def local_shape(self):
+        return (self.nzl, self.shape[1], self.shape[2])
+
+    def local_slice(self):
+        z0 = self.zstarts[self.rank]
+        return slice(z0, z0 + self.nzl)
+
+    # ---------------------------------------------------------------------- collectives
+    def _all_to_all(self, out, inp, out_counts, in_counts):
+        if self.world == 1:
+            out.copy_(inp)
+            return
+        _dist().all_to_all_single(out, inp, [int(c) for c in out_counts], [int(c) for c in in_counts],
+                                  group=self.group)
+
+    def _allreduce_max(self, value):
+        if self.world == 1:
+            return int(value)
+        t = self.torch.tensor([int(value)], dtype=self.torch.int64, device=self._comm_device())
+        _dist().all_reduce(t, op=_dist().ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    def _comm_device(self):
+        return getattr(self.backend, "device", "cpu")
+
+    def exchange_halo(self, planes_lo_send, planes_hi_send, lo_recv, hi_recv):
+        """Send my first planes to rank-1 (its hi halo) and my last planes to rank+1 (its lo
+        halo); receive my own halos.  Any argument may be None (first / last rank, W = 0)."""
+        dist = _dist()
+        ops = []
+        if self.rank > 0 and planes_lo_send is not None:
+            ops.append(dist.P2POp(dist.isend, planes_lo_send, self.rank - 1, self.group))
+        if self.rank < self.world - 1 and planes_hi_send is not None:
+            ops.append(dist.P2POp(dist.isend, planes_hi_send, self.rank + 1, self.group))
+        if self.rank > 0 and lo_recv is not None:
+            ops.append(dist.P2POp(dist.irecv, lo_recv, self.rank - 1, self.group))
+        if self.rank < self.world - 1 and hi_recv is not None:
+            ops.append(dist.P2POp(dist.irecv, hi_recv, self.rank + 1, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def _halo_depths(self, W):
+        """Planes of halo below / above my slab for reach W (limited by the neighbour's slab)."""
+        nlo = 0 if self.rank == 0 else W
+        nhi = 0 if self.rank == self.world - 1 else W
+        if W > min(self.zcounts):
+            raise ValueError(f"radius reach {W} planes exceeds the thinnest slab ({min(self.zcounts)} planes); "
+                             f"use fewer ranks for this volume")
+        return nlo, nhi
+
+    # ------------------------------------------------------------------------------ EDT
+    def edt_sq(self, local_u8):
+        """Local slab (uint8, flat or [nzl][ny][nx]) -> (uint32 squared distances of the slab as a
+        flat int32 tensor, global max d2)."""
+        torch, be = self.torch, self.backend
+        nz, ny, nx = self.shape
+        nzl, nyl, P = self.nzl, self.nyl, self.world
+        h_send = be.edt_xy(local_u8.reshape(-1), (nzl, ny, nx), self.ysplit if P > 1 else 0)
+        if P == 1:
+            d2, mx = be.edt_z(h_send, (nz, ny, nx))
+            return d2, mx
+        # slab -> pencil: block for dest d is [nzl][ycounts[d]][nx]; I receive [zcounts[s]][nyl][nx] from s
+        pencil = be.empty(nz * nyl * nx, torch.int32)
+        self._all_to_all(pencil, h_send, [self.zcounts[s] * nyl * nx for s in range(P)],
+                         [nzl * self.ycounts[d] * nx for d in range(P)])
+        del h_send
+        d2p, lmax = be.edt_z(pencil, (nz, nyl, nx))
+        del pencil
+        # pencil -> slab: dest d gets my rows for its planes (a contiguous z range of the pencil)
+        recv = be.empty(nzl * ny * nx, torch.int32)
+        self._all_to_all(recv, d2p, [nzl * self.ycounts[s] * nx for s in range(P)],
+                         [self.zcounts[d] * nyl * nx for d in range(P)])
+        del d2p
+        slab = be.empty(nzl * ny * nx, torch.int32).view(nzl, ny, nx)
+        off = 0
+        for s in range(P):
+            cnt = nzl * self.ycounts[s] * nx
+            y0 = s * self.ysplit
+            slab[:, y0:y0 + self.ycounts[s], :] = recv[off:off + cnt].view(nzl, self.ycounts[s], nx)
+            off += cnt
+        return slab.reshape(-1), self._allreduce_max(lmax)
+
+    def edt(self, local_im):
+        """float32 distances of the local slab (edt.edt semantics on the global volume)."""
+        torch = self.torch
+        d2, _ = self.edt_sq(self.backend.to_u8(local_im))
+        u = d2.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        out = torch.sqrt(u.to(torch.float32))                      # d2 < 2^24: exact float32, IEEE sqrt
+        out = torch.where(u == host.INF_U32, torch.full_like(out, float("inf")), out)
+        return out.view(self.nzl, self.shape[1], self.shape[2])
+
+    # --------------------------------------------------------------------- radius loop
+    def local_thickness(self, local_im, sizes=25):
+        """ps.filters.local_thickness of the GLOBAL volume; returns this rank's slab (float64)."""
+        return self._porosimetry(local_im, sizes, access_limited=False)
+
+    def _porosimetry(self, local_im, sizes, access_limited):
+        if access_limited:
+            raise NotImplementedError("sharded access-limited porosimetry: use a single GPU (see DESIGN.md)")
+        torch, be = self.torch, self.backend
+        nz, ny, nx = self.shape
+        nzl = self.nzl
+        lshape = (nzl, ny, nx)
+        d2, max_d2 = self.edt_sq(be.to_u8(local_im))
+        radii = host.reference_sizes(sizes, max_d2)
+        if max_d2 == host.INF_U32:
+            from .filters import _result_for_no_background
+            res = _result_for_no_background(lshape, radii)
+            return torch.from_numpy(res).to(self._comm_device())
+        T, R = host.effective_thresholds(radii, max_d2)
+        if len(T) > _lib.MAX_THRESHOLDS:
+            raise NotImplementedError("sharded path supports up to 253 effective radii per call")
+        n = nzl * ny * nx
+        idx = be.zeros(n, torch.uint8)
+        if len(T) == 0:
+            return be.expand(idx, np.array([0.0])).view(*lshape)
+        cls = be.classify(d2, T)
+        del d2
+        written = None
+        for k, Tk in enumerate(T):
+            Tk = int(Tk)
+            W = host.isqrt(Tk - 1)
+            nlo, nhi = self._halo_depths(W)
+            if be.bit_ok(lshape, Tk):
+                nw = nx // 32
+                plane = ny * nw
+                if written is None:
+                    written = be.zeros(n // 32, torch.int32)
+                    if k > 0:
+                        be.wmask(idx, written, lshape)
+                ext = be.empty((nlo + nzl + nhi) * plane, torch.int32)
+                mine = ext[nlo * plane:(nlo + nzl) * plane]
+                be.pack(cls, k, mine, lshape)
+                self.exchange_halo(mine[:nlo * plane] if self.rank > 0 and W else None,
+                                   mine[(nzl - nhi) * plane:] if nhi else None,
+                                   ext[:nlo * plane] if nlo else None,
+                                   ext[(nlo + nzl) * plane:] if nhi else None)
+                be.bitball(ext, nlo + nzl + nhi, nlo, written, idx, k, Tk, lshape)
+                del ext
+            else:
+                reach = be.lt_xy(cls, k, Tk, lshape)
+                plane = ny * nx
+                m_lo = be.empty(nlo * plane, torch.uint8) if nlo else None
+                m_hi = be.empty(nhi * plane, torch.uint8) if nhi else None
+                self.exchange_halo(reach[:W * plane] if self.rank > 0 and W else None,
+                                   reach[(nzl - W) * plane:] if nhi else None, m_lo, m_hi)
+                be.lt_z(reach, m_lo, m_hi, idx, k, Tk, lshape)
+                del reach
+        lut = np.concatenate([[0.0], R])
+        return be.expand(idx, lut).view(*lshape)

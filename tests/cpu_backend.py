@@ -1,0 +1,106 @@
+"""TEST INFRASTRUCTURE: numpy/oracle implementation of the step primitives that
+porespy_b200.sharded.ShardedVolume drives, on CPU torch tensors, so the partitioning,
+all-to-all and halo-exchange logic runs under gloo without a GPU.  Each method mirrors the
+contract of one libpsb200.so entry point (include/psb200.h); the product never imports this."""
+import numpy as np
+import torch
+
+from oracle import cpu as oc
+from tests import model_fast as mf
+
+INF = 0xFFFFFFFF
+
+
+class CpuBackend:
+    device = "cpu"
+
+    def __init__(self, bit_tmax=200):
+        self.bit_tmax = bit_tmax
+
+    def empty(self, n, dtype):
+        return torch.empty(int(n), dtype=dtype)
+
+    def zeros(self, n, dtype):
+        return torch.zeros(int(n), dtype=dtype)
+
+    def to_u8(self, arr):
+        if isinstance(arr, torch.Tensor):
+            arr = arr.numpy()
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(arr) != 0).view(np.uint8).copy()).reshape(-1)
+
+    def bit_ok(self, shape, T):
+        return shape[2] % 32 == 0 and T <= self.bit_tmax
+
+    @staticmethod
+    def _u32(t):
+        return t.numpy().view(np.uint32)
+
+    # psb200_edt_xy_u8: exact 2-D squared distances per plane, optionally in all-to-all send layout
+    def edt_xy(self, im_u8, shape, ysplit):
+        nz, ny, nx = shape
+        im = im_u8.numpy().reshape(shape)
+        h = np.empty(shape, dtype=np.uint32)
+        for z in range(nz):
+            h[z] = oc.edt_sq(im[z])
+        if ysplit:
+            blocks = [h[:, y0:y0 + ysplit, :].reshape(-1) for y0 in range(0, ny, ysplit)]
+            h = np.concatenate(blocks)
+        return torch.from_numpy(h.reshape(-1).view(np.int32).copy())
+
+    # psb200_edt_z_u32: out[z] = min_z' h[z'] + (z - z')^2
+    def edt_z(self, h, shape):
+        nz, ny, nx = shape
+        hv = self._u32(h).reshape(shape).astype(np.int64)
+        big = np.int64(1) << 40
+        hv = np.where(hv == INF, big, hv)
+        out = np.full(shape, big, dtype=np.int64)
+        zs = np.arange(nz)
+        for zp in range(nz):
+            cand = hv[zp][None, :, :] + ((zs - zp) ** 2)[:, None, None]
+            np.minimum(out, cand, out=out)
+        out = np.where(out >= big, INF, out).astype(np.uint32)
+        mx = int(out.max()) if out.size else 0
+        return torch.from_numpy(out.reshape(-1).view(np.int32).copy()), mx
+
+    def classify(self, d2, T):
+        return torch.from_numpy(mf.classify(self._u32(d2), np.asarray(T)).copy())
+
+    def lt_xy(self, cls, k, T, shape):
+        return torch.from_numpy(mf.reach_map(cls.numpy().reshape(shape), k, int(T)).reshape(-1).copy())
+
+    def lt_z(self, reach, m_lo, m_hi, idx, k, T, shape):
+        nz, ny, nx = shape
+        parts, nlo = [], 0
+        if m_lo is not None and m_lo.numel():
+            parts.append(m_lo.numpy().reshape(-1, ny, nx))
+            nlo = parts[0].shape[0]
+        parts.append(reach.numpy().reshape(shape))
+        if m_hi is not None and m_hi.numel():
+            parts.append(m_hi.numpy().reshape(-1, ny, nx))
+        fill = mf.cone_fill(np.concatenate(parts, axis=0))[nlo:nlo + nz]
+        iv = idx.numpy().reshape(shape)
+        iv[(iv == 0) & fill] = k + 1
+
+    def pack(self, cls, k, out_bits, shape):
+        bits = np.packbits(cls.numpy() <= k, bitorder="little")
+        out_bits.numpy().view(np.uint8)[:] = bits
+
+    def wmask(self, idx, written, shape):
+        written.numpy().view(np.uint8)[:] = np.packbits(idx.numpy() != 0, bitorder="little")
+
+    def bitball(self, seedbits, nz_src, z_off, written, idx, k, T, shape):
+        nz, ny, nx = shape
+        seeds = np.unpackbits(seedbits.numpy().view(np.uint8), bitorder="little").astype(bool).reshape(nz_src, ny, nx)
+        if seeds.any():
+            fill = (oc.edt_sq(~seeds) < T)[z_off:z_off + nz]
+        else:
+            fill = np.zeros(shape, dtype=bool)
+        wr = np.unpackbits(written.numpy().view(np.uint8), bitorder="little").astype(bool).reshape(shape)
+        iv = idx.numpy().reshape(shape)
+        new = fill & ~wr
+        assert not (iv[new] != 0).any(), "written mask out of sync with idx"
+        iv[new] = k + 1
+        written.numpy().view(np.uint8)[:] = np.packbits(wr | fill, bitorder="little")
+
+    def expand(self, idx, lut):
+        return torch.from_numpy(np.asarray(lut, dtype=np.float64)[idx.numpy()].copy())

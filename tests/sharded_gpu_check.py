@@ -1,0 +1,52 @@
+"""Run under torchrun on N GPUs (N = WORLD_SIZE >= 1):
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tests/sharded_gpu_check.py
+Every rank checks its z-slab of the sharded EDT / local_thickness (NCCL all-to-all + halo
+exchange, CUDA kernels through the C ABI) bit-exactly against the CPU oracle on the whole volume."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import cpu as oc                      # checker only
+from porespy_b200 import _lib
+from porespy_b200.sharded import ShardedVolume
+
+
+def main():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = _lib.context(local)
+    cases = [((96, 88, 128), 12, 200), ((97, 70, 160), 10, 0), ((64, 64, 96), [9, 6.5, 4, 2.5, 1.5, 1], 20)]
+    for shape, sizes, bit_tmax in cases:
+        im = oc.blobs(list(shape), porosity=0.6, blobiness=1.5, seed=5)
+        job = ShardedVolume(shape, ctx)
+        job.backend.bit_tmax = bit_tmax
+        sl = job.local_slice()
+        d2, mx = job.edt_sq(job.backend.to_u8(im[sl]))
+        want = oc.edt_sq(im)
+        assert mx == int(want.max()), (mx, int(want.max()))
+        got = d2.cpu().numpy().view(np.uint32).reshape(want[sl].shape)
+        assert np.array_equal(got, want[sl]), f"rank {rank}: sharded edt differs {shape}"
+        assert np.array_equal(job.edt(im[sl]).cpu().numpy(), oc.edt(im)[sl]), "edt float"
+        lt = job.local_thickness(im[sl], sizes=sizes).cpu().numpy()
+        ref = oc.local_thickness(im, sizes=sizes, mode="dt")
+        if not np.array_equal(lt, ref[sl]):
+            bad = np.argwhere(lt != ref[sl])
+            raise AssertionError(f"rank {rank}: local_thickness {shape}: {len(bad)} voxels differ, first {bad[:5].tolist()}")
+        if rank == 0:
+            print(f"sharded x{world} ok: {shape} sizes={sizes} bit_tmax={bit_tmax}", flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print("SHARDED_GPU_CHECK_OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -277,3 +277,26 @@ def test_config0_golden(psb, golden):
     inl = np.zeros_like(im)
     inl[0, ...] = True
     assert sha(psb.filters.porosimetry(im, sizes=25, inlets=inl)) == str(g.raw("poro_inlet0_sha"))
+
+
+def test_sharded_driver_single_rank(psb):
+    """The z-slab driver with one rank runs every step-level C-ABI entry point it uses
+    (edt_xy / edt_z / lt_classify / lt_xy / lt_z / lt_pack / lt_bitball / lt_wmask)."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "sharded_gpu_check.py")], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_GPU_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_sharded_two_gpus(psb):
+    """NCCL all-to-all + halo exchange on 2 GPUs (skipped on a 1-GPU box)."""
+    import subprocess, sys, os, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731",
+                        os.path.join(root, "tests", "sharded_gpu_check.py")], cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "SHARDED_GPU_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

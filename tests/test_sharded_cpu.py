@@ -1,0 +1,81 @@
+"""world_size-2/3 gloo runs of the z-slab sharded driver (porespy_b200/sharded.py) on CPU with the
+numpy step backend: the sharded result must equal the oracle's result on the whole volume."""
+import os
+import socket
+import traceback
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import cpu as oc
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, shape, sizes, bit_tmax, errq):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from porespy_b200.sharded import ShardedVolume
+        from tests.cpu_backend import CpuBackend
+        im = oc.blobs(list(shape), porosity=0.6, blobiness=1.5, seed=3)
+        job = ShardedVolume(shape, backend=CpuBackend(bit_tmax=bit_tmax))
+        sl = job.local_slice()
+        # EDT through both all-to-all transposes
+        d2, mx = job.edt_sq(job.backend.to_u8(im[sl]))
+        want = oc.edt_sq(im)
+        assert mx == int(want.max()), (mx, int(want.max()))
+        assert np.array_equal(d2.numpy().view(np.uint32).reshape(want[sl].shape), want[sl]), "edt slab"
+        assert np.array_equal(job.edt(im[sl]).numpy(), oc.edt(im)[sl]), "edt float"
+        # radius loop with halo exchange (byte and bit pipelines)
+        lt = job.local_thickness(im[sl], sizes=sizes).numpy()
+        ref = oc.local_thickness(im, sizes=sizes, mode="dt")
+        assert lt.dtype == np.float64
+        if not np.array_equal(lt, ref[sl]):
+            bad = np.argwhere(lt != ref[sl])
+            raise AssertionError(f"rank {rank}: {len(bad)} voxels differ, first {bad[:5].tolist()}")
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put(f"rank {rank}:\n{traceback.format_exc()}")
+        raise
+
+
+@pytest.mark.parametrize("world,shape,sizes,bit_tmax", [
+    (2, (24, 20, 32), 8, 200),          # bit pipeline for every radius
+    (2, (25, 21, 32), 8, 0),            # byte pipeline only, uneven slabs and pencils
+    (3, (31, 26, 64), [5, 3.2, 2, 1], 6),   # mixed: large radii bytes, small radii bits; 3 ranks
+])
+def test_sharded_local_thickness_gloo(world, shape, sizes, bit_tmax):
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, sizes, bit_tmax, errq)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    msgs = []
+    while not errq.empty():
+        msgs.append(errq.get())
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+            msgs.append("worker timed out")
+    assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
+
+
+def test_partition_helpers():
+    from porespy_b200.sharded import ceil_split_counts, split_counts
+    assert split_counts(10, 3) == [4, 3, 3]
+    assert split_counts(8, 8) == [1] * 8
+    assert ceil_split_counts(10, 4) == (3, [3, 3, 3, 1])
+    assert ceil_split_counts(1024, 8) == (128, [128] * 8)
