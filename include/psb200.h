@@ -114,8 +114,10 @@ int psb200_edt_pass(psb200_ctx *ctx, int axis, const uint8_t *in, uint32_t *d2,
  *   ysplit = 0: h_out is [nz][ny][nx].  ysplit > 0: h_out is written in the send layout of the
  *   slab->pencil all-to-all, [dest d][nz][rows of d][nx] with dest d owning rows
  *   [d*ysplit, min(ny,(d+1)*ysplit)) -- the pack is fused into the store.
+ *   Values >= 0xC000FFFE in h_out mean "infinite" (no zero in that plane); only
+ *   psb200_edt_z_u32 consumes them.
  * psb200_edt_z_u32: z pass on a pencil [nz][ny_local][nx] (all planes, a range of rows);
- *   out_kind / max_out as in psb200_edt_u8.  out may not alias h. */
+ *   out_kind / max_out as in psb200_edt_u8 (max_out is required here).  out may not alias h. */
 int psb200_edt_xy_u8(psb200_ctx *ctx, const uint8_t *in, uint32_t *h_out,
                      int64_t nz, int64_t ny, int64_t nx, int64_t ysplit,
                      void *ws, size_t ws_bytes, psb200_stream stream);

@@ -66,29 +66,42 @@ __device__ __forceinline__ uint4 mp_load_row(const typename Src::T *row, int x, 
 // slab -> pencil all-to-all, so no separate pack pass is needed.
 // grid.x = ceil(nxc/128) * ceil(n/L)  (row tiles fastest: neighbours share halo rows in L2).
 // OUT 0: uint32 squared distance (PSB_INF when infinite); OUT 1: float32 sqrt (edt.edt's result).
+#define MP_R 4                 // rows per lane: a lane owns a 4 (rows) x 4 (columns) block of outputs
+
+__device__ __forceinline__ void mp_relax(uint4 &b, const uint4 &u, uint32_t d2)
+{
+    b.x = __viaddmin_u32(u.x, d2, b.x); b.y = __viaddmin_u32(u.y, d2, b.y);
+    b.z = __viaddmin_u32(u.z, d2, b.z); b.w = __viaddmin_u32(u.w, d2, b.w);
+}
+__device__ __forceinline__ uint32_t mp_max4(const uint4 &b) { return max(max(b.x, b.y), max(b.z, b.w)); }
+
+// Register tiling along the pass axis: the two rows fetched at step dy (one above, one below the
+// 4-row block) serve all 4 output rows with the offsets (dy + i)^2 / (dy + 3 - i)^2, so the
+// shared-memory traffic and the loop overhead per output are a quarter of the one-row form.
 template <typename Src, int OUT>
 __global__ void __launch_bounds__(MP_WARPS * 32)
 edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ dst, int n,
                    int64_t rstride, int64_t nxc, int64_t ostride, int L, int H, int vec,
                    uint32_t *__restrict__ gmax, int split)
 {
-    extern __shared__ uint4 mp_tile[];                     // [L + 2H][32]
+    extern __shared__ uint4 mp_tile[];                     // [roundup4(L) + 2H][32]
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int nrt = (n + L - 1) / L;
     const int row0 = (int)(blockIdx.x % nrt) * L;
     const int64_t x0 = (int64_t)(blockIdx.x / nrt) * MP_TX;
     const int64_t valid = nxc - x0;                        // columns of this tile inside the row
     const typename Src::T *sbase = src + (int64_t)blockIdx.y * ostride + x0;
-    const int rows = L + 2 * H;
-    const int xl = 4 * lane;
+    const int Lr = (L + MP_R - 1) & ~(MP_R - 1);
+    const int rows = Lr + 2 * H;
+    const uint4 INF4 = make_uint4(MP_INF, MP_INF, MP_INF, MP_INF);
 
     for (int r0 = warp; r0 < rows; r0 += 4 * MP_WARPS) {   // 4 independent row loads in flight
         uint4 v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = r0 + i * MP_WARPS, gr = row0 - H + r;
-            v[i] = make_uint4(MP_INF, MP_INF, MP_INF, MP_INF);
-            if (r < rows && gr >= 0 && gr < n) v[i] = mp_load_row<Src>(sbase + (int64_t)gr * rstride, xl, valid, vec);
+            v[i] = INF4;
+            if (r < rows && gr >= 0 && gr < n) v[i] = mp_load_row<Src>(sbase + (int64_t)gr * rstride, 4 * lane, valid, vec);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -98,70 +111,121 @@ edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ d
     }
     __syncthreads();
 
+    // Warp footprint: 32 columns x 16 rows (lane = 8 column groups x 4 row blocks) -- compact, so
+    // the lanes of a warp see similar distances; every quarter-warp still reads 128 contiguous
+    // bytes of one tile row (conflict-free LDS.128).  Block: 4 warps across x, 2 down.
     uint32_t lmax = 0;
-    for (int ry = warp; ry < L; ry += MP_WARPS) {
-        const int gr = row0 + ry;
-        if (gr >= n) break;
+    const int cg = (warp & 3) * 8 + (lane & 7);            // column group (uint4) inside the tile row
+    const int xl = 4 * cg;
+    const uint4 *col = mp_tile + cg;
+    for (int ry = ((warp >> 2) * 4 + (lane >> 3)) * MP_R; ry < L; ry += 2 * 4 * MP_R) {
+        const int gr = row0 + ry;                          // first output row of the block
+        if (gr >= n) break;                                // (per lane: no warp-wide operation inside)
         const int rr = ry + H;
-        uint4 b = mp_tile[rr * 32 + lane];
-        for (int dy = 1;; ++dy) {
-            const uint32_t bm = max(max(b.x, b.y), max(b.z, b.w));
-            const uint32_t d2 = (uint32_t)dy * (uint32_t)dy;
-            if (d2 >= bm) break;
-            const bool up_in = gr - dy >= 0, dn_in = gr + dy < n;
-            if (!up_in && !dn_in) break;
+        uint4 O[MP_R], B[MP_R];
+#pragma unroll
+        for (int i = 0; i < MP_R; ++i) O[i] = col[(rr + i) * 32];
+#pragma unroll
+        for (int i = 0; i < MP_R; ++i) {
+            B[i] = O[i];
+#pragma unroll
+            for (int j = 0; j < MP_R; ++j)
+                if (j != i) mp_relax(B[i], O[j], (uint32_t)((i - j) * (i - j)));
+            if (gr + i >= n) B[i] = make_uint4(0u, 0u, 0u, 0u);      // rows past the end: nothing to do
+        }
+        // fast loop: both fetched rows are inside the staged tile (rows outside the volume hold INF)
+        const int dlim = min(rr, rows - 1 - (rr + MP_R - 1));
+        int dy = 1;
+        bool done = false;
+        for (; dy <= dlim; ++dy) {
+            const uint32_t bm = max(max(mp_max4(B[0]), mp_max4(B[1])), max(mp_max4(B[2]), mp_max4(B[3])));
+            if ((uint32_t)(dy * dy) >= bm) { done = true; break; }
+            const uint4 top = col[(rr - dy) * 32], bot = col[(rr + MP_R - 1 + dy) * 32];
+#pragma unroll
+            for (int i = 0; i < MP_R; ++i) {
+                mp_relax(B[i], top, (uint32_t)((dy + i) * (dy + i)));
+                mp_relax(B[i], bot, (uint32_t)((dy + MP_R - 1 - i) * (dy + MP_R - 1 - i)));
+            }
+        }
+        // slow loop (rare): rows beyond the staged halo come from global memory
+        while (!done) {
+            const uint32_t bm = max(max(mp_max4(B[0]), mp_max4(B[1])), max(mp_max4(B[2]), mp_max4(B[3])));
+            const bool up_in = gr - dy >= 0, dn_in = gr + MP_R - 1 + dy < n;
+            if ((uint32_t)dy * (uint32_t)dy >= bm || (!up_in && !dn_in)) break;
             if (up_in) {
-                const uint4 u = (rr - dy >= 0) ? mp_tile[(rr - dy) * 32 + lane]
-                                               : mp_load_row<Src>(sbase + (int64_t)(gr - dy) * rstride, xl, valid, vec);
-                b.x = __viaddmin_u32(u.x, d2, b.x); b.y = __viaddmin_u32(u.y, d2, b.y);
-                b.z = __viaddmin_u32(u.z, d2, b.z); b.w = __viaddmin_u32(u.w, d2, b.w);
+                const uint4 top = (rr - dy >= 0) ? col[(rr - dy) * 32]
+                                                 : mp_load_row<Src>(sbase + (int64_t)(gr - dy) * rstride, xl, valid, vec);
+#pragma unroll
+                for (int i = 0; i < MP_R; ++i) mp_relax(B[i], top, (uint32_t)(dy + i) * (uint32_t)(dy + i));
             }
             if (dn_in) {
-                const uint4 u = (rr + dy < rows) ? mp_tile[(rr + dy) * 32 + lane]
-                                                 : mp_load_row<Src>(sbase + (int64_t)(gr + dy) * rstride, xl, valid, vec);
-                b.x = __viaddmin_u32(u.x, d2, b.x); b.y = __viaddmin_u32(u.y, d2, b.y);
-                b.z = __viaddmin_u32(u.z, d2, b.z); b.w = __viaddmin_u32(u.w, d2, b.w);
+                const int rb = rr + MP_R - 1 + dy;
+                const uint4 bot = (rb < rows) ? col[rb * 32]
+                                              : mp_load_row<Src>(sbase + (int64_t)(gr + MP_R - 1 + dy) * rstride, xl, valid, vec);
+#pragma unroll
+                for (int i = 0; i < MP_R; ++i)
+                    mp_relax(B[i], bot, (uint32_t)(dy + MP_R - 1 - i) * (uint32_t)(dy + MP_R - 1 - i));
             }
+            ++dy;
         }
-        uint32_t o[4] = {b.x, b.y, b.z, b.w};
+        // ---- store the block
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (o[j] >= MP_INF) o[j] = PSB_INF;
-            if (xl + j < valid) lmax = max(lmax, o[j]);
-        }
-        int64_t oi = (int64_t)blockIdx.y * ostride + x0 + (int64_t)gr * rstride + xl;
-        if (split > 0) {
-            // y pass of a z-slab: store in all-to-all send layout [dest d][z][y - d*split][x]
-            // (dest d owns rows [d*split, min(n, (d+1)*split)) of the pencil decomposition)
-            const int d = gr / split, yy = gr - d * split;
-            const int nyd = min(split, n - d * split);
-            oi = ((int64_t)d * split * gridDim.y + (int64_t)blockIdx.y * nyd + yy) * rstride + x0 + xl;
-        }
-        if (OUT == 0) {
-            uint32_t *orow = reinterpret_cast<uint32_t *>(dst) + oi;
-            if (vec && xl + 3 < valid) *reinterpret_cast<uint4 *>(orow) = make_uint4(o[0], o[1], o[2], o[3]);
-            else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (xl + j < valid) orow[j] = o[j];
+        for (int i = 0; i < MP_R; ++i) {
+            const int g = gr + i;
+            if (g >= n || ry + i >= L) continue;
+            int64_t oi = (int64_t)blockIdx.y * ostride + x0 + (int64_t)g * rstride + xl;
+            if (split > 0) {
+                // y pass of a z-slab: all-to-all send layout [dest d][z][y - d*split][x]
+                // (dest d owns rows [d*split, min(n, (d+1)*split)) of the pencil decomposition)
+                const int d = g / split, yy = g - d * split;
+                const int nyd = min(split, n - d * split);
+                oi = ((int64_t)d * split * gridDim.y + (int64_t)blockIdx.y * nyd + yy) * rstride + x0 + xl;
             }
-        } else {
-            float *orow = reinterpret_cast<float *>(dst) + oi;
-            float f[4];
+            const uint32_t o[4] = {B[i].x, B[i].y, B[i].z, B[i].w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) f[j] = (o[j] == PSB_INF) ? __int_as_float(0x7F800000) : sqrtf((float)o[j]);
-            if (vec && xl + 3 < valid) *reinterpret_cast<float4 *>(orow) = make_float4(f[0], f[1], f[2], f[3]);
-            else {
+            for (int j = 0; j < 4; ++j)
+                if (xl + j < valid) lmax = max(lmax, o[j]);
+            if (OUT == 0) {
+                // infinite values stay >= MP_INF here; edt_fix_inf_kernel maps them to PSB_INF
+                // afterwards, and only when the running max says there are any
+                uint32_t *orow = reinterpret_cast<uint32_t *>(dst) + oi;
+                if (vec && xl + 3 < valid) *reinterpret_cast<uint4 *>(orow) = B[i];
+                else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (xl + j < valid) orow[j] = f[j];
+                    for (int j = 0; j < 4; ++j)
+                        if (xl + j < valid) orow[j] = o[j];
+                }
+            } else {
+                float *orow = reinterpret_cast<float *>(dst) + oi;
+                float f[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f[j] = (o[j] >= MP_INF) ? __int_as_float(0x7F800000) : sqrtf((float)o[j]);
+                if (vec && xl + 3 < valid) *reinterpret_cast<float4 *>(orow) = make_float4(f[0], f[1], f[2], f[3]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (xl + j < valid) orow[j] = f[j];
+                }
             }
         }
     }
     if (gmax) {
         lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
-        if (lane == 0 && lmax) atomicMax(gmax, lmax);
+        if (lane == 0 && lmax) atomicMax(gmax, min(lmax, MP_INF));
     }
+}
+
+// values >= MP_INF (infinite: no background in the volume / plane) -> PSB_INF
+// Runs only when the running max of the last pass says there are any (device-side gate, no
+// host round trip); also turns the max itself into PSB_INF.
+__global__ void __launch_bounds__(256)
+edt_fix_inf_kernel(uint32_t *__restrict__ d2, int64_t n, uint32_t *__restrict__ gmax)
+{
+    if (*reinterpret_cast<volatile uint32_t *>(gmax) < MP_INF) return;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+        if (d2 && d2[i] >= MP_INF) d2[i] = PSB_INF;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(gmax, PSB_INF);
 }
 
 // --------------------------------------------------------------- per-radius y pass (uint16x2)
@@ -175,6 +239,8 @@ __device__ __forceinline__ uint32_t sq_cap2(uint32_t a, uint32_t b, uint32_t W, 
     return sa | (sb << 16);
 }
 
+#define LTY_LUT_MAX 8192       // reach LUT in shared memory for T <= this, sqrtf above
+
 __global__ void __launch_bounds__(256)
 lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny, int nx, uint32_t T,
              int W, int Ly, const int *__restrict__ gate)
@@ -183,11 +249,16 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
     extern __shared__ uint4 lty2_smem[];
     uint2 *tile = reinterpret_cast<uint2 *>(lty2_smem);          // [rows][32] : 4 x u16 per lane
     const int tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
-    const int rows = Ly + 2 * W;
+    const int rows = ((Ly + 3) & ~3) + 2 * W;                     // Ly rounded up to whole 4-row blocks
     int *range = reinterpret_cast<int *>(tile + (size_t)rows * 32);   // [0] = first useful row, [1] = last
+    uint32_t *sout = reinterpret_cast<uint32_t *>(range + 4);         // [Ly][32] reach bytes of the tile
+    uint8_t *lut = reinterpret_cast<uint8_t *>(sout + (size_t)Ly * 32);   // lut[h] = ceil(sqrt(T - h)), lut[T] = 0
+    const bool use_lut = T <= LTY_LUT_MAX;
     const int x0 = blockIdx.x * MP_TX, y0 = blockIdx.y * Ly;
     const int64_t zoff = (int64_t)blockIdx.z * ny;
     if (tid == 0) { range[0] = rows; range[1] = -1; }
+    if (use_lut)
+        for (uint32_t h = tid; h <= T; h += 256) lut[h] = h >= T ? 0 : (uint8_t)ceil_sqrt_small(T - h);
     __syncthreads();
 
     // ---- stage: thread = 16 voxels of one row (8 threads per row, 32 rows per sweep)
@@ -229,35 +300,74 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
     __syncthreads();
     const int rlo = range[0], rhi = range[1];
 
+    // ---- scan, register-tiled like edt_minplus_kernel: a lane owns 4 rows x 4 columns; the two
+    // rows fetched at step dy serve all 4 outputs.  Warp footprint 64 columns x 8 rows (lane = 16
+    // column groups x 2 row blocks: every half-warp reads 128 contiguous bytes, conflict-free).
     const uint32_t T2 = T * 0x00010001u;
-    for (int ry = warp; ry < Ly; ry += 8) {
-        const int y = y0 + ry;
-        if (y >= ny) break;
+    const int cq = (warp & 1) * 16 + (lane & 15);            // uint2 index inside the tile row
+    for (int ry = ((warp >> 1) * 2 + (lane >> 4)) * 4; ry < Ly; ry += 32) {
+        if (y0 + ry >= ny) break;
         const int rr = ry + W;
-        uint32_t outv = 0;
-        // rows that can matter: within W of this row and inside [rlo, rhi]
-        const int dmax = min(W, max(rr - rlo, rhi - rr));
-        if (rhi >= 0 && dmax >= 0 && rr - dmax <= rhi && rr + dmax >= rlo) {
-            const uint2 own = tile[rr * 32 + lane];
-            uint32_t b0 = __vminu2(own.x, T2), b1 = __vminu2(own.y, T2);
-            for (int dy = 1; dy <= dmax; ++dy) {
-                const uint32_t m2 = __vmaxu2(b0, b1);
-                const uint32_t bm = max(m2 & 0xFFFFu, m2 >> 16);
-                const uint32_t d1 = (uint32_t)(dy * dy);
-                if (d1 >= bm) break;
-                const uint32_t d2 = d1 * 0x00010001u;
-                const uint2 up = tile[(rr - dy) * 32 + lane];
-                const uint2 dn = tile[(rr + dy) * 32 + lane];
-                b0 = __viaddmin_u16x2(up.x, d2, b0); b1 = __viaddmin_u16x2(up.y, d2, b1);
-                b0 = __viaddmin_u16x2(dn.x, d2, b0); b1 = __viaddmin_u16x2(dn.y, d2, b1);
-            }
-            const uint32_t h[4] = {b0 & 0xFFFFu, b0 >> 16, b1 & 0xFFFFu, b1 >> 16};
-            uint32_t m[4];
+        uint32_t m[4][4];
+        const bool reachable = rhi >= 0 && !(rr + 3 + W < rlo || rr - W > rhi);
+        if (!reachable) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) m[j] = h[j] >= T ? 0u : ceil_sqrt_small(T - h[j]);
-            outv = pack4(m[0], m[1], m[2], m[3]);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m[i][j] = 0;
+        } else {
+            uint2 O[4];
+            uint32_t B0[4], B1[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) O[i] = tile[(rr + i) * 32 + cq];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                B0[i] = __vminu2(O[i].x, T2);
+                B1[i] = __vminu2(O[i].y, T2);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j != i) {
+                        const uint32_t d = (uint32_t)((i - j) * (i - j)) * 0x00010001u;
+                        B0[i] = __viaddmin_u16x2(O[j].x, d, B0[i]);
+                        B1[i] = __viaddmin_u16x2(O[j].y, d, B1[i]);
+                    }
+            }
+            // rows outside [rlo, rhi] hold nothing below T: clip the scan
+            const int dmax = min(W, max(rr + 3 - rlo, rhi - rr));
+            for (int dy = 1; dy <= dmax; ++dy) {
+                const uint32_t m2 = __vmaxu2(__vmaxu2(__vmaxu2(B0[0], B1[0]), __vmaxu2(B0[1], B1[1])),
+                                             __vmaxu2(__vmaxu2(B0[2], B1[2]), __vmaxu2(B0[3], B1[3])));
+                const uint32_t bm = max(m2 & 0xFFFFu, m2 >> 16);
+                if ((uint32_t)(dy * dy) >= bm) break;
+                const uint2 top = tile[(rr - dy) * 32 + cq];
+                const uint2 bot = tile[(rr + 3 + dy) * 32 + cq];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    // offsets are capped at T so that value + offset <= 2T stays inside 16 bits
+                    const uint32_t dt = min((uint32_t)((dy + i) * (dy + i)), T) * 0x00010001u;
+                    const uint32_t db = min((uint32_t)((dy + 3 - i) * (dy + 3 - i)), T) * 0x00010001u;
+                    B0[i] = __viaddmin_u16x2(top.x, dt, B0[i]); B1[i] = __viaddmin_u16x2(top.y, dt, B1[i]);
+                    B0[i] = __viaddmin_u16x2(bot.x, db, B0[i]); B1[i] = __viaddmin_u16x2(bot.y, db, B1[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t h[4] = {B0[i] & 0xFFFFu, B0[i] >> 16, B1[i] & 0xFFFFu, B1[i] >> 16};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    m[i][j] = use_lut ? (uint32_t)lut[min(h[j], T)] : (h[j] >= T ? 0u : ceil_sqrt_small(T - h[j]));
+            }
         }
-        const int x = x0 + 4 * lane;
-        if (x < nx) *reinterpret_cast<uint32_t *>(reach + (zoff + y) * nx + x) = outv;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (ry + i < Ly) sout[(ry + i) * 32 + cq] = pack4(m[i][0], m[i][1], m[i][2], m[i][3]);
+    }
+    __syncthreads();
+    // ---- coalesced write-out of the reach tile (16 bytes per thread)
+    for (int i = tid; i < Ly * 8; i += 256) {
+        const int r = i >> 3, ch = i & 7;
+        const int y = y0 + r, x = x0 + 16 * ch;
+        if (y < ny && x < nx)
+            *reinterpret_cast<uint4 *>(reach + (zoff + y) * nx + x) = reinterpret_cast<const uint4 *>(sout)[i];
     }
 }

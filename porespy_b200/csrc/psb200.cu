@@ -47,12 +47,12 @@ static int fail(int code, const char *fmt, ...)
 enum KernelId {
     K_EDT_X = 0, K_EDT_Y, K_EDT_Z, K_SQRT, K_MAX, K_CLASSIFY, K_LT_XY, K_LT_X, K_LT_Y, K_LT_Z, K_LT_POINT, K_EXPAND,
     K_MARK_WRITTEN, K_UF_INIT, K_UF_ACTIVATE, K_UF_MARK, K_FLOOD_MISC, K_GEN_X, K_GEN_Y, K_GEN_Z,
-    K_FH_X, K_FH_Y, K_FH_Z, K_LT_PACK, K_LT_BITBALL, K_LT_WMASK, K_COUNT
+    K_FH_X, K_FH_Y, K_FH_Z, K_LT_PACK, K_LT_BITBALL, K_LT_WMASK, K_EDT_FIX, K_COUNT
 };
 static const char *const kKernelNames[K_COUNT] = {
     "edt_x", "edt_y", "edt_z", "sqrt_f32", "max_u32", "lt_classify", "lt_xy", "lt_x", "lt_y", "lt_z", "lt_point",
     "lt_expand", "lt_mark_written", "uf_init", "uf_activate", "uf_mark", "flood_misc",
-    "generic_x", "generic_y", "generic_z", "edt_fh_x", "edt_fh_y", "edt_fh_z", "lt_pack", "lt_bitball", "lt_wmask"};
+    "generic_x", "generic_y", "generic_z", "edt_fh_x", "edt_fh_y", "edt_fh_z", "lt_pack", "lt_bitball", "lt_wmask", "edt_fix_inf"};
 
 struct ProfScope {
     psb200_ctx *c;
@@ -311,7 +311,7 @@ static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src,
     int L, H;
     if (n <= 128) { L = n; H = 0; }
     else { L = 64; H = 32; }
-    const size_t smem = (size_t)(L + 2 * H) * 512;
+    const size_t smem = (size_t)(((L + 3) & ~3) + 2 * H) * 512;
     const int vec = (nxc % 4 == 0) && (rstride % 4 == 0) && (ostride % 4 == 0) &&
                     ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0);
     const int64_t gx = ((nxc + MP_TX - 1) / MP_TX) * ((n + L - 1) / L);
@@ -329,6 +329,18 @@ static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src,
     return PSB200_OK;
 }
 
+// last pass epilogue: map infinite values to PSB_INF (device-gated on the running max)
+static int launch_fix_inf(psb200_ctx *ctx, void *out, int out_kind, uint32_t *gmax, int64_t n, cudaStream_t st)
+{
+    {
+        ProfScope ps__(ctx, st, K_EDT_FIX);
+        edt_fix_inf_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(
+            out_kind == 0 ? reinterpret_cast<uint32_t *>(out) : nullptr, n, gmax);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
 static int edt_fast(psb200_ctx *ctx, const uint8_t *in, void *out, int out_kind, uint32_t *gmax,
                     int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes, cudaStream_t st)
 {
@@ -339,13 +351,18 @@ static int edt_fast(psb200_ctx *ctx, const uint8_t *in, void *out, int out_kind,
         return fail(PSB200_ERR_WORKSPACE, "edt needs %zu workspace bytes, got %zu", need + 256, ws_bytes);
     uint16_t *dx = reinterpret_cast<uint16_t *>(base);
     uint32_t *mid = reinterpret_cast<uint32_t *>(base + align256(n * 2));
-    if (gmax) CUDA_TRY(cudaMemsetAsync(gmax, 0, sizeof(uint32_t), st));
+    if (!gmax) gmax = reinterpret_cast<uint32_t *>(base + align256(n * 2) + ((nz > 1) ? align256(n * 4) : 0));
+    CUDA_TRY(cudaMemsetAsync(gmax, 0, sizeof(uint32_t), st));
     int rc = launch_xdist<XD_EDT>(ctx, in, dx, nz * ny, (int)nx, 0, 0, nullptr, st);
     if (rc) return rc;
-    if (nz == 1) return launch_minplus<MpSrcU16>(ctx, 1, dx, out, out_kind, gmax, nz, ny, nx, st);
-    rc = launch_minplus<MpSrcU16>(ctx, 1, dx, mid, 0, nullptr, nz, ny, nx, st);
+    if (nz == 1) rc = launch_minplus<MpSrcU16>(ctx, 1, dx, out, out_kind, gmax, nz, ny, nx, st);
+    else {
+        rc = launch_minplus<MpSrcU16>(ctx, 1, dx, mid, 0, nullptr, nz, ny, nx, st);
+        if (rc) return rc;
+        rc = launch_minplus<MpSrcU32>(ctx, 0, mid, out, out_kind, gmax, nz, ny, nx, st);
+    }
     if (rc) return rc;
-    return launch_minplus<MpSrcU32>(ctx, 0, mid, out, out_kind, gmax, nz, ny, nx, st);
+    return launch_fix_inf(ctx, out, out_kind, gmax, (int64_t)n, st);
 }
 
 extern "C" int psb200_edt_pass(psb200_ctx *ctx, int axis, const uint8_t *in, uint32_t *d2,
@@ -440,8 +457,11 @@ extern "C" int psb200_edt_z_u32(psb200_ctx *ctx, const uint32_t *h, void *out, i
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (max_out) CUDA_TRY(cudaMemsetAsync(max_out, 0, sizeof(uint32_t), st));
-    return launch_minplus<MpSrcU32>(ctx, 0, h, out, out_kind, max_out, nz, ny, nx, st);
+    if (!max_out) return fail(PSB200_ERR_INVALID, "edt_z_u32: max_out is required (device uint32)");
+    CUDA_TRY(cudaMemsetAsync(max_out, 0, sizeof(uint32_t), st));
+    rc = launch_minplus<MpSrcU32>(ctx, 0, h, out, out_kind, max_out, nz, ny, nx, st);
+    if (rc) return rc;
+    return launch_fix_inf(ctx, out, out_kind, max_out, nz * ny * nx, st);
 }
 
 extern "C" int psb200_sqrt_f32(psb200_ctx *ctx, const uint32_t *d2, float *out, int64_t n,
@@ -639,8 +659,8 @@ static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_
     if (rc) return rc;
     {   // y pass
         int Ly = ny < 128 ? (int)ny : 128;
-        const int rows = Ly + 2 * W;
-        const size_t smem = (size_t)rows * 256 + 16;
+        const int rows = ((Ly + 3) & ~3) + 2 * W;
+        const size_t smem = (size_t)rows * 256 + 16 + (size_t)Ly * 128 + (T <= LTY_LUT_MAX ? ((T + 16) & ~15u) : 0);
         if ((int)smem > ctx->max_smem_optin)
             return fail(PSB200_ERR_UNSUPPORTED, "lt_y: tile needs %zu bytes of shared memory", smem);
         dim3 grid((unsigned)((nx + MP_TX - 1) / MP_TX), (unsigned)((ny + Ly - 1) / Ly), (unsigned)nz);
