@@ -114,7 +114,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -272,7 +272,10 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers (rank-local volume)
     e2e = None
     if world == 1:
-        im_host = im.cpu().numpy().astype(bool)
+        # the user's volume: a numpy bool array in page-locked memory (psb.pinned_empty); the result
+        # comes back as a fresh numpy float64 array (page-locked too) every call
+        im_host = psb.pinned_empty(shape, np.bool_)
+        np.copyto(im_host, im.cpu().numpy().astype(bool))
         h2d, d2h = im_host.nbytes, im_host.size * 8
         n_e2e = max(1, min(args.steps, args.e2e_steps))
         res = psb.filters.local_thickness(im_host, sizes=SIZES)      # warm-up
@@ -286,7 +289,7 @@ def run_ours(args):
         te = (time.perf_counter() - t0) / n_e2e
         e2e = {"value": nvox / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3, "steps": n_e2e,
-               "api": "porespy_b200.filters.local_thickness(numpy bool) -> numpy float64"}
+               "api": "porespy_b200.filters.local_thickness(numpy bool, page-locked) -> numpy float64"}
         del im_host
 
     if rank != 0:
@@ -300,7 +303,9 @@ def run_ours(args):
         tot_ms, cnt = fam[dom]
         avg_s = tot_ms / cnt * 1e-3
         achieved = ALG_BYTES[dom] * per_voxels / avg_s / 1e9
-        n_eff = sum(c for k, (m, c) in prof.items() if k in ("lt_xy", "lt_y", "lt_point")) / args.steps
+        # one per effective radius: byte pipeline (lt_xy | lt_y), bit pipeline (lt_bitball), T == 1 (lt_point)
+        n_eff = sum(c for k, (m, c) in prof.items()
+                    if k in ("lt_xy", "lt_y", "lt_point", "lt_bitball", "generic_x")) / args.steps
         path_bytes = (21 + 22 * n_eff + 9) * nvox
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

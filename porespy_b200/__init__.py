@@ -12,10 +12,11 @@ from . import filters
 from .edt import edt, edtsq
 from .filters import local_thickness, porosimetry, trim_disconnected_blobs
 from .patch import install, uninstall
+from ._device import pinned_empty, to_pinned
 
 __version__ = "0.1.0"
 __all__ = ["edt", "edtsq", "filters", "local_thickness", "porosimetry",
-           "trim_disconnected_blobs", "install", "uninstall", "build"]
+           "trim_disconnected_blobs", "install", "uninstall", "build", "pinned_empty", "to_pinned"]
 
 
 def build(force=False, verbose=False):

@@ -21,6 +21,88 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+PIN_MIN_BYTES = 1 << 20      # below this a pageable copy is as fast as a pinned one
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array backed by page-locked host memory (torch's caching host allocator owns it and
+    recycles the block when the array is garbage-collected).  Volumes handed to the public API in
+    such arrays are uploaded by one DMA at PCIe speed instead of through the driver's staging
+    copies of pageable memory."""
+    torch = _torch()
+    tdt = {np.dtype(np.bool_): torch.bool, np.dtype(np.uint8): torch.uint8, np.dtype(np.float32): torch.float32,
+           np.dtype(np.float64): torch.float64, np.dtype(np.uint32): torch.int32,
+           np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+    t = torch.empty(tuple(int(s) for s in shape), dtype=tdt, pin_memory=True)
+    a = t.numpy()
+    return a.view(np.uint32) if np.dtype(dtype) == np.dtype(np.uint32) else a
+
+
+def to_pinned(arr):
+    """Copy of a numpy array in page-locked memory (see pinned_empty)."""
+    arr = np.asarray(arr)
+    out = pinned_empty(arr.shape, arr.dtype)
+    np.copyto(out, arr)
+    return out
+
+
+def to_host(t):
+    """Device tensor -> numpy.  Large results land in page-locked memory (one DMA at PCIe speed;
+    a pageable destination costs several times more), small ones take the plain path."""
+    torch = _torch()
+    if t.numel() * t.element_size() < PIN_MIN_BYTES:
+        return t.cpu().numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()
+
+
+_copy_streams = {}
+
+
+def copy_stream(device):
+    torch = _torch()
+    if device not in _copy_streams:
+        _copy_streams[device] = torch.cuda.Stream(device=device)
+    return _copy_streams[device]
+
+
+def expand_idx_to_host(ctx, idx, lut, shape, chunk=1 << 27):
+    """Radius-index map (uint8, device) -> float64 numpy in page-locked memory, without ever holding
+    the 8 B/voxel map in HBM: the LUT expansion (psb200_expand_idx_f64) runs chunk by chunk into two
+    device buffers while the previous chunk is on its way over PCIe on a second stream."""
+    torch = _torch()
+    n = idx.numel()
+    if n * 8 < PIN_MIN_BYTES:
+        out = torch.empty(n, dtype=torch.float64, device=idx.device)
+        expand_idx(ctx, idx, lut, out)
+        return out.cpu().numpy().reshape(shape)
+    host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    main = torch.cuda.current_stream()
+    side = copy_stream(idx.device)
+    chunk = min(chunk, n)
+    bufs = [torch.empty(chunk, dtype=torch.float64, device=idx.device) for _ in range(2)]
+    done = [None, None]
+    for i, s in enumerate(range(0, n, chunk)):
+        e = min(n, s + chunk)
+        b = bufs[i & 1][:e - s]
+        if done[i & 1] is not None:
+            main.wait_event(done[i & 1])
+        expand_idx(ctx, idx[s:e], lut, b)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            host[s:e].copy_(b, non_blocking=True)
+            d = torch.cuda.Event()
+            d.record(side)
+        done[i & 1] = d
+    side.synchronize()
+    main.wait_stream(side)
+    return host.numpy().reshape(shape)
+
+
 def to_device_u8(arr, ctx):
     """Host array or torch tensor -> contiguous uint8 device tensor whose non-zero bytes mark the
     foreground (the kernels test `byte != 0`, so bool / uint8 data is passed through as is)."""
@@ -38,7 +120,7 @@ def to_device_u8(arr, ctx):
         a = np.ascontiguousarray(a).view(np.uint8)
     else:
         a = np.ascontiguousarray(a != 0).view(np.uint8)
-    return torch.from_numpy(a).to(dev, non_blocking=False)
+    return torch.from_numpy(a).to(dev, non_blocking=False)      # a single DMA when `a` is page-locked
 
 
 def edt_run(ctx, im_u8, shape, as_f32=False, want_max=False):

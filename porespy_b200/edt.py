@@ -44,7 +44,7 @@ def _run(data, squared):
     else:
         out = dev.edt_run(ctx, im_u8, shape, as_f32=True)[0]      # sqrt fused into the last pass
     out = out.view(*shape)
-    return out.cpu().numpy() if as_numpy else out
+    return dev.to_host(out) if as_numpy else out
 
 
 def edt(data, anisotropy=None, black_border=False, order="K", parallel=1, voxel_graph=None):
@@ -66,4 +66,4 @@ def edt_sq_u32(data):
     shape = tuple(int(s) for s in data.shape)
     ctx = _lib.context()
     d2 = dev.edt_sq(ctx, dev.to_device_u8(data, ctx), shape)
-    return d2.cpu().numpy().view(np.uint32).reshape(shape)
+    return dev.to_host(d2).view(np.uint32).reshape(shape)

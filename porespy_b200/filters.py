@@ -36,10 +36,14 @@ def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True):
     """Device loop over the effective thresholds (in groups of <= 253) -> float64 radius map."""
     torch = dev._torch()
     n = int(np.prod(shape))
-    out = torch.empty(n, dtype=torch.float64, device=d2.device)
     idx = torch.empty(n, dtype=torch.uint8, device=d2.device)
     G = _lib.MAX_THRESHOLDS
     ngroups = max(1, -(-len(T) // G))
+    if ngroups == 1 and as_numpy:
+        # common case: the float64 map (F:1178) is only materialised on the host
+        dev.local_thickness_idx(ctx, d2, T, idx, inlets_u8, inlet_mode, ndim, shape, 0)
+        return dev.expand_idx_to_host(ctx, idx, np.concatenate([[0.0], R]), shape)
+    out = torch.empty(n, dtype=torch.float64, device=d2.device)
     for g in range(ngroups):
         Tg, Rg = T[g * G:(g + 1) * G], R[g * G:(g + 1) * G]
         flags = 0
@@ -53,8 +57,7 @@ def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True):
     out = out.view(*shape) if len(shape) else out
     if not as_numpy:
         return out
-    res = out.cpu().numpy()
-    return res
+    return dev.to_host(out)
 
 
 def porosimetry(im, sizes: int = 25, inlets=None, access_limited: bool = True,
@@ -141,5 +144,5 @@ def trim_disconnected_blobs(im, inlets, strel=None):
     fg = dev.to_device_u8(im > 0, ctx)
     inl = dev.to_device_u8(mask, ctx)
     shape3 = host.shape3(im.shape)
-    keep = dev.flood(ctx, fg, inl, conn, shape3).view(*im.shape).cpu().numpy().astype(bool)
+    keep = dev.to_host(dev.flood(ctx, fg, inl, conn, shape3).view(*im.shape)).astype(bool)
     return keep * im
