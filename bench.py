@@ -42,8 +42,24 @@ ALG_BYTES = {
     "edt_x": 5, "edt_y": 8, "edt_z": 8, "edt_fh_x": 5, "edt_fh_y": 8, "edt_fh_z": 8,              # 1+4, 4+4, 4+4  (B_edt = 21)
     "lt_xy": 16, "lt_x": 8, "lt_y": 8, "lt_z": 6, "lt_point": 22,         # x(4+4) + y(4+4); z(4+1+1)  (B_rad = 22)
     "lt_expand": 9, "lt_classify": 5,
+    "lt_bitball": 22,                                                     # one launch = the whole radius step
     "generic_x": 8, "generic_y": 8, "generic_z": 6,
 }
+
+
+def ncu_traffic(kernel, edge):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, scripts/ncu_traffic.py); None when the
+    capture was taken at another volume size."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if int(t["edge"]) != int(edge):
+            return None
+        return float(t["kernels"][kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def peaks():
@@ -308,7 +324,10 @@ def run_ours(args):
                     if k in ("lt_xy", "lt_y", "lt_point", "lt_bitball", "generic_x")) / args.steps
         path_bytes = (21 + 22 * n_eff + 9) * nvox
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak,
+                "traffic": ncu_traffic(dom, args.size) if world == 1 else None,
+                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/ncu_traffic.json)",
+                "alg_bytes_per_launch": ALG_BYTES[dom] * per_voxels, "peak_source": peak_src,
                 "alg_bytes_per_voxel_per_launch": ALG_BYTES[dom],
                 "avg_launch_ms": tot_ms / cnt, "launches_per_step": cnt / args.steps,
                 "share_of_step": tot_ms / ms if world == 1 else None,
