@@ -197,6 +197,36 @@ int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t *inlets, ui
                  int conn, int64_t nz, int64_t ny, int64_t nx,
                  void *ws, size_t ws_bytes, psb200_stream stream);
 
+/* Step-level access-limited flooding (F:1181-1183 inside the radius loop) for volumes sharded
+ * into z-slabs: this rank holds planes [z0, z0+nz) of nz_global.  The union-find
+ * (parent: nz*ny*nx + 1 uint32, node 0 = virtual inlet root) is slab-local and kept across radii;
+ * connectivity through a slab face is exchanged by the host as one byte per face voxel:
+ *   psb200_uf_begin    : rcls = "not reached" class map, parent = every inlet -> root.  With
+ *                        PSB200_INLETS_FACES the faces predicate uses GLOBAL z (z0, nz_global);
+ *                        with PSB200_INLETS_MASK `inlets` is the local slab of the mask.
+ *   psb200_uf_activate : link the voxels with klo < cls <= khi to their active 6-neighbours.
+ *   psb200_uf_face     : flags_out[ny*nx] = node of local plane `zplane` is connected to the inlets.
+ *   psb200_uf_inject   : nb_flags = the neighbour rank's facing plane from psb200_uf_face; links the
+ *                        nodes under a set flag to the root; *changed_dev = 1 if that was news.
+ *   psb200_uf_mark     : rcls[v] = k for seeds (cls <= k) now connected (F:1268-1269); *any_dev = 1
+ *                        once any voxel was ever marked.
+ * The host repeats face -> exchange -> inject until no rank reports a change, then marks. */
+int psb200_uf_begin(psb200_ctx *ctx, const uint8_t *cls, uint8_t *rcls, uint32_t *parent,
+                    const uint8_t *inlets, int inlet_mode, int ndim, int64_t nz, int64_t ny,
+                    int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream);
+int psb200_uf_activate(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
+                       int inlet_mode, int ndim, int klo, int khi, int64_t nz, int64_t ny,
+                       int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream);
+int psb200_uf_face(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
+                   int inlet_mode, int ndim, int k, int64_t zplane, uint8_t *flags_out, int64_t nz,
+                   int64_t ny, int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream);
+int psb200_uf_inject(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
+                     int inlet_mode, int ndim, int k, int64_t zplane, const uint8_t *nb_flags,
+                     int *changed_dev, int64_t nz, int64_t ny, int64_t nx, int64_t z0,
+                     int64_t nz_global, psb200_stream stream);
+int psb200_uf_mark(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, uint8_t *rcls, int k,
+                   int *any_dev, int64_t n, psb200_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

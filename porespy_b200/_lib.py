@@ -78,6 +78,11 @@ SIGNATURES = {
     "psb200_lt_bitball": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _u32, _i64, _i64, _i64, _vp]),
     "psb200_expand_idx_f64": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _i32, _vp]),
     "psb200_mark_written": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "psb200_uf_begin": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "psb200_uf_activate": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "psb200_uf_face": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "psb200_uf_inject": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "psb200_uf_mark": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "psb200_flood_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
     "psb200_flood": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
 }

@@ -18,7 +18,8 @@
 struct InletSpec {
     int mode;                 // 1 = faces predicate, 2 = mask
     int ndim;                 // dimensionality of the squeezed image (faces predicate)
-    const uint8_t *mask;      // mode 2
+    const uint8_t *mask;      // mode 2 (the local slab of the mask)
+    int z0, nzg;              // z-slab shard: local plane z is global plane z + z0 of nzg planes
 };
 
 __device__ __forceinline__ bool is_inlet(const InletSpec &s, int64_t v, int z, int y, int x,
@@ -26,7 +27,7 @@ __device__ __forceinline__ bool is_inlet(const InletSpec &s, int64_t v, int z, i
 {
     if (s.mode == 2) return s.mask[v] != 0;
     // get_border(shape, mode='faces') (generators/_borders.py:93-100); ndim 1: all True
-    if (s.ndim >= 3) return z == 0 || z == nz - 1 || y == 0 || y == ny - 1 || x == 0 || x == nx - 1;
+    if (s.ndim >= 3) return z + s.z0 == 0 || z + s.z0 == s.nzg - 1 || y == 0 || y == ny - 1 || x == 0 || x == nx - 1;
     if (s.ndim == 2) return y == 0 || y == ny - 1 || x == 0 || x == nx - 1;
     return true;
 }
@@ -115,6 +116,44 @@ uf_mark_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, uint8_t *__res
         else ((volatile uint32_t *)parent)[v + 1] = root;        // compress
     }
     if (__any_sync(0xFFFFFFFFu, any) && lane_id() == 0 && *((volatile int *)gate) == 0) *gate = 1;
+}
+
+// ---- z-slab shards: the union-find is slab-local; connectivity through a slab face travels as
+// one byte per face voxel ("this node is connected to the inlets") and is injected on the
+// other side as a link to the virtual root.  Repeated by the host until no rank changes.
+// out[i] = 1 if voxel i of local plane z is a graph node (inlet or cls <= k) whose root is 0.
+__global__ void __launch_bounds__(256)
+uf_face_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpec inl, int k, int z,
+               int nz, int ny, int nx, uint8_t *__restrict__ out)
+{
+    const int64_t plane = (int64_t)ny * nx;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += step) {
+        const int64_t v = (int64_t)z * plane + i;
+        const int y = (int)(i / nx), x = (int)(i % nx);
+        const bool node = (int)cls[v] <= k || is_inlet(inl, v, z, y, x, nz, ny, nx);
+        out[i] = (node && uf_find(parent, (uint32_t)(v + 1)) == 0u) ? 1 : 0;
+    }
+}
+
+// nb[i] != 0: the 6-neighbour of voxel i of local plane z across the slab face is connected to
+// the inlets.  Every node of the plane under such a neighbour is linked to the root; *changed
+// is set when that reached a component that was not connected before.
+__global__ void __launch_bounds__(256)
+uf_inject_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpec inl, int k, int z,
+                 int nz, int ny, int nx, const uint8_t *__restrict__ nb, int *changed)
+{
+    const int64_t plane = (int64_t)ny * nx;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += step) {
+        if (nb[i] == 0) continue;
+        const int64_t v = (int64_t)z * plane + i;
+        const int y = (int)(i / nx), x = (int)(i % nx);
+        if (!((int)cls[v] <= k || is_inlet(inl, v, z, y, x, nz, ny, nx))) continue;
+        if (uf_find(parent, (uint32_t)(v + 1)) == 0u) continue;
+        uf_union(parent, (uint32_t)(v + 1), 0u);
+        *changed = 1;
+    }
 }
 
 // rcls init: background stays background, every foreground voxel is "not reached yet".

@@ -47,12 +47,13 @@ static int fail(int code, const char *fmt, ...)
 enum KernelId {
     K_EDT_X = 0, K_EDT_Y, K_EDT_Z, K_SQRT, K_MAX, K_CLASSIFY, K_LT_XY, K_LT_X, K_LT_Y, K_LT_Z, K_LT_POINT, K_EXPAND,
     K_MARK_WRITTEN, K_UF_INIT, K_UF_ACTIVATE, K_UF_MARK, K_FLOOD_MISC, K_GEN_X, K_GEN_Y, K_GEN_Z,
-    K_FH_X, K_FH_Y, K_FH_Z, K_LT_PACK, K_LT_BITBALL, K_LT_WMASK, K_EDT_FIX, K_COUNT
+    K_FH_X, K_FH_Y, K_FH_Z, K_LT_PACK, K_LT_BITBALL, K_LT_WMASK, K_EDT_FIX, K_UF_FACE, K_COUNT
 };
 static const char *const kKernelNames[K_COUNT] = {
     "edt_x", "edt_y", "edt_z", "sqrt_f32", "max_u32", "lt_classify", "lt_xy", "lt_x", "lt_y", "lt_z", "lt_point",
     "lt_expand", "lt_mark_written", "uf_init", "uf_activate", "uf_mark", "flood_misc",
-    "generic_x", "generic_y", "generic_z", "edt_fh_x", "edt_fh_y", "edt_fh_z", "lt_pack", "lt_bitball", "lt_wmask", "edt_fix_inf"};
+    "generic_x", "generic_y", "generic_z", "edt_fh_x", "edt_fh_y", "edt_fh_z", "lt_pack", "lt_bitball", "lt_wmask", "edt_fix_inf",
+    "uf_face"};
 
 struct ProfScope {
     psb200_ctx *c;
@@ -891,7 +892,7 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
     if (rc) return rc;
 
     const bool al = inlet_mode != PSB200_INLETS_NONE;
-    InletSpec inl{inlet_mode, ndim, inlets};
+    InletSpec inl{inlet_mode, ndim, inlets, 0, (int)nz};
     const int g = grid_for(n, 256, ctx->sm_count, 16);
     if (al) {
         CUDA_TRY(cudaMemsetAsync(w.gate, 0, sizeof(int), st));
@@ -1012,6 +1013,121 @@ extern "C" int psb200_mark_written(psb200_ctx *ctx, const double *out, uint8_t *
     return PSB200_OK;
 }
 
+// ---- step-level access-limited flooding for z-slab shards (flood halos)
+static int uf_args(const char *who, psb200_ctx *ctx, const void *parent, const void *cls, const uint8_t *inlets,
+                   int inlet_mode, int ndim, int64_t nz, int64_t ny, int64_t nx, int64_t z0, int64_t nz_global)
+{
+    if (!ctx || !parent || !cls) return fail(PSB200_ERR_INVALID, "%s: NULL argument", who);
+    if (inlet_mode != PSB200_INLETS_FACES && inlet_mode != PSB200_INLETS_MASK)
+        return fail(PSB200_ERR_INVALID, "%s: inlet_mode must be FACES or MASK", who);
+    if (inlet_mode == PSB200_INLETS_MASK && !inlets) return fail(PSB200_ERR_INVALID, "%s: inlet mask is NULL", who);
+    if (ndim < 1 || ndim > 3) return fail(PSB200_ERR_INVALID, "%s: ndim must be 1..3", who);
+    int rc = check_dims(who, nz, ny, nx);
+    if (rc) return rc;
+    if (z0 < 0 || z0 + nz > nz_global || nz_global > PSB200_MAX_DIM)
+        return fail(PSB200_ERR_INVALID, "%s: slab [z0, z0+nz) outside [0, nz_global)", who);
+    if (nz * ny * nx > 0xFFFFFFF0LL) return fail(PSB200_ERR_UNSUPPORTED, "%s: flooding supports < 2^32 voxels per GPU", who);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_uf_begin(psb200_ctx *ctx, const uint8_t *cls, uint8_t *rcls, uint32_t *parent,
+                               const uint8_t *inlets, int inlet_mode, int ndim, int64_t nz, int64_t ny,
+                               int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream)
+{
+    int rc = uf_args("uf_begin", ctx, parent, cls, inlets, inlet_mode, ndim, nz, ny, nx, z0, nz_global);
+    if (rc) return rc;
+    if (!rcls) return fail(PSB200_ERR_INVALID, "uf_begin: rcls is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = nz * ny * nx;
+    const int g = grid_for(n, 256, ctx->sm_count, 16);
+    InletSpec inl{inlet_mode, ndim, inlets, (int)z0, (int)nz_global};
+    {
+        ProfScope ps__(ctx, st, K_UF_INIT);
+        uf_rcls_init_kernel<<<g, 256, 0, st>>>(cls, rcls, n);
+    }
+    LAUNCH_CHECK(ctx);
+    {
+        ProfScope ps__(ctx, st, K_UF_INIT);
+        uf_init_kernel<<<g, 256, 0, st>>>(parent, inl, (int)nz, (int)ny, (int)nx);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_uf_activate(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
+                                  int inlet_mode, int ndim, int klo, int khi, int64_t nz, int64_t ny,
+                                  int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream)
+{
+    int rc = uf_args("uf_activate", ctx, parent, cls, inlets, inlet_mode, ndim, nz, ny, nx, z0, nz_global);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    InletSpec inl{inlet_mode, ndim, inlets, (int)z0, (int)nz_global};
+    {
+        ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+        uf_activate_kernel<<<grid_for(nz * ny * nx, 256, ctx->sm_count, 16), 256, 0, st>>>(
+            parent, cls, inl, klo, khi, 6, (int)nz, (int)ny, (int)nx);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_uf_face(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
+                              int inlet_mode, int ndim, int k, int64_t zplane, uint8_t *flags_out, int64_t nz,
+                              int64_t ny, int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream)
+{
+    int rc = uf_args("uf_face", ctx, parent, cls, inlets, inlet_mode, ndim, nz, ny, nx, z0, nz_global);
+    if (rc) return rc;
+    if (!flags_out || zplane < 0 || zplane >= nz) return fail(PSB200_ERR_INVALID, "uf_face: bad plane / output");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    InletSpec inl{inlet_mode, ndim, inlets, (int)z0, (int)nz_global};
+    {
+        ProfScope ps__(ctx, st, K_UF_FACE);
+        uf_face_kernel<<<grid_for(ny * nx, 256, ctx->sm_count, 16), 256, 0, st>>>(
+            parent, cls, inl, k, (int)zplane, (int)nz, (int)ny, (int)nx, flags_out);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_uf_inject(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
+                                int inlet_mode, int ndim, int k, int64_t zplane, const uint8_t *nb_flags,
+                                int *changed_dev, int64_t nz, int64_t ny, int64_t nx, int64_t z0,
+                                int64_t nz_global, psb200_stream stream)
+{
+    int rc = uf_args("uf_inject", ctx, parent, cls, inlets, inlet_mode, ndim, nz, ny, nx, z0, nz_global);
+    if (rc) return rc;
+    if (!nb_flags || !changed_dev || zplane < 0 || zplane >= nz)
+        return fail(PSB200_ERR_INVALID, "uf_inject: bad plane / flags / changed pointer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    InletSpec inl{inlet_mode, ndim, inlets, (int)z0, (int)nz_global};
+    {
+        ProfScope ps__(ctx, st, K_UF_FACE);
+        uf_inject_kernel<<<grid_for(ny * nx, 256, ctx->sm_count, 16), 256, 0, st>>>(
+            parent, cls, inl, k, (int)zplane, (int)nz, (int)ny, (int)nx, nb_flags, changed_dev);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_uf_mark(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, uint8_t *rcls, int k,
+                              int *any_dev, int64_t n, psb200_stream stream)
+{
+    if (!ctx || !parent || !cls || !rcls || !any_dev || n < 0) return fail(PSB200_ERR_INVALID, "uf_mark: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        ProfScope ps__(ctx, st, K_UF_MARK);
+        uf_mark_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(parent, cls, rcls, k, n, any_dev);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
 // -------------------------------------------------------------------------------- flood
 extern "C" int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t *inlets, uint8_t *out,
                             int conn, int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
@@ -1037,7 +1153,7 @@ extern "C" int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t 
     if (!ws || w.total + 256 > ws_bytes)
         return fail(PSB200_ERR_WORKSPACE, "flood needs %zu workspace bytes, got %zu", w.total + 256, ws_bytes);
     const int g = grid_for(n, 256, ctx->sm_count, 16);
-    InletSpec inl{PSB200_INLETS_MASK, 3, inlets};
+    InletSpec inl{PSB200_INLETS_MASK, 3, inlets, 0, (int)nz};
     CUDA_TRY(cudaMemsetAsync(w.gate, 0, sizeof(int), st));
     {
         ProfScope ps__(ctx, st, K_FLOOD_MISC);

@@ -131,6 +131,59 @@ class CudaBackend:
         dev.expand_idx(self.ctx, idx, lut, out)
         return out
 
+    # -- access-limited flooding (slab-local union-find + face flags, psb200_uf_*)
+    def uf_begin(self, cls, inlets_u8, shape, z0, nz_global):
+        nz, ny, nx = shape
+        st = UfState()
+        st.cls, st.shape, st.z0, st.nzg = cls, shape, int(z0), int(nz_global)
+        st.inlets = inlets_u8
+        st.mode = _lib.INLETS_FACES if inlets_u8 is None else _lib.INLETS_MASK
+        st.rcls = self.empty(nz * ny * nx, self.torch.uint8)
+        st.parent = self.empty(nz * ny * nx + 1, self.torch.int32)
+        st.flags = self.zeros(2, self.torch.int32)            # [changed, any marked]
+        _lib.check(self.ctx.lib.psb200_uf_begin(self.ctx.handle, dev.ptr(cls), dev.ptr(st.rcls), dev.ptr(st.parent),
+                                                dev.ptr(st.inlets), st.mode, 3, nz, ny, nx, st.z0, st.nzg,
+                                                dev.stream_ptr()))
+        return st
+
+    def uf_activate(self, st, klo, khi):
+        nz, ny, nx = st.shape
+        _lib.check(self.ctx.lib.psb200_uf_activate(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls),
+                                                   dev.ptr(st.inlets), st.mode, 3, int(klo), int(khi), nz, ny, nx,
+                                                   st.z0, st.nzg, dev.stream_ptr()))
+
+    def uf_face(self, st, k, zplane):
+        nz, ny, nx = st.shape
+        out = self.empty(ny * nx, self.torch.uint8)
+        _lib.check(self.ctx.lib.psb200_uf_face(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls), dev.ptr(st.inlets),
+                                               st.mode, 3, int(k), int(zplane), dev.ptr(out), nz, ny, nx, st.z0,
+                                               st.nzg, dev.stream_ptr()))
+        return out
+
+    def uf_inject(self, st, k, zplane, nb_flags):
+        nz, ny, nx = st.shape
+        _lib.check(self.ctx.lib.psb200_uf_inject(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls),
+                                                 dev.ptr(st.inlets), st.mode, 3, int(k), int(zplane),
+                                                 dev.ptr(nb_flags), dev.ptr(st.flags), nz, ny, nx, st.z0, st.nzg,
+                                                 dev.stream_ptr()))
+
+    def uf_changed(self, st):
+        """1 if an inject since the last call connected something new (reads and clears the flag)."""
+        c = int(st.flags[0].item())
+        if c:
+            st.flags[0] = 0
+        return c
+
+    def uf_mark(self, st, k):
+        _lib.check(self.ctx.lib.psb200_uf_mark(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls), dev.ptr(st.rcls),
+                                               int(k), ctypes.c_void_p(st.flags.data_ptr() + 4), st.cls.numel(),
+                                               dev.stream_ptr()))
+
+
+class UfState:
+    """Buffers of one slab's union-find across the radius loop (owned by the backend)."""
+    pass
+
 
 class ShardedVolume:
     """Driver of the z-slab sharded hot path.  `shape` is the GLOBAL (nz, ny, nx)."""
@@ -256,9 +309,35 @@ class ShardedVolume:
         """ps.filters.local_thickness of the GLOBAL volume; returns this rank's slab (float64)."""
         return self._porosimetry(local_im, sizes, access_limited=False)
 
-    def _porosimetry(self, local_im, sizes, access_limited):
-        if access_limited:
-            raise NotImplementedError("sharded access-limited porosimetry: use a single GPU (see DESIGN.md)")
+    def porosimetry(self, local_im, sizes=25, inlets=None, access_limited=True):
+        """ps.filters.porosimetry of the GLOBAL volume (F:1032-1212); returns this rank's slab.
+        `inlets`: None = all faces of the global volume (F:1128-1129), else this rank's slab
+        [nzl][ny][nx] of the global inlet mask."""
+        return self._porosimetry(local_im, sizes, access_limited=access_limited, inlets=inlets)
+
+    def _flood_exchange(self, st, k):
+        """Propagate inlet connectivity through the slab faces until no rank learns anything new
+        (trim_disconnected_blobs on the global volume, F:1252-1270).  Returns the sweep count."""
+        be = self.backend
+        nzl, ny, nx = self.local_shape
+        if self.world == 1:
+            return 0
+        sweeps = 0
+        while True:
+            sweeps += 1
+            lo_send = be.uf_face(st, k, 0) if self.rank > 0 else None
+            hi_send = be.uf_face(st, k, nzl - 1) if self.rank < self.world - 1 else None
+            lo_recv = be.empty(ny * nx, self.torch.uint8) if self.rank > 0 else None
+            hi_recv = be.empty(ny * nx, self.torch.uint8) if self.rank < self.world - 1 else None
+            self.exchange_halo(lo_send, hi_send, lo_recv, hi_recv)
+            if lo_recv is not None:
+                be.uf_inject(st, k, 0, lo_recv)
+            if hi_recv is not None:
+                be.uf_inject(st, k, nzl - 1, hi_recv)
+            if not self._allreduce_max(be.uf_changed(st)):
+                return sweeps
+
+    def _porosimetry(self, local_im, sizes, access_limited, inlets=None):
         torch, be = self.torch, self.backend
         nz, ny, nx = self.shape
         nzl = self.nzl
@@ -278,11 +357,27 @@ class ShardedVolume:
             return be.expand(idx, np.array([0.0])).view(*lshape)
         cls = be.classify(d2, T)
         del d2
+        st = None
+        if access_limited:
+            inl = None
+            if inlets is not None:
+                if tuple(np.shape(inlets)) != lshape:
+                    raise Exception("inlets not valid, refer to docstring for info")
+                inl = be.to_u8(inlets)
+            st = be.uf_begin(cls, inl, lshape, self.zstarts[self.rank], nz)
+            self.flood_sweeps = []
         written = None
         for k, Tk in enumerate(T):
             Tk = int(Tk)
             W = host.isqrt(Tk - 1)
             nlo, nhi = self._halo_depths(W)
+            if st is not None:
+                # F:1181-1183: keep only the seeds connected to the inlets; seed sets are nested, so
+                # the union-find only links the voxels that became seeds at this radius
+                be.uf_activate(st, k - 1, k)
+                self.flood_sweeps.append(self._flood_exchange(st, k))
+                be.uf_mark(st, k)
+                cls = st.rcls
             if be.bit_ok(lshape, Tk):
                 nw = nx // 32
                 plane = ny * nw

@@ -104,3 +104,53 @@ class CpuBackend:
 
     def expand(self, idx, lut):
         return torch.from_numpy(np.asarray(lut, dtype=np.float64)[idx.numpy()].copy())
+
+    # psb200_uf_*: slab-local connectivity to the inlets + links injected through the slab faces
+    def uf_begin(self, cls, inlets_u8, shape, z0, nz_global):
+        import types
+        nz, ny, nx = shape
+        st = types.SimpleNamespace()
+        st.cls = cls.numpy().reshape(shape)
+        if inlets_u8 is None:          # get_border(global shape, 'faces') restricted to this slab
+            m = np.zeros(shape, dtype=bool)
+            zg = np.arange(z0, z0 + nz)
+            m[(zg == 0) | (zg == nz_global - 1)] = True
+            m[:, [0, -1], :] = True
+            m[:, :, [0, -1]] = True
+            st.inlet = m
+        else:
+            st.inlet = inlets_u8.numpy().reshape(shape) != 0
+        st.injected = np.zeros(shape, dtype=bool)
+        st.rcls = torch.from_numpy(np.where(st.cls == mf.CLS_BG, mf.CLS_BG, mf.CLS_NEVER).astype(np.uint8).reshape(-1))
+        st.shape, st.changed = shape, 0
+        return st
+
+    def _connected(self, st, k):
+        import scipy.ndimage as spim
+        nodes = st.inlet | (st.cls <= k)
+        lab = spim.label(nodes, structure=spim.generate_binary_structure(3, 1))[0]
+        keep = np.unique(lab[(st.inlet | st.injected) & nodes])
+        return nodes, np.isin(lab, keep[keep > 0])
+
+    def uf_activate(self, st, klo, khi):
+        pass
+
+    def uf_face(self, st, k, zplane):
+        return torch.from_numpy(self._connected(st, k)[1][zplane].astype(np.uint8).reshape(-1).copy())
+
+    def uf_inject(self, st, k, zplane, nb_flags):
+        nodes, conn = self._connected(st, k)
+        ny, nx = st.shape[1:]
+        new = nodes[zplane] & (nb_flags.numpy().reshape(ny, nx) != 0) & ~conn[zplane]
+        if new.any():
+            st.injected[zplane] |= new
+            st.changed = 1
+
+    def uf_changed(self, st):
+        c, st.changed = st.changed, 0
+        return c
+
+    def uf_mark(self, st, k):
+        conn = self._connected(st, k)[1]
+        r = st.rcls.numpy().reshape(st.shape)
+        r[(st.cls <= k) & conn & (r == mf.CLS_NEVER)] = k

@@ -39,6 +39,21 @@ def main():
         if not np.array_equal(lt, ref[sl]):
             bad = np.argwhere(lt != ref[sl])
             raise AssertionError(f"rank {rank}: local_thickness {shape}: {len(bad)} voxels differ, first {bad[:5].tolist()}")
+        # access-limited: slab-local union-find + face-flag exchange (psb200_uf_*)
+        for inl in (None, "z0", "x0"):
+            mask = None
+            if inl is not None:
+                mask = np.zeros(shape, dtype=bool)
+                if inl == "z0":
+                    mask[0] = True
+                else:
+                    mask[:, :, 0] = True
+            mip = job.porosimetry(im[sl], sizes=sizes, inlets=None if mask is None else mask[sl]).cpu().numpy()
+            ref = oc.porosimetry(im, sizes=sizes, inlets=mask, mode="dt")
+            if not np.array_equal(mip, ref[sl]):
+                bad = np.argwhere(mip != ref[sl])
+                raise AssertionError(f"rank {rank}: porosimetry {shape} inlets={inl}: {len(bad)} voxels differ, "
+                                     f"first {bad[:5].tolist()}")
         if rank == 0:
             print(f"sharded x{world} ok: {shape} sizes={sizes} bit_tmax={bit_tmax}", flush=True)
     if world > 1:

@@ -300,3 +300,55 @@ def test_sharded_two_gpus(psb):
                         os.path.join(root, "tests", "sharded_gpu_check.py")], cwd=root,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "SHARDED_GPU_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_flood_face_exchange_one_gpu(psb, nslabs):
+    """psb200_uf_begin / activate / face / inject / mark: the slab-local union-finds of a volume cut
+    into z-slabs, coupled only through the face flags (what ShardedVolume._flood_exchange sends
+    between ranks), must reproduce trim_disconnected_blobs on the whole volume for every radius."""
+    import torch
+    from porespy_b200 import _lib, _host
+    from porespy_b200.sharded import CudaBackend, split_counts
+    be = CudaBackend(_lib.context())
+    shape = (60, 48, 64)
+    nz, ny, nx = shape
+    im = oc.blobs(list(shape), porosity=0.55, blobiness=1.5, seed=11)
+    d2 = oc.edt_sq(im)
+    radii = np.array([6.0, 4.5, 3.0, 2.0, 1.0])
+    T, R = _host.effective_thresholds(radii, int(d2.max()))
+    counts = split_counts(nz, nslabs)
+    starts = [sum(counts[:i]) for i in range(nslabs)]
+    for inl_kind in ("faces", "z0"):
+        mask = None
+        if inl_kind == "z0":
+            mask = np.zeros(shape, dtype=bool)
+            mask[0] = True
+        inlets_full = mask if mask is not None else oc.border_faces(shape)
+        sts = []
+        for s0, c in zip(starts, counts):
+            d2s = torch.from_numpy(d2[s0:s0 + c].astype(np.uint32).view(np.int32).copy()).cuda().reshape(-1)
+            cls = be.classify(d2s, T)
+            inl = None if mask is None else be.to_u8(mask[s0:s0 + c])
+            sts.append(be.uf_begin(cls, inl, (c, ny, nx), s0, nz))
+        for k, Tk in enumerate(T):
+            for st in sts:
+                be.uf_activate(st, k - 1, k)
+            sweeps = 0
+            while True:
+                sweeps += 1
+                faces = [(be.uf_face(st, k, 0), be.uf_face(st, k, st.shape[0] - 1)) for st in sts]
+                for i, st in enumerate(sts):
+                    if i > 0:
+                        be.uf_inject(st, k, 0, faces[i - 1][1])
+                    if i < nslabs - 1:
+                        be.uf_inject(st, k, st.shape[0] - 1, faces[i + 1][0])
+                if not max(be.uf_changed(st) for st in sts):
+                    break
+                assert sweeps < 50
+            for st in sts:
+                be.uf_mark(st, k)
+            seeds = d2 >= Tk
+            want = oc.trim_disconnected_blobs(seeds, inlets_full, strel=oc._cross(3))
+            got = np.concatenate([(st.rcls.cpu().numpy().reshape(st.shape) <= k) for st in sts], axis=0)
+            assert_same(got, want, f"reached seeds, inlets={inl_kind}, k={k}, T={Tk}, {sweeps} sweeps")

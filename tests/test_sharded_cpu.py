@@ -42,6 +42,23 @@ def _worker(rank, world, port, shape, sizes, bit_tmax, errq):
         if not np.array_equal(lt, ref[sl]):
             bad = np.argwhere(lt != ref[sl])
             raise AssertionError(f"rank {rank}: {len(bad)} voxels differ, first {bad[:5].tolist()}")
+        # access-limited porosimetry: slab-local flooding + face-flag exchange (default face inlets,
+        # then a single-face mask: the path from the inlet face crosses every slab boundary)
+        for inl in (None, "z0", "x0"):
+            mask = None
+            if inl is not None:
+                mask = np.zeros(shape, dtype=bool)
+                if inl == "z0":
+                    mask[0] = True
+                else:
+                    mask[:, :, 0] = True
+            mip = job.porosimetry(im[sl], sizes=sizes, inlets=None if mask is None else mask[sl]).numpy()
+            ref = oc.porosimetry(im, sizes=sizes, inlets=mask, mode="dt")
+            if not np.array_equal(mip, ref[sl]):
+                bad = np.argwhere(mip != ref[sl])
+                raise AssertionError(f"rank {rank}: porosimetry inlets={inl}: {len(bad)} voxels differ, "
+                                     f"first {bad[:5].tolist()}")
+            assert max(job.flood_sweeps) >= 1
         dist.barrier()
         dist.destroy_process_group()
     except Exception:
