@@ -94,8 +94,12 @@ def porosimetry(im, sizes: int = 25, inlets=None, access_limited: bool = True,
             inlet_mode = _lib.INLETS_FACES
         else:
             if isinstance(inlets, torch.Tensor):
-                inlets = inlets.cpu().numpy()
-            mask = host.normalise_inlets(inlets, shape)
+                # device-resident mask: the same validation as F:1256-1259 without a host round trip
+                if tuple(inlets.shape) != shape or int(inlets.max().item()) != 1:
+                    raise Exception("inlets not valid, refer to docstring for info")
+                mask = inlets
+            else:
+                mask = host.normalise_inlets(inlets, shape)
             inlet_mode, inlets_u8 = _lib.INLETS_MASK, dev.to_device_u8(mask, ctx)
 
     if max_d2 == host.INF_U32:
