@@ -214,9 +214,11 @@ int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t *inlets, ui
 int psb200_uf_begin(psb200_ctx *ctx, const uint8_t *cls, uint8_t *rcls, uint32_t *parent,
                     const uint8_t *inlets, int inlet_mode, int ndim, int64_t nz, int64_t ny,
                     int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream);
+size_t psb200_uf_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx);
 int psb200_uf_activate(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
                        int inlet_mode, int ndim, int klo, int khi, int64_t nz, int64_t ny,
-                       int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream);
+                       int64_t nx, int64_t z0, int64_t nz_global, void *ws, size_t ws_bytes,
+                       psb200_stream stream);   /* ws: psb200_uf_workspace_bytes() of scratch */
 int psb200_uf_face(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
                    int inlet_mode, int ndim, int k, int64_t zplane, uint8_t *flags_out, int64_t nz,
                    int64_t ny, int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream);

@@ -73,47 +73,152 @@ uf_init_kernel(uint32_t *__restrict__ parent, InletSpec inl, int nz, int ny, int
     if (blockIdx.x == 0 && threadIdx.x == 0) parent[0] = 0u;
 }
 
-// Link every voxel with klo < cls <= khi to its active neighbours (active: inlet or cls <= khi).
-// conn: 6 (faces) or 26 (faces+edges+corners); with nz == 1 these are 4- and 8-connectivity.
+// Activation of one radius, in two kernels so that the pointer chasing of the unions runs with
+// one thread per (voxel, neighbour) job instead of inside a sparse grid-stride scan:
+//   uf_collect_kernel    : list of the voxels v in [v0, v1) with klo < cls[v] <= khi
+//   uf_union_list_kernel : every listed voxel is linked to its active neighbours (active: inlet
+//                          or cls <= khi).  conn: 6 (faces) or 26 (faces+edges+corners); with
+//                          nz == 1 these are 4- and 8-connectivity.
 __global__ void __launch_bounds__(256)
-uf_activate_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpec inl, int klo,
-                   int khi, int conn, int nz, int ny, int nx)
+uf_collect_kernel(const uint8_t *__restrict__ cls, int klo, int khi, int64_t v0, int64_t v1,
+                  uint32_t *__restrict__ list, uint32_t *__restrict__ count)
 {
-    const int64_t n = (int64_t)nz * ny * nx;
+    const int lane = lane_id();
+    const int64_t ngroups = (v1 - v0 + 15) / 16;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += step) {
-        const int c = cls[v];
-        if (c <= klo || c > khi) continue;
-        const int x = (int)(v % nx);
-        const int64_t t = v / nx;
-        const int y = (int)(t % ny), z = (int)(t / ny);
-        for (int dz = -1; dz <= 1; ++dz)
-            for (int dy = -1; dy <= 1; ++dy)
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int nn = (dz != 0) + (dy != 0) + (dx != 0);
-                    if (nn == 0 || (conn == 6 && nn != 1)) continue;
-                    const int zz = z + dz, yy = y + dy, xx = x + dx;
-                    if (zz < 0 || zz >= nz || yy < 0 || yy >= ny || xx < 0 || xx >= nx) continue;
-                    const int64_t u = ((int64_t)zz * ny + yy) * nx + xx;
-                    if ((int)cls[u] <= khi || is_inlet(inl, u, zz, yy, xx, nz, ny, nx))
-                        uf_union(parent, (uint32_t)(v + 1), (uint32_t)(u + 1));
+    const bool aligned = (((uintptr_t)(cls + v0)) & 15u) == 0;
+    // warp-uniform trip count: every lane takes part in the scan below
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); g0 < ngroups; g0 += step) {
+        const int64_t g = g0 + lane;
+        const int64_t v = v0 + 16 * g;
+        uint32_t mask = 0;
+        if (g < ngroups) {
+            if (aligned && v + 16 <= v1) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(cls + v));
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = (int)byte_of(w[i >> 2], i & 3);
+                    if (c > klo && c <= khi) mask |= 1u << i;
                 }
+            } else {
+                for (int i = 0; i < 16 && v + i < v1; ++i) {
+                    const int c = (int)cls[v + i];
+                    if (c > klo && c <= khi) mask |= 1u << i;
+                }
+            }
+        }
+        const int cnt = __popc(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (total == 0) continue;
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(count, (uint32_t)total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31) + (uint32_t)(incl - cnt);
+        while (mask) {
+            const int i = __ffs(mask) - 1;
+            mask &= mask - 1;
+            list[base++] = (uint32_t)(v + i);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+uf_union_list_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpec inl, int klo, int khi,
+                     int conn, int nz, int ny, int nx, const uint32_t *__restrict__ list,
+                     const uint32_t *__restrict__ count)
+{
+    const int ndir = conn == 6 ? 6 : 26;
+    const int64_t jobs = (int64_t)(*count) * ndir;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < jobs; j += step) {
+        const uint32_t e = (uint32_t)(j / ndir);
+        const int d = (int)(j - (int64_t)e * ndir);
+        const uint32_t v = list[e];
+        int dz, dy, dx;
+        if (conn == 6) {
+            const int ax = d >> 1, sg = (d & 1) ? 1 : -1;
+            dz = ax == 0 ? sg : 0; dy = ax == 1 ? sg : 0; dx = ax == 2 ? sg : 0;
+        } else {
+            const int q = d < 13 ? d : d + 1;          // skip the centre of the 3x3x3 cube
+            dz = q / 9 - 1; dy = (q / 3) % 3 - 1; dx = q % 3 - 1;
+        }
+        const int x = (int)(v % (uint32_t)nx);
+        const uint32_t t = v / (uint32_t)nx;
+        const int y = (int)(t % (uint32_t)ny), z = (int)(t / (uint32_t)ny);
+        const int zz = z + dz, yy = y + dy, xx = x + dx;
+        if (zz < 0 || zz >= nz || yy < 0 || yy >= ny || xx < 0 || xx >= nx) continue;
+        const int64_t u = ((int64_t)zz * ny + yy) * nx + xx;
+        const int cu = (int)cls[u];
+        if (cu > klo && cu <= khi) {
+            if (u > (int64_t)v) continue;              // both new: the pair is linked once, from the larger index
+        } else if (!(cu <= khi || is_inlet(inl, u, zz, yy, xx, nz, ny, nx))) continue;
+        uf_union(parent, v + 1u, (uint32_t)(u + 1));
     }
 }
 
 // rcls[v] = k for every seed (cls <= k) that is connected to the inlets and was not marked
 // at an earlier radius; *gate (monotone) is set once any voxel has ever been marked.
+// A thread owns 16 consecutive voxels; the two levels parent[v], parent[parent[v]] of all its
+// candidates are fetched as independent loads (after earlier compression that already decides
+// almost every voxel), only deeper chains take the serial find.
 __global__ void __launch_bounds__(256)
 uf_mark_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, uint8_t *__restrict__ rcls,
                int k, int64_t n, int *gate)
 {
+    const int64_t ngroups = (n + 15) / 16;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    const bool aligned = ((((uintptr_t)cls) | ((uintptr_t)rcls)) & 15u) == 0;
     int any = 0;
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += step) {
-        if ((int)cls[v] > k || rcls[v] != CLS_NEVER) continue;
-        const uint32_t root = uf_find(parent, (uint32_t)(v + 1));
-        if (root == 0u) { rcls[v] = (uint8_t)k; any = 1; }
-        else ((volatile uint32_t *)parent)[v + 1] = root;        // compress
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += step) {
+        const int64_t v = 16 * g;
+        if (aligned && v + 16 <= n) {
+            const uint4 cq = __ldg(reinterpret_cast<const uint4 *>(cls + v));
+            uint4 rq = *reinterpret_cast<const uint4 *>(rcls + v);
+            const uint32_t cw[4] = {cq.x, cq.y, cq.z, cq.w};
+            uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+            uint32_t cand = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if ((int)byte_of(cw[i >> 2], i & 3) <= k && byte_of(rw[i >> 2], i & 3) == CLS_NEVER) cand |= 1u << i;
+            if (cand == 0) continue;
+            const volatile uint32_t *vp = parent;
+            uint32_t p[16], gp[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) p[i] = (cand >> i & 1u) ? vp[v + i + 1] : 0u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gp[i] = (cand >> i & 1u) ? vp[p[i]] : 0u;
+            bool changed = false;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (!(cand >> i & 1u)) continue;
+                uint32_t root = p[i];
+                if (gp[i] != p[i]) {
+                    root = uf_find(parent, gp[i]);
+                    if (root != 0u) ((volatile uint32_t *)parent)[v + i + 1] = root;     // compress
+                }
+                if (root == 0u) {
+                    rw[i >> 2] = (rw[i >> 2] & ~(0xFFu << (8 * (i & 3)))) | ((uint32_t)k << (8 * (i & 3)));
+                    changed = true;
+                }
+            }
+            if (changed) {
+                *reinterpret_cast<uint4 *>(rcls + v) = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+                any = 1;
+            }
+        } else {
+            for (int i = 0; i < 16 && v + i < n; ++i) {
+                if ((int)cls[v + i] > k || rcls[v + i] != CLS_NEVER) continue;
+                const uint32_t root = uf_find(parent, (uint32_t)(v + i + 1));
+                if (root == 0u) { rcls[v + i] = (uint8_t)k; any = 1; }
+                else ((volatile uint32_t *)parent)[v + i + 1] = root;
+            }
+        }
     }
     if (__any_sync(0xFFFFFFFFu, any) && lane_id() == 0 && *((volatile int *)gate) == 0) *gate = 1;
 }

@@ -137,14 +137,23 @@ edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ d
         const int dlim = min(rr, rows - 1 - (rr + MP_R - 1));
         int dy = 1;
         bool done = false;
-        for (; dy <= dlim; ++dy) {
+        // two steps per termination test (a step past the bound only relaxes with valid candidates)
+        while (dy <= dlim) {
             const uint32_t bm = max(max(mp_max4(B[0]), mp_max4(B[1])), max(mp_max4(B[2]), mp_max4(B[3])));
             if ((uint32_t)(dy * dy) >= bm) { done = true; break; }
-            const uint4 top = col[(rr - dy) * 32], bot = col[(rr + MP_R - 1 + dy) * 32];
 #pragma unroll
-            for (int i = 0; i < MP_R; ++i) {
-                mp_relax(B[i], top, (uint32_t)((dy + i) * (dy + i)));
-                mp_relax(B[i], bot, (uint32_t)((dy + MP_R - 1 - i) * (dy + MP_R - 1 - i)));
+            for (int s2 = 0; s2 < 2; ++s2) {
+                if (dy > dlim) break;
+                const uint4 top = col[(rr - dy) * 32], bot = col[(rr + MP_R - 1 + dy) * 32];
+                uint32_t of[MP_R];
+#pragma unroll
+                for (int i = 0; i < MP_R; ++i) of[i] = (uint32_t)((dy + i) * (dy + i));
+#pragma unroll
+                for (int i = 0; i < MP_R; ++i) {
+                    mp_relax(B[i], top, of[i]);
+                    mp_relax(B[i], bot, of[MP_R - 1 - i]);
+                }
+                ++dy;
             }
         }
         // slow loop (rare): rows beyond the staged halo come from global memory
@@ -251,7 +260,8 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
     const int tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
     const int rows = ((Ly + 3) & ~3) + 2 * W;                     // Ly rounded up to whole 4-row blocks
     int *range = reinterpret_cast<int *>(tile + (size_t)rows * 32);   // [0] = first useful row, [1] = last
-    uint32_t *sout = reinterpret_cast<uint32_t *>(range + 4);         // [Ly][32] reach bytes of the tile
+    uint4 *offt = reinterpret_cast<uint4 *>(range + 4);               // [W + 2]: offt[d] = packed capped squares of d .. d+3
+    uint32_t *sout = reinterpret_cast<uint32_t *>(offt + (W + 2));    // [Ly][32] reach bytes of the tile
     uint8_t *lut = reinterpret_cast<uint8_t *>(sout + (size_t)Ly * 32);   // lut[h] = ceil(sqrt(T - h)), lut[T] = 0
     const bool use_lut = T <= LTY_LUT_MAX;
     const int x0 = blockIdx.x * MP_TX, y0 = blockIdx.y * Ly;
@@ -259,6 +269,13 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
     if (tid == 0) { range[0] = rows; range[1] = -1; }
     if (use_lut)
         for (uint32_t h = tid; h <= T; h += 256) lut[h] = h >= T ? 0 : (uint8_t)ceil_sqrt_small(T - h);
+    // offsets are capped at T so that value + offset <= 2T stays inside 16 bits
+    for (int d = tid; d < W + 2; d += 256) {
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = min((uint32_t)((d + i) * (d + i)), T) * 0x00010001u;
+        offt[d] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
     __syncthreads();
 
     // ---- stage: thread = 16 voxels of one row (8 threads per row, 32 rows per sweep)
@@ -334,20 +351,25 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
             }
             // rows outside [rlo, rhi] hold nothing below T: clip the scan
             const int dmax = min(W, max(rr + 3 - rlo, rhi - rr));
-            for (int dy = 1; dy <= dmax; ++dy) {
+            // two steps per termination test (a step past the bound only relaxes with valid candidates)
+            for (int dy = 1; dy <= dmax; dy += 2) {
                 const uint32_t m2 = __vmaxu2(__vmaxu2(__vmaxu2(B0[0], B1[0]), __vmaxu2(B0[1], B1[1])),
                                              __vmaxu2(__vmaxu2(B0[2], B1[2]), __vmaxu2(B0[3], B1[3])));
                 const uint32_t bm = max(m2 & 0xFFFFu, m2 >> 16);
                 if ((uint32_t)(dy * dy) >= bm) break;
-                const uint2 top = tile[(rr - dy) * 32 + cq];
-                const uint2 bot = tile[(rr + 3 + dy) * 32 + cq];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    // offsets are capped at T so that value + offset <= 2T stays inside 16 bits
-                    const uint32_t dt = min((uint32_t)((dy + i) * (dy + i)), T) * 0x00010001u;
-                    const uint32_t db = min((uint32_t)((dy + 3 - i) * (dy + 3 - i)), T) * 0x00010001u;
-                    B0[i] = __viaddmin_u16x2(top.x, dt, B0[i]); B1[i] = __viaddmin_u16x2(top.y, dt, B1[i]);
-                    B0[i] = __viaddmin_u16x2(bot.x, db, B0[i]); B1[i] = __viaddmin_u16x2(bot.y, db, B1[i]);
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int d = dy + s2;
+                    if (d > dmax) break;
+                    const uint2 top = tile[(rr - d) * 32 + cq];
+                    const uint2 bot = tile[(rr + 3 + d) * 32 + cq];
+                    const uint4 o4 = offt[d];                      // capped (d + i)^2, i = 0..3, both halves
+                    const uint32_t of[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        B0[i] = __viaddmin_u16x2(top.x, of[i], B0[i]); B1[i] = __viaddmin_u16x2(top.y, of[i], B1[i]);
+                        B0[i] = __viaddmin_u16x2(bot.x, of[3 - i], B0[i]); B1[i] = __viaddmin_u16x2(bot.y, of[3 - i], B1[i]);
+                    }
                 }
             }
 #pragma unroll

@@ -517,10 +517,17 @@ static int check_thresholds(const char *who, const uint32_t *T, int nT)
     return PSB200_OK;
 }
 
+// access-limited flooding: the voxels that become active at one radius are listed segment by
+// segment (UF_SEG voxels of the volume per segment bound the list), then linked by one thread
+// per (voxel, neighbour) job
+#define UF_SEG (1LL << 27)
+static size_t uf_list_entries(int64_t n) { return (size_t)(n < UF_SEG ? n : UF_SEG); }
+
 struct LtWorkspace {
     uint8_t *cls, *rcls, *reach, *gx;
     uint32_t *seedbits, *written;   // bit path: one bit per voxel
     uint32_t *parent;
+    uint32_t *uf_list;    // voxels activated at the current radius (one segment of UF_SEG voxels at a time)
     int *gate;
     uint32_t *gen_d2;     // generic algo: full u32 distance map of ~seeds
     char *gen_stk;
@@ -543,6 +550,7 @@ static LtWorkspace carve_lt(const psb200_ctx *ctx, char *base, int64_t nz, int64
     if (inlet_mode != PSB200_INLETS_NONE) {
         w.rcls = c.take<uint8_t>(n + 16);
         w.parent = c.take<uint32_t>(n + 1);
+        w.uf_list = c.take<uint32_t>(uf_list_entries((int64_t)n) + 64);
     }
     if (ctx->algo == PSB200_ALGO_GENERIC) {
         w.gen_d2 = c.take<uint32_t>(n);
@@ -661,7 +669,7 @@ static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_
     {   // y pass
         int Ly = ny < 128 ? (int)ny : 128;
         const int rows = ((Ly + 3) & ~3) + 2 * W;
-        const size_t smem = (size_t)rows * 256 + 16 + (size_t)Ly * 128 + (T <= LTY_LUT_MAX ? ((T + 16) & ~15u) : 0);
+        const size_t smem = (size_t)rows * 256 + 16 + (size_t)(W + 2) * 16 + (size_t)Ly * 128 + (T <= LTY_LUT_MAX ? ((T + 16) & ~15u) : 0);
         if ((int)smem > ctx->max_smem_optin)
             return fail(PSB200_ERR_UNSUPPORTED, "lt_y: tile needs %zu bytes of shared memory", smem);
         dim3 grid((unsigned)((nx + MP_TX - 1) / MP_TX), (unsigned)((ny + Ly - 1) / Ly), (unsigned)nz);
@@ -724,19 +732,41 @@ extern "C" int psb200_lt_z(psb200_ctx *ctx, uint8_t *reach, const uint8_t *m_lo,
     return lt_z_impl(ctx, reach, m_lo, nlo, m_hi, nhi, idx, k, T, nz, ny, nx, nullptr, (cudaStream_t)stream);
 }
 
+static int uf_activate_impl(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const InletSpec &inl, int klo,
+                            int khi, int conn, int64_t nz, int64_t ny, int64_t nx, uint32_t *list,
+                            cudaStream_t st)
+{
+    const int64_t n = nz * ny * nx;
+    uint32_t *count = list;                 // entry 0..15: the counter, the list starts at entry 16
+    uint32_t *items = list + 16;
+    for (int64_t v0 = 0; v0 < n; v0 += UF_SEG) {
+        const int64_t v1 = v0 + UF_SEG < n ? v0 + UF_SEG : n;
+        CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint32_t), st));
+        {
+            ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+            uf_collect_kernel<<<grid_for((v1 - v0 + 15) / 16, 256, ctx->sm_count, 16), 256, 0, st>>>(
+                cls, klo, khi, v0, v1, items, count);
+        }
+        LAUNCH_CHECK(ctx);
+        {
+            ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+            uf_union_list_kernel<<<ctx->sm_count * 16, 256, 0, st>>>(parent, cls, inl, klo, khi, conn, (int)nz,
+                                                                     (int)ny, (int)nx, items, count);
+        }
+        LAUNCH_CHECK(ctx);
+    }
+    return PSB200_OK;
+}
+
 static int uf_step(psb200_ctx *ctx, LtWorkspace &w, const InletSpec &inl, int klo, int khi, int conn,
                    int64_t nz, int64_t ny, int64_t nx, cudaStream_t st)
 {
     const int64_t n = nz * ny * nx;
-    const int g = grid_for(n, 256, ctx->sm_count, 16);
-    {
-        ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-        uf_activate_kernel<<<g, 256, 0, st>>>(w.parent, w.cls, inl, klo, khi, conn, (int)nz, (int)ny, (int)nx);
-    }
-    LAUNCH_CHECK(ctx);
+    int rc = uf_activate_impl(ctx, w.parent, w.cls, inl, klo, khi, conn, nz, ny, nx, w.uf_list, st);
+    if (rc) return rc;
     {
         ProfScope ps__(ctx, st, K_UF_MARK);
-        uf_mark_kernel<<<g, 256, 0, st>>>(w.parent, w.cls, w.rcls, khi, n, w.gate);
+        uf_mark_kernel<<<grid_for((n + 15) / 16, 256, ctx->sm_count, 16), 256, 0, st>>>(w.parent, w.cls, w.rcls, khi, n, w.gate);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
@@ -1055,22 +1085,27 @@ extern "C" int psb200_uf_begin(psb200_ctx *ctx, const uint8_t *cls, uint8_t *rcl
     return PSB200_OK;
 }
 
+extern "C" size_t psb200_uf_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx)
+{
+    if (!ctx) return 0;
+    return (uf_list_entries(nz * ny * nx) + 64) * sizeof(uint32_t) + 512;
+}
+
 extern "C" int psb200_uf_activate(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
                                   int inlet_mode, int ndim, int klo, int khi, int64_t nz, int64_t ny,
-                                  int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream)
+                                  int64_t nx, int64_t z0, int64_t nz_global, void *ws, size_t ws_bytes,
+                                  psb200_stream stream)
 {
     int rc = uf_args("uf_activate", ctx, parent, cls, inlets, inlet_mode, ndim, nz, ny, nx, z0, nz_global);
     if (rc) return rc;
+    char *base = ws ? (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
+    const size_t need = (uf_list_entries(nz * ny * nx) + 64) * sizeof(uint32_t);
+    if (!base || ws_bytes < need + (size_t)(base - (char *)ws))
+        return fail(PSB200_ERR_WORKSPACE, "uf_activate needs %zu workspace bytes, got %zu", need + 256, ws_bytes);
     CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
     InletSpec inl{inlet_mode, ndim, inlets, (int)z0, (int)nz_global};
-    {
-        ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-        uf_activate_kernel<<<grid_for(nz * ny * nx, 256, ctx->sm_count, 16), 256, 0, st>>>(
-            parent, cls, inl, klo, khi, 6, (int)nz, (int)ny, (int)nx);
-    }
-    LAUNCH_CHECK(ctx);
-    return PSB200_OK;
+    return uf_activate_impl(ctx, parent, cls, inl, klo, khi, 6, nz, ny, nx, reinterpret_cast<uint32_t *>(base),
+                            (cudaStream_t)stream);
 }
 
 extern "C" int psb200_uf_face(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
@@ -1122,7 +1157,7 @@ extern "C" int psb200_uf_mark(psb200_ctx *ctx, uint32_t *parent, const uint8_t *
     cudaStream_t st = (cudaStream_t)stream;
     {
         ProfScope ps__(ctx, st, K_UF_MARK);
-        uf_mark_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(parent, cls, rcls, k, n, any_dev);
+        uf_mark_kernel<<<grid_for((n + 15) / 16, 256, ctx->sm_count, 16), 256, 0, st>>>(parent, cls, rcls, k, n, any_dev);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;

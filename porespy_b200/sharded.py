@@ -148,9 +148,10 @@ class CudaBackend:
 
     def uf_activate(self, st, klo, khi):
         nz, ny, nx = st.shape
+        ws = self.ctx.workspace(self.ctx.lib.psb200_uf_workspace_bytes(self.ctx.handle, nz, ny, nx))
         _lib.check(self.ctx.lib.psb200_uf_activate(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls),
                                                    dev.ptr(st.inlets), st.mode, 3, int(klo), int(khi), nz, ny, nx,
-                                                   st.z0, st.nzg, dev.stream_ptr()))
+                                                   st.z0, st.nzg, dev.ptr(ws), ws.numel(), dev.stream_ptr()))
 
     def uf_face(self, st, k, zplane):
         nz, ny, nx = st.shape
