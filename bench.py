@@ -201,10 +201,20 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def workload_blobiness(size, n):
+    """Weak scaling keeps the per-GPU WORK fixed, so the blobs keep the feature size of the one-GPU
+    workload (sigma = S/(40*2) voxels): blobs() ties sigma to mean(shape)/(40*blobiness), hence the
+    blobiness of the grown volume is scaled by mean(shape)/S (a larger field of view of the same
+    material, not a magnified copy of it)."""
+    return BLOBINESS * float(np.mean(global_shape(size, n))) / float(size)
+
+
 def workload_config(args, n):
     shape = global_shape(args.size, n)
     return {"workload": f"ps.filters.local_thickness(blobs({list(shape)}, porosity={POROSITY}, "
-                        f"blobiness={BLOBINESS}), sizes={SIZES})",
+                        f"blobiness={workload_blobiness(args.size, n):.4g}), sizes={SIZES})",
+            "feature_size": f"sigma = {args.size / (40.0 * BLOBINESS):.1f} voxels at every N (blobiness scaled with "
+                            f"mean(shape) so that per-GPU work is fixed)",
             "shape": list(shape), "sizes": SIZES, "sharding": "none" if n == 1 else f"z-slab x{n}",
             "l2": "inputs (>=1 B/voxel x 1e9 voxels) exceed the 126 MB L2; no flush needed"}
 
@@ -244,7 +254,7 @@ def run_ours(args):
         job = sharded.ShardedVolume(shape, ctx)
         # every rank generates its own slab (independent noise per slab: it is only an input)
         im = device_blobs(job.local_shape, POROSITY, BLOBINESS, seed=rank, device=device,
-                          sigma_shape=shape)
+                          sigma_shape=(args.size,) * 3)       # feature size of the one-GPU workload
 
         def step():
             return job.local_thickness(im, sizes=SIZES)
@@ -285,28 +295,45 @@ def run_ours(args):
     nvox = float(np.prod(shape))
     value = nvox / (ms_per_step * 1e-3)
 
-    # ---- end to end through the public API with host buffers (rank-local volume)
-    e2e = None
-    if world == 1:
-        # the user's volume: a numpy bool array in page-locked memory (psb.pinned_empty); the result
-        # comes back as a fresh numpy float64 array (page-locked too) every call
-        im_host = psb.pinned_empty(shape, np.bool_)
-        np.copyto(im_host, im.cpu().numpy().astype(bool))
-        h2d, d2h = im_host.nbytes, im_host.size * 8
-        n_e2e = max(1, min(args.steps, args.e2e_steps))
-        res = psb.filters.local_thickness(im_host, sizes=SIZES)      # warm-up
+    # ---- end to end through the public API with host buffers (every rank: its own volume / slab)
+    # the user's volume: a numpy bool array in page-locked memory (psb.pinned_empty); the result
+    # comes back as a fresh numpy float64 array (page-locked too) every call
+    lshape = shape if world == 1 else job.local_shape
+    im_host = psb.pinned_empty(lshape, np.bool_)
+    np.copyto(im_host, im.cpu().numpy().astype(bool).reshape(lshape))
+    # result bytes that cross PCIe: index bytes for the share widened by host threads, float64 for the rest
+    from porespy_b200 import _device as pdev
+    share = pdev.HOST_WIDEN_PERMILLE / 1000.0
+    h2d = im_host.nbytes * world
+    d2h = int(im_host.size * (share * 1 + (1.0 - share) * 8)) * world
+
+    def step_e2e():
+        if world == 1:
+            return psb.filters.local_thickness(im_host, sizes=SIZES)
+        return job.local_thickness(im_host, sizes=SIZES, to_host=True)
+
+    n_e2e = max(1, min(args.steps, args.e2e_steps))
+    res = step_e2e()      # warm-up
+    del res
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        res = step_e2e()
         del res
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            res = psb.filters.local_thickness(im_host, sizes=SIZES)
-            del res
-        torch.cuda.synchronize()
-        te = (time.perf_counter() - t0) / n_e2e
-        e2e = {"value": nvox / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3, "steps": n_e2e,
-               "api": "porespy_b200.filters.local_thickness(numpy bool, page-locked) -> numpy float64"}
-        del im_host
+    barrier()
+    te = (time.perf_counter() - t0) / n_e2e
+    if world > 1:
+        t = torch.tensor([te], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    api = ("porespy_b200.filters.local_thickness(numpy bool, page-locked) -> numpy float64" if world == 1 else
+           "ShardedVolume.local_thickness(numpy bool slab, page-locked, to_host=True) -> numpy float64 slab, every rank")
+    e2e = {"value": nvox / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3, "steps": n_e2e, "api": api,
+           "result": f"float64 map of {im_host.size * 8 * world} bytes in host memory; {pdev.HOST_WIDEN_PERMILLE / 10:.0f} % of "
+                     f"the volume leaves the device as 1-byte radius indices and is widened by the library's host "
+                     f"threads (psb200_expand_idx_f64_to_host)"}
+    del im_host
 
     if rank != 0:
         return

@@ -185,6 +185,18 @@ int psb200_lt_bitball(psb200_ctx *ctx, const uint32_t *seedbits, int64_t nz_src,
  * voxels with idx in [1, nlut) are written. */
 int psb200_expand_idx_f64(psb200_ctx *ctx, const uint8_t *idx, const double *lut_host,
                           int nlut, double *out, int64_t n, int flags, psb200_stream stream);
+/* The same map delivered into HOST memory (`return imresults`, F:1212) -- synchronous, returns when
+ * out_host[0, n) is complete.  The device holds one index byte per voxel, so the volume is split:
+ * the first cpu_permille/1000 of it crosses PCIe as index bytes (into stage_host, page-locked,
+ * stage_bytes >= that many voxels) and is widened to float64 by `nthreads` host threads of this
+ * library (table lookup only; 0 = all hardware threads); the rest is widened on the device into two
+ * chunk buffers carved from the device workspace `ws` and crosses PCIe as float64.  Both halves
+ * overlap.  cpu_permille = 0 (or stage_host NULL) selects the all-device path.  out_host should be
+ * page-locked for full PCIe speed; `idx` is produced on `stream`. */
+int psb200_expand_idx_f64_to_host(psb200_ctx *ctx, const uint8_t *idx, const double *lut_host,
+                                  int nlut, double *out_host, int64_t n, uint8_t *stage_host,
+                                  size_t stage_bytes, void *ws, size_t ws_bytes, int cpu_permille,
+                                  int nthreads, psb200_stream stream);
 /* idx[i] = out[i] != 0 ? PSB200_IDX_KEEP : 0   (continuation across >253 thresholds) */
 int psb200_mark_written(psb200_ctx *ctx, const double *out, uint8_t *idx, int64_t n,
                         psb200_stream stream);

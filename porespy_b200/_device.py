@@ -1,6 +1,7 @@
 """Thin device-side helpers: torch tensors are used only as device allocations and for the
 host<->device copies; every computation is a call into libpsb200.so."""
 import ctypes
+import os
 
 import numpy as np
 
@@ -68,38 +69,37 @@ def copy_stream(device):
     return _copy_streams[device]
 
 
-def expand_idx_to_host(ctx, idx, lut, shape, chunk=1 << 27):
+# share (per mille) of the volume whose radius index crosses PCIe as bytes and is widened to float64
+# by the library's host threads (psb200_expand_idx_f64_to_host); the rest is widened on the device.
+# Tuned on the B200 boxes of this pool (scripts/epilogue_probe.py); 0 = all-device path.
+HOST_WIDEN_PERMILLE = int(os.environ.get("PSB200_HOST_WIDEN_PERMILLE", "1000"))
+HOST_WIDEN_THREADS = int(os.environ.get("PSB200_HOST_WIDEN_THREADS", "0"))      # 0: all hardware threads
+
+
+def expand_idx_to_host(ctx, idx, lut, shape, chunk=1 << 26, cpu_permille=None, nthreads=None):
     """Radius-index map (uint8, device) -> float64 numpy in page-locked memory, without ever holding
-    the 8 B/voxel map in HBM: the LUT expansion (psb200_expand_idx_f64) runs chunk by chunk into two
-    device buffers while the previous chunk is on its way over PCIe on a second stream."""
+    the 8 B/voxel map in HBM (psb200_expand_idx_f64_to_host): part of the volume leaves the device
+    as index bytes and is widened by host threads of the library, the rest is widened on the
+    device chunk by chunk while the previous chunk is on its way over PCIe."""
     torch = _torch()
     n = idx.numel()
     if n * 8 < PIN_MIN_BYTES:
         out = torch.empty(n, dtype=torch.float64, device=idx.device)
         expand_idx(ctx, idx, lut, out)
         return out.cpu().numpy().reshape(shape)
+    cpu_permille = HOST_WIDEN_PERMILLE if cpu_permille is None else int(cpu_permille)
+    nthreads = HOST_WIDEN_THREADS if nthreads is None else int(nthreads)
     host = torch.empty(n, dtype=torch.float64, pin_memory=True)
-    main = torch.cuda.current_stream()
-    side = copy_stream(idx.device)
+    stage_n = (n * cpu_permille) // 1000
+    stage = torch.empty(max(stage_n, 1), dtype=torch.uint8, pin_memory=True)
     chunk = min(chunk, n)
-    bufs = [torch.empty(chunk, dtype=torch.float64, device=idx.device) for _ in range(2)]
-    done = [None, None]
-    for i, s in enumerate(range(0, n, chunk)):
-        e = min(n, s + chunk)
-        b = bufs[i & 1][:e - s]
-        if done[i & 1] is not None:
-            main.wait_event(done[i & 1])
-        expand_idx(ctx, idx[s:e], lut, b)
-        ready = torch.cuda.Event()
-        ready.record(main)
-        side.wait_event(ready)
-        with torch.cuda.stream(side):
-            host[s:e].copy_(b, non_blocking=True)
-            d = torch.cuda.Event()
-            d.record(side)
-        done[i & 1] = d
-    side.synchronize()
-    main.wait_stream(side)
+    ws = ctx.workspace(2 * chunk * 8 + 256)
+    lut = np.ascontiguousarray(lut, dtype=np.float64)
+    _lib.check(ctx.lib.psb200_expand_idx_f64_to_host(
+        ctx.handle, ptr(idx), lut.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(lut),
+        ctypes.c_void_p(host.data_ptr()), n, ctypes.c_void_p(stage.data_ptr()), stage.numel(),
+        ptr(ws), ws.numel(), cpu_permille, nthreads, stream_ptr()))
+    del stage
     return host.numpy().reshape(shape)
 
 

@@ -77,6 +77,8 @@ SIGNATURES = {
     "psb200_lt_wmask": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "psb200_lt_bitball": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _u32, _i64, _i64, _i64, _vp]),
     "psb200_expand_idx_f64": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _i32, _vp]),
+    "psb200_expand_idx_f64_to_host": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _vp, _sz,
+                                             _vp, _sz, _i32, _i32, _vp]),
     "psb200_mark_written": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "psb200_uf_begin": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _vp]),
     "psb200_uf_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),

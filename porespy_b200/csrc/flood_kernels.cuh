@@ -11,7 +11,17 @@
 //
 // In the porosimetry loop the seed sets are nested (class <= k grows with k), so the forest
 // is kept across radii: each radius only links the voxels that became seeds since the
-// previous radius (uf_activate) and then re-tests the not-yet-reached seeds (uf_mark).
+// previous radius (uf_activate).
+//
+// Join times.  Links are made between roots, so along any path to the root the radius index at
+// which each link was made never decreases, and the link INTO node 0 carries the index at which
+// the whole subtree became connected to the inlets.  That index is kept in jtime[] for the
+// children of node 0 (inlet voxels: 0), and path compression never bypasses a child of node 0.
+// The single-GPU loop therefore runs all activations first and reads the first radius at which
+// every voxel is a reached seed in ONE pass at the end (uf_resolve:  rcls = max(cls, jtime[top]))
+// instead of re-testing the unreached seeds after every radius; the step-level ABI of the
+// z-slab shards still marks per radius (uf_mark), because connectivity arrives through the slab
+// faces between radii.
 #pragma once
 #include "common.cuh"
 
@@ -39,14 +49,17 @@ __device__ __forceinline__ uint32_t uf_find(uint32_t *parent, uint32_t x)
     while (p != x) {
         const uint32_t gp = vp[p];
         if (gp == p) return p;         // p is the root
-        vp[x] = gp;                    // path halving (benign race: gp is always an ancestor, gp < x)
+        if (gp != 0u) vp[x] = gp;      // path halving (benign race: gp is always an ancestor, gp < x);
+                                       // a child of node 0 is never bypassed: it holds the join time
         x = gp;
         p = vp[x];
     }
     return x;
 }
 
-__device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t b)
+// jtime != NULL: a root that is hung under node 0 records the radius index k of that event.
+__device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t b,
+                                         uint8_t *jtime = nullptr, int k = 0)
 {
     while (true) {
         a = uf_find(parent, a);
@@ -54,6 +67,9 @@ __device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t 
         if (a == b) return;
         if (a < b) { const uint32_t t = a; a = b; b = t; }     // a > b: hang a under b
         const uint32_t old = atomicMin(&parent[a], b);
+        // a hangs under node 0 from now on (also when it lost a race against a link made in the
+        // same launch -- atomicMin then still lowered parent[a] from `old` to 0): note the step
+        if (jtime && b == 0u && old != 0u) jtime[a] = (uint8_t)k;
         if (old == a) return;                                   // a was still a root: linked
         a = old;                                                // lost a race: retry from its new parent
     }
@@ -79,59 +95,84 @@ uf_init_kernel(uint32_t *__restrict__ parent, InletSpec inl, int nz, int ny, int
 //   uf_union_list_kernel : every listed voxel is linked to its active neighbours (active: inlet
 //                          or cls <= khi).  conn: 6 (faces) or 26 (faces+edges+corners); with
 //                          nz == 1 these are 4- and 8-connectivity.
+// Redundant links are skipped: a y or z face pair (v, u) whose left neighbours (v-1, u-1) are
+// both active is already connected through  v ~ v-1 ~ u-1 ~ u  (x links are always made, and
+// the pair (v-1, u-1) is linked or skipped by the same rule: induction along the row, started
+// by the first pair of every common run).  Only about one y/z link per pair of touching runs
+// is left, instead of one per voxel.
 __global__ void __launch_bounds__(256)
 uf_collect_kernel(const uint8_t *__restrict__ cls, int klo, int khi, int64_t v0, int64_t v1,
                   uint32_t *__restrict__ list, uint32_t *__restrict__ count)
 {
-    const int lane = lane_id();
-    const int64_t ngroups = (v1 - v0 + 15) / 16;
-    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    // A block takes 256 x 64 consecutive voxels per round and reserves its list range with ONE
+    // atomicAdd (a per-warp reservation serialises ~2M same-address atomics per radius at 1024^3).
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t block_base;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int64_t per_block = 256 * 64;
+    const int64_t nrounds = (v1 - v0 + per_block - 1) / per_block;
     const bool aligned = (((uintptr_t)(cls + v0)) & 15u) == 0;
-    // warp-uniform trip count: every lane takes part in the scan below
-    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); g0 < ngroups; g0 += step) {
-        const int64_t g = g0 + lane;
-        const int64_t v = v0 + 16 * g;
-        uint32_t mask = 0;
-        if (g < ngroups) {
-            if (aligned && v + 16 <= v1) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(cls + v));
-                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    for (int64_t r = blockIdx.x; r < nrounds; r += gridDim.x) {
+        // thread t owns the 16-voxel groups t, t + 256, t + 512, t + 768 of the round (coalesced loads)
+        uint32_t mask[4];
+        int cnt = 0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = (int)byte_of(w[i >> 2], i & 3);
-                    if (c > klo && c <= khi) mask |= 1u << i;
-                }
-            } else {
-                for (int i = 0; i < 16 && v + i < v1; ++i) {
-                    const int c = (int)cls[v + i];
-                    if (c > klo && c <= khi) mask |= 1u << i;
+        for (int q = 0; q < 4; ++q) {
+            const int64_t v = v0 + r * per_block + ((int64_t)q * 256 + threadIdx.x) * 16;
+            uint32_t m = 0;
+            if (v < v1) {
+                if (aligned && v + 16 <= v1) {
+                    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(cls + v));
+                    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = (int)byte_of(w[i >> 2], i & 3);
+                        if (c > klo && c <= khi) m |= 1u << i;
+                    }
+                } else {
+                    for (int i = 0; i < 16 && v + i < v1; ++i) {
+                        const int c = (int)cls[v + i];
+                        if (c > klo && c <= khi) m |= 1u << i;
+                    }
                 }
             }
+            mask[q] = m;
+            cnt += __popc(m);
         }
-        const int cnt = __popc(mask);
         int incl = cnt;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
             if (lane >= off) incl += t;
         }
-        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        if (total == 0) continue;
-        uint32_t base = 0;
-        if (lane == 31) base = atomicAdd(count, (uint32_t)total);
-        base = __shfl_sync(0xFFFFFFFFu, base, 31) + (uint32_t)(incl - cnt);
-        while (mask) {
-            const int i = __ffs(mask) - 1;
-            mask &= mask - 1;
-            list[base++] = (uint32_t)(v + i);
+        if (lane == 31) warp_tot[warp] = (uint32_t)incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const uint32_t t = warp_tot[w]; warp_tot[w] = tot; tot += t; }
+            block_base = tot ? atomicAdd(count, tot) : 0u;
         }
+        __syncthreads();
+        uint32_t base = block_base + warp_tot[warp] + (uint32_t)(incl - cnt);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t v = v0 + r * per_block + ((int64_t)q * 256 + threadIdx.x) * 16;
+            uint32_t m = mask[q];
+            while (m) {
+                const int i = __ffs(m) - 1;
+                m &= m - 1;
+                list[base++] = (uint32_t)(v + i);
+            }
+        }
+        __syncthreads();                                   // warp_tot / block_base are reused next round
     }
 }
 
 __global__ void __launch_bounds__(256)
 uf_union_list_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpec inl, int klo, int khi,
                      int conn, int nz, int ny, int nx, const uint32_t *__restrict__ list,
-                     const uint32_t *__restrict__ count)
+                     const uint32_t *__restrict__ count, uint8_t *jtime)
 {
     const int ndir = conn == 6 ? 6 : 26;
     const int64_t jobs = (int64_t)(*count) * ndir;
@@ -158,7 +199,12 @@ uf_union_list_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpe
         if (cu > klo && cu <= khi) {
             if (u > (int64_t)v) continue;              // both new: the pair is linked once, from the larger index
         } else if (!(cu <= khi || is_inlet(inl, u, zz, yy, xx, nz, ny, nx))) continue;
-        uf_union(parent, v + 1u, (uint32_t)(u + 1));
+        if (dx == 0 && (dy == 0) != (dz == 0) && x > 0) {
+            // y / z face pair: redundant when the pair one step to the left is active too
+            const bool lv = (int)cls[v - 1u] <= khi || is_inlet(inl, (int64_t)v - 1, z, y, x - 1, nz, ny, nx);
+            if (lv && ((int)cls[u - 1] <= khi || is_inlet(inl, u - 1, zz, yy, x - 1, nz, ny, nx))) continue;
+        }
+        uf_union(parent, v + 1u, (uint32_t)(u + 1), jtime, khi);
     }
 }
 
@@ -222,6 +268,49 @@ uf_mark_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, uint8_t *__res
     }
     if (__any_sync(0xFFFFFFFFu, any) && lane_id() == 0 && *((volatile int *)gate) == 0) *gate = 1;
 }
+
+// One pass after the last activation (single-GPU loop):  rcls[v] = first radius index at which v
+// is a seed connected to the inlets = max(cls[v], jtime[top]) where top is the child of node 0
+// on v's path (see "Join times" above); CLS_NEVER for seeds whose tree never joined node 0.
+// *kmin receives the smallest value written (the first radius with any reached seed).
+// One thread per voxel: the lanes of a warp hold 32 consecutive voxels, which almost always sit
+// in the same tree, so the walk of a warp is one chain of broadcast loads rather than 32 chains.
+__global__ void __launch_bounds__(256)
+uf_resolve_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, const uint8_t *__restrict__ jtime,
+                  uint8_t *__restrict__ rcls, int64_t n, int *kmin)
+{
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    volatile uint32_t *vp = parent;
+    uint32_t lmin = 255u;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += step) {
+        const uint32_t c = cls[v];
+        uint32_t r = c == CLS_BG ? CLS_BG : CLS_NEVER;      // background stays background
+        if (c < CLS_NEVER) {
+            const uint32_t self = (uint32_t)(v + 1);
+            uint32_t x = self, p = vp[x], top = 0u;         // top: child of node 0 on the path, 0: none
+            int hops = 0;
+            while (true) {
+                if (p == 0u) { top = x; break; }
+                if (p == x) break;                          // a root other than node 0: not connected
+                x = p;
+                p = vp[x];
+                ++hops;
+            }
+            if (hops > 1) vp[self] = x;                     // compress (top or the stranded root)
+            if (top != 0u) {
+                r = max(c, (uint32_t)jtime[top]);
+                lmin = min(lmin, r);
+            }
+        }
+        rcls[v] = (uint8_t)r;
+    }
+    lmin = __reduce_min_sync(0xFFFFFFFFu, lmin);
+    if (lane_id() == 0 && lmin < 255u) atomicMin(kmin, (int)lmin);
+}
+
+// *gate = 1 once the radius index k has any reached seed (the per-radius kernels return at once
+// while it is 0: F:1184 skips a radius without seeds)
+__global__ void uf_gate_kernel(int *gate, const int *__restrict__ kmin, int k) { *gate = *kmin <= k ? 1 : 0; }
 
 // ---- z-slab shards: the union-find is slab-local; connectivity through a slab face travels as
 // one byte per face voxel ("this node is connected to the inlets") and is injected on the

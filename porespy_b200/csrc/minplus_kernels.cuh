@@ -82,8 +82,9 @@ template <typename Src, int OUT>
 __global__ void __launch_bounds__(MP_WARPS * 32)
 edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ dst, int n,
                    int64_t rstride, int64_t nxc, int64_t ostride, int L, int H, int vec,
-                   uint32_t *__restrict__ gmax, int split)
+                   uint32_t *__restrict__ gmax, int split, const int *__restrict__ gate)
 {
+    if (gate && *gate == 0) return;        // the 16-bit form of the pass (below) resolved every voxel
     extern __shared__ uint4 mp_tile[];                     // [roundup4(L) + 2H][32]
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int nrt = (n + L - 1) / L;
@@ -221,6 +222,189 @@ edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ d
     if (gmax) {
         lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
         if (lane == 0 && lmax) atomicMax(gmax, min(lmax, MP_INF));
+    }
+}
+
+// ------------------------------------------------- EDT pass, two voxels per instruction
+// The same bounded scan with 16-bit lanes (VIADDMNMX.U16x2: half the issue slots and half the
+// shared-memory bytes per voxel).  Values and offsets are capped at MP16_CAP = 32767, so a sum
+// never wraps, and a result below the cap is exact: its minimising candidate has value and
+// offset below the cap (represented exactly), and every other candidate's capped sum is
+// >= min(its true sum, cap).  A result >= cap (a voxel 181+ voxels away from the background
+// along this and the previous axes -- never on porous media) raises *overflow, and the
+// uint32 kernel above, launched right behind on the same stream and gated on that flag,
+// recomputes the pass.
+#define MP16_CAP 0x7FFFu
+#define MP16_WARPS 8
+
+__device__ __forceinline__ uint2 mp16_pack(const uint4 &v)
+{
+    return make_uint2(min(v.x, MP16_CAP) | (min(v.y, MP16_CAP) << 16),
+                      min(v.z, MP16_CAP) | (min(v.w, MP16_CAP) << 16));
+}
+__device__ __forceinline__ uint32_t mp16_off(int d) { return min((uint32_t)(d * d), MP16_CAP) * 0x00010001u; }
+
+// grid / tile geometry as edt_minplus_kernel; dyn smem = rows * 256 + (H + 2) * 16 bytes.
+template <typename Src, int OUT>
+__global__ void __launch_bounds__(MP16_WARPS * 32)
+edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__ dst, int n,
+                     int64_t rstride, int64_t nxc, int64_t ostride, int L, int H, int vec,
+                     uint32_t *__restrict__ gmax, int split, int *__restrict__ overflow)
+{
+    extern __shared__ uint4 mp16_smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
+    const int nrt = (n + L - 1) / L;
+    const int row0 = (int)(blockIdx.x % nrt) * L;
+    const int64_t x0 = (int64_t)(blockIdx.x / nrt) * MP_TX;
+    const int64_t valid = nxc - x0;
+    const typename Src::T *sbase = src + (int64_t)blockIdx.y * ostride + x0;
+    const int Lr = (L + 3) & ~3;
+    const int rows = Lr + 2 * H;
+    uint2 *tile = reinterpret_cast<uint2 *>(mp16_smem);                   // [rows][32]: 4 x u16 per entry
+    uint4 *offt = reinterpret_cast<uint4 *>(tile + (size_t)rows * 32);    // [H + 2]: packed capped (d + i)^2, i = 0..3
+    for (int d = tid; d < H + 2; d += MP16_WARPS * 32)
+        offt[d] = make_uint4(mp16_off(d), mp16_off(d + 1), mp16_off(d + 2), mp16_off(d + 3));
+    const uint4 INF4 = make_uint4(MP_INF, MP_INF, MP_INF, MP_INF);
+    for (int r0 = warp; r0 < rows; r0 += 4 * MP16_WARPS) {                // 4 independent row loads in flight
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + i * MP16_WARPS, gr = row0 - H + r;
+            v[i] = INF4;
+            if (r < rows && gr >= 0 && gr < n) v[i] = mp_load_row<Src>(sbase + (int64_t)gr * rstride, 4 * lane, valid, vec);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + i * MP16_WARPS;
+            if (r < rows) tile[r * 32 + lane] = mp16_pack(v[i]);
+        }
+    }
+    __syncthreads();
+
+    // A lane owns 4 rows x 4 columns; warp footprint 64 columns x 8 rows (16 column groups x 2 row
+    // blocks: every half-warp reads 128 contiguous bytes of one tile row).  Block: 2 warps across x, 4 down.
+    uint32_t lmax = 0;
+    bool ovf = false;
+    const int cq = (warp & 1) * 16 + (lane & 15);
+    const int xl = 4 * cq;
+    for (int ry = ((warp >> 1) * 2 + (lane >> 4)) * 4; ry < L; ry += 32) {
+        const int gr = row0 + ry;
+        if (gr >= n) break;
+        const int rr = ry + H;
+        uint2 O[4];
+        uint32_t B0[4], B1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) O[i] = tile[(rr + i) * 32 + cq];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            B0[i] = O[i].x;
+            B1[i] = O[i].y;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j != i) {
+                    const uint32_t d = (uint32_t)((i - j) * (i - j)) * 0x00010001u;
+                    B0[i] = __viaddmin_u16x2(O[j].x, d, B0[i]);
+                    B1[i] = __viaddmin_u16x2(O[j].y, d, B1[i]);
+                }
+            if (gr + i >= n) B0[i] = B1[i] = 0u;                         // rows past the end: nothing to do
+        }
+        const int dlim = min(min(rr, rows - 1 - (rr + 3)), H);
+        int dy = 1;
+        bool done = false;
+        // fast loop: both fetched rows are inside the staged tile (rows outside the volume hold the cap);
+        // two steps per termination test (a step past the bound only relaxes with valid candidates)
+        while (dy <= dlim) {
+            const uint32_t m2 = __vmaxu2(__vmaxu2(__vmaxu2(B0[0], B1[0]), __vmaxu2(B0[1], B1[1])),
+                                         __vmaxu2(__vmaxu2(B0[2], B1[2]), __vmaxu2(B0[3], B1[3])));
+            const uint32_t bm = max(m2 & 0xFFFFu, m2 >> 16);
+            if ((uint32_t)(dy * dy) >= bm) { done = true; break; }
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                if (dy > dlim) break;
+                const uint2 top = tile[(rr - dy) * 32 + cq];
+                const uint2 bot = tile[(rr + 3 + dy) * 32 + cq];
+                const uint4 o4 = offt[dy];
+                const uint32_t of[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    B0[i] = __viaddmin_u16x2(top.x, of[i], B0[i]); B1[i] = __viaddmin_u16x2(top.y, of[i], B1[i]);
+                    B0[i] = __viaddmin_u16x2(bot.x, of[3 - i], B0[i]); B1[i] = __viaddmin_u16x2(bot.y, of[3 - i], B1[i]);
+                }
+                ++dy;
+            }
+        }
+        // slow loop (rare): rows beyond the staged halo come from global memory
+        while (!done) {
+            const uint32_t m2 = __vmaxu2(__vmaxu2(__vmaxu2(B0[0], B1[0]), __vmaxu2(B0[1], B1[1])),
+                                         __vmaxu2(__vmaxu2(B0[2], B1[2]), __vmaxu2(B0[3], B1[3])));
+            const uint32_t bm = max(m2 & 0xFFFFu, m2 >> 16);
+            const bool up_in = gr - dy >= 0, dn_in = gr + 3 + dy < n;
+            if ((uint32_t)dy * (uint32_t)dy >= bm || (!up_in && !dn_in)) break;
+            const uint32_t of[4] = {mp16_off(dy), mp16_off(dy + 1), mp16_off(dy + 2), mp16_off(dy + 3)};
+            if (up_in) {
+                const uint2 top = (rr - dy >= 0) ? tile[(rr - dy) * 32 + cq]
+                                                 : mp16_pack(mp_load_row<Src>(sbase + (int64_t)(gr - dy) * rstride, xl, valid, vec));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    B0[i] = __viaddmin_u16x2(top.x, of[i], B0[i]); B1[i] = __viaddmin_u16x2(top.y, of[i], B1[i]);
+                }
+            }
+            if (dn_in) {
+                const int rb = rr + 3 + dy;
+                const uint2 bot = (rb < rows) ? tile[rb * 32 + cq]
+                                              : mp16_pack(mp_load_row<Src>(sbase + (int64_t)(gr + 3 + dy) * rstride, xl, valid, vec));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    B0[i] = __viaddmin_u16x2(bot.x, of[3 - i], B0[i]); B1[i] = __viaddmin_u16x2(bot.y, of[3 - i], B1[i]);
+                }
+            }
+            ++dy;
+        }
+        // ---- store the block
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int g = gr + i;
+            if (g >= n || ry + i >= L) continue;
+            int64_t oi = (int64_t)blockIdx.y * ostride + x0 + (int64_t)g * rstride + xl;
+            if (split > 0) {
+                // y pass of a z-slab: all-to-all send layout [dest d][z][y - d*split][x]
+                const int d = g / split, yy = g - d * split;
+                const int nyd = min(split, n - d * split);
+                oi = ((int64_t)d * split * gridDim.y + (int64_t)blockIdx.y * nyd + yy) * rstride + x0 + xl;
+            }
+            const uint32_t o[4] = {B0[i] & 0xFFFFu, B0[i] >> 16, B1[i] & 0xFFFFu, B1[i] >> 16};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (xl + j < valid) {
+                    lmax = max(lmax, o[j]);
+                    ovf |= o[j] >= MP16_CAP;
+                }
+            if (OUT == 0) {
+                uint32_t *orow = reinterpret_cast<uint32_t *>(dst) + oi;
+                if (vec && xl + 3 < valid) *reinterpret_cast<uint4 *>(orow) = make_uint4(o[0], o[1], o[2], o[3]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (xl + j < valid) orow[j] = o[j];
+                }
+            } else {
+                float *orow = reinterpret_cast<float *>(dst) + oi;
+                float f[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f[j] = sqrtf((float)o[j]);
+                if (vec && xl + 3 < valid) *reinterpret_cast<float4 *>(orow) = make_float4(f[0], f[1], f[2], f[3]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (xl + j < valid) orow[j] = f[j];
+                }
+            }
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, ovf) && lane == 0) *overflow = 1;
+    if (gmax) {
+        lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
+        if (lane == 0 && lmax) atomicMax(gmax, lmax);
     }
 }
 

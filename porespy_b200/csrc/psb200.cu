@@ -734,7 +734,7 @@ extern "C" int psb200_lt_z(psb200_ctx *ctx, uint8_t *reach, const uint8_t *m_lo,
 
 static int uf_activate_impl(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const InletSpec &inl, int klo,
                             int khi, int conn, int64_t nz, int64_t ny, int64_t nx, uint32_t *list,
-                            cudaStream_t st)
+                            cudaStream_t st, uint8_t *jtime = nullptr)
 {
     const int64_t n = nz * ny * nx;
     uint32_t *count = list;                 // entry 0..15: the counter, the list starts at entry 16
@@ -744,14 +744,14 @@ static int uf_activate_impl(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cl
         CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint32_t), st));
         {
             ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-            uf_collect_kernel<<<grid_for((v1 - v0 + 15) / 16, 256, ctx->sm_count, 16), 256, 0, st>>>(
+            uf_collect_kernel<<<grid_for((v1 - v0 + 63) / 64, 256, ctx->sm_count, 8), 256, 0, st>>>(
                 cls, klo, khi, v0, v1, items, count);
         }
         LAUNCH_CHECK(ctx);
         {
             ProfScope ps__(ctx, st, K_UF_ACTIVATE);
             uf_union_list_kernel<<<ctx->sm_count * 16, 256, 0, st>>>(parent, cls, inl, klo, khi, conn, (int)nz,
-                                                                     (int)ny, (int)nx, items, count);
+                                                                     (int)ny, (int)nx, items, count, jtime);
         }
         LAUNCH_CHECK(ctx);
     }
@@ -925,15 +925,28 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
     InletSpec inl{inlet_mode, ndim, inlets, 0, (int)nz};
     const int g = grid_for(n, 256, ctx->sm_count, 16);
     if (al) {
+        // F:1181-1183 for every radius at once: the seed sets are nested, so the union-find links
+        // the voxels of class k at step k and keeps, for every tree that joins the inlets, the step
+        // at which it did (jtime, in the reach buffer: the dilation passes only start afterwards);
+        // one resolve pass then yields  rcls = first radius at which the voxel is a reached seed.
+        uint8_t *jtime = w.reach;
+        int *kmin = w.gate + 1;
         CUDA_TRY(cudaMemsetAsync(w.gate, 0, sizeof(int), st));
-        {
-            ProfScope ps__(ctx, st, K_UF_INIT);
-            uf_rcls_init_kernel<<<g, 256, 0, st>>>(w.cls, w.rcls, n);
-        }
-        LAUNCH_CHECK(ctx);
+        CUDA_TRY(cudaMemsetAsync(kmin, 0x7F, sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(jtime, 0, (size_t)n + 1, st));
         {
             ProfScope ps__(ctx, st, K_UF_INIT);
             uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx);
+        }
+        LAUNCH_CHECK(ctx);
+        for (int k = 0; k < nT; ++k) {
+            rc = uf_activate_impl(ctx, w.parent, w.cls, inl, k - 1, k, 6, nz, ny, nx, w.uf_list, st, jtime);
+            if (rc) return rc;
+        }
+        {
+            ProfScope ps__(ctx, st, K_UF_MARK);
+            uf_resolve_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(
+                w.parent, w.cls, jtime, w.rcls, n, kmin);
         }
         LAUNCH_CHECK(ctx);
     }
@@ -945,8 +958,8 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
     for (int k = 0; k < nT; ++k) {
         const uint32_t T = T_host[k];
         if (al) {
-            rc = uf_step(ctx, w, inl, k - 1, k, 6, nz, ny, nx, st);
-            if (rc) return rc;
+            uf_gate_kernel<<<1, 1, 0, st>>>(w.gate, w.gate + 1, k);
+            LAUNCH_CHECK(ctx);
         }
         if (bit_ok && T <= (uint32_t)ctx->bit_tmax) {
             // small radii: bit-parallel ball dilation (thresholds descend: every later radius too)
@@ -1027,6 +1040,34 @@ extern "C" int psb200_expand_idx_f64(psb200_ctx *ctx, const uint8_t *idx, const 
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
+}
+
+// ---- host-result epilogue (host_epilogue.cuh)
+#include "host_epilogue.cuh"
+static HostEpilogueStreams g_epilogue_streams[64];         // per device, created on first use
+
+static int launch_expand_chunk(psb200_ctx *ctx, const uint8_t *idx, const double *lut_host, int nlut, double *out,
+                               int64_t n, cudaStream_t st)
+{
+    return psb200_expand_idx_f64(ctx, idx, lut_host, nlut, out, n, 0, (psb200_stream)st);
+}
+
+extern "C" int psb200_expand_idx_f64_to_host(psb200_ctx *ctx, const uint8_t *idx, const double *lut_host, int nlut,
+                                             double *out_host, int64_t n, uint8_t *stage_host, size_t stage_bytes,
+                                             void *ws, size_t ws_bytes, int cpu_permille, int nthreads,
+                                             psb200_stream stream)
+{
+    if (!ctx || !idx || !lut_host || !out_host || nlut < 1 || nlut > 254 || n < 0)
+        return fail(PSB200_ERR_INVALID, "expand_idx_f64_to_host: bad argument");
+    if (cpu_permille < 0 || cpu_permille > 1000 || nthreads < 0 || nthreads > 1024)
+        return fail(PSB200_ERR_INVALID, "expand_idx_f64_to_host: cpu_permille must be in [0,1000], nthreads in [0,1024]");
+    if (ctx->device < 0 || ctx->device >= 64) return fail(PSB200_ERR_UNSUPPORTED, "expand_idx_f64_to_host: device index");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (nthreads == 0) nthreads = (int)std::thread::hardware_concurrency();
+    return host_epilogue_run(ctx, g_epilogue_streams[ctx->device], idx, lut_host, nlut, out_host, n, stage_host,
+                             stage_bytes, ws, ws_bytes, cpu_permille, nthreads, (cudaStream_t)stream,
+                             launch_expand_chunk);
 }
 
 extern "C" int psb200_mark_written(psb200_ctx *ctx, const double *out, uint8_t *idx, int64_t n,

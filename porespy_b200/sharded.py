@@ -131,6 +131,13 @@ class CudaBackend:
         dev.expand_idx(self.ctx, idx, lut, out)
         return out
 
+    def expand_to_host(self, idx, lut, shape, world):
+        """float64 slab in (page-locked) host memory; the host threads of the box are shared by the
+        ranks, so each rank widens its share of index bytes with cpu_count/world of them."""
+        import os
+        threads = max(1, (os.cpu_count() or 1) // max(1, world))
+        return dev.expand_idx_to_host(self.ctx, idx, lut, shape, nthreads=threads)
+
     # -- access-limited flooding (slab-local union-find + face flags, psb200_uf_*)
     def uf_begin(self, cls, inlets_u8, shape, z0, nz_global):
         nz, ny, nx = shape
@@ -306,15 +313,16 @@ class ShardedVolume:
         return out.view(self.nzl, self.shape[1], self.shape[2])
 
     # --------------------------------------------------------------------- radius loop
-    def local_thickness(self, local_im, sizes=25):
-        """ps.filters.local_thickness of the GLOBAL volume; returns this rank's slab (float64)."""
-        return self._porosimetry(local_im, sizes, access_limited=False)
+    def local_thickness(self, local_im, sizes=25, to_host=False):
+        """ps.filters.local_thickness of the GLOBAL volume; returns this rank's slab (float64):
+        a device tensor, or with `to_host` a numpy array (the reference's return type)."""
+        return self._porosimetry(local_im, sizes, access_limited=False, to_host=to_host)
 
-    def porosimetry(self, local_im, sizes=25, inlets=None, access_limited=True):
+    def porosimetry(self, local_im, sizes=25, inlets=None, access_limited=True, to_host=False):
         """ps.filters.porosimetry of the GLOBAL volume (F:1032-1212); returns this rank's slab.
         `inlets`: None = all faces of the global volume (F:1128-1129), else this rank's slab
         [nzl][ny][nx] of the global inlet mask."""
-        return self._porosimetry(local_im, sizes, access_limited=access_limited, inlets=inlets)
+        return self._porosimetry(local_im, sizes, access_limited=access_limited, inlets=inlets, to_host=to_host)
 
     def _flood_exchange(self, st, k):
         """Propagate inlet connectivity through the slab faces until no rank learns anything new
@@ -338,7 +346,7 @@ class ShardedVolume:
             if not self._allreduce_max(be.uf_changed(st)):
                 return sweeps
 
-    def _porosimetry(self, local_im, sizes, access_limited, inlets=None):
+    def _porosimetry(self, local_im, sizes, access_limited, inlets=None, to_host=False):
         torch, be = self.torch, self.backend
         nz, ny, nx = self.shape
         nzl = self.nzl
@@ -405,4 +413,6 @@ class ShardedVolume:
                 be.lt_z(reach, m_lo, m_hi, idx, k, Tk, lshape)
                 del reach
         lut = np.concatenate([[0.0], R])
+        if to_host and hasattr(be, "expand_to_host"):
+            return be.expand_to_host(idx, lut, lshape, self.world)
         return be.expand(idx, lut).view(*lshape)

@@ -352,3 +352,21 @@ def test_flood_face_exchange_one_gpu(psb, nslabs):
             want = oc.trim_disconnected_blobs(seeds, inlets_full, strel=oc._cross(3))
             got = np.concatenate([(st.rcls.cpu().numpy().reshape(st.shape) <= k) for st in sts], axis=0)
             assert_same(got, want, f"reached seeds, inlets={inl_kind}, k={k}, T={Tk}, {sweeps} sweeps")
+
+
+@pytest.mark.parametrize("permille,threads", [(0, 0), (500, 3), (1000, 0), (730, 16)])
+def test_host_epilogue_split(psb, permille, threads):
+    """psb200_expand_idx_f64_to_host: any split between host-thread widening of index bytes and
+    device-side widening gives the same float64 map (odd length: partial chunks, unaligned tail)."""
+    import torch
+    from porespy_b200 import _device as dev
+    from porespy_b200 import _lib
+    ctx = _lib.context()
+    n = 3 * (1 << 24) + 12345
+    g = torch.Generator(device="cuda")
+    g.manual_seed(permille)
+    idx = torch.randint(0, 40, (n,), generator=g, device="cuda", dtype=torch.uint8)
+    lut = np.concatenate([[0.0], np.sort(np.random.default_rng(1).uniform(1, 50, 39))[::-1]])
+    out = dev.expand_idx_to_host(ctx, idx, lut, (n,), cpu_permille=permille, nthreads=threads, chunk=1 << 22)
+    assert out.dtype == np.float64 and out.shape == (n,)
+    assert np.array_equal(out, lut[idx.cpu().numpy()])
