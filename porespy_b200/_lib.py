@@ -138,6 +138,11 @@ class Context:
         """Thresholds T <= tmax run the bit-parallel dilation kernels (0 = never)."""
         check(self.lib.psb200_set_option(self.handle, b"bit_tmax", int(tmax)))
 
+    def set_edt16(self, on):
+        """EDT y/z passes: run the 16-bit two-voxels-per-instruction kernel first (default); off =
+        the uint32 kernel only."""
+        check(self.lib.psb200_set_option(self.handle, b"edt16", 1 if on else 0))
+
     def set_profile(self, on):
         check(self.lib.psb200_set_option(self.handle, b"profile", 1 if on else 0))
 

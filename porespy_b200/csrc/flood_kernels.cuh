@@ -25,6 +25,8 @@
 #pragma once
 #include "common.cuh"
 
+#define UF_TIME_UNSET 0xFFu   // jtime of a node that never hung directly under node 0
+
 struct InletSpec {
     int mode;                 // 1 = faces predicate, 2 = mask
     int ndim;                 // dimensionality of the squeezed image (faces predicate)
@@ -42,41 +44,61 @@ __device__ __forceinline__ bool is_inlet(const InletSpec &s, int64_t v, int z, i
     return true;
 }
 
-__device__ __forceinline__ uint32_t uf_find(uint32_t *parent, uint32_t x)
+// Root of x, with path halving.  Node 0 is never read (it is the root of everything that reaches
+// it): parent[0] and the few children of node 0 that carry whole percolating clusters would
+// otherwise be fetched by every find of every launch -- one L2 slice serialising the kernel.
+// With join times (jtime != NULL) a node is re-pointed from a child p of node 0 to node 0 itself
+// only together with p's join time.  A time is written (once, or by several threads with the same
+// value) just before the link that makes it meaningful; no fence orders the two, so a reader that
+// sees the link but still the UF_TIME_UNSET sentinel simply does not re-point.
+__device__ __forceinline__ uint32_t uf_find(uint32_t *parent, uint32_t x, uint8_t *jtime = nullptr)
 {
+    if (x == 0u) return 0u;
     volatile uint32_t *vp = parent;
     uint32_t p = vp[x];
     while (p != x) {
+        if (p == 0u) return 0u;
         const uint32_t gp = vp[p];
         if (gp == p) return p;         // p is the root
-        if (gp != 0u) vp[x] = gp;      // path halving (benign race: gp is always an ancestor, gp < x);
-                                       // a child of node 0 is never bypassed: it holds the join time
+        if (gp == 0u) {                // p is a child of node 0: x joins node 0 directly
+            if (jtime) {
+                const uint8_t t = reinterpret_cast<volatile uint8_t *>(jtime)[p];
+                if (t == UF_TIME_UNSET) return 0u;      // p's time is not visible yet: leave x where it is
+                reinterpret_cast<volatile uint8_t *>(jtime)[x] = t;
+            }
+            vp[x] = 0u;
+            return 0u;
+        }
+        vp[x] = gp;                    // path halving (benign race: gp is always an ancestor, gp < x)
         x = gp;
         p = vp[x];
     }
     return x;
 }
 
-// jtime != NULL: a root that is hung under node 0 records the radius index k of that event.
+// jtime != NULL: a node that is hung under node 0 records the radius index k of that event
+// (written before the link, see uf_find).
 __device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t b,
                                          uint8_t *jtime = nullptr, int k = 0)
 {
     while (true) {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
+        a = uf_find(parent, a, jtime);
+        b = uf_find(parent, b, jtime);
         if (a == b) return;
         if (a < b) { const uint32_t t = a; a = b; b = t; }     // a > b: hang a under b
+        if (jtime && b == 0u) {
+            // a was a root a moment ago, so if it hangs under node 0 already that happened in this
+            // launch (same k); atomicMin lowers parent[a] to 0 whether or not a is still a root
+            reinterpret_cast<volatile uint8_t *>(jtime)[a] = (uint8_t)k;
+        }
         const uint32_t old = atomicMin(&parent[a], b);
-        // a hangs under node 0 from now on (also when it lost a race against a link made in the
-        // same launch -- atomicMin then still lowered parent[a] from `old` to 0): note the step
-        if (jtime && b == 0u && old != 0u) jtime[a] = (uint8_t)k;
         if (old == a) return;                                   // a was still a root: linked
         a = old;                                                // lost a race: retry from its new parent
     }
 }
 
 __global__ void __launch_bounds__(256)
-uf_init_kernel(uint32_t *__restrict__ parent, InletSpec inl, int nz, int ny, int nx)
+uf_init_kernel(uint32_t *__restrict__ parent, InletSpec inl, int nz, int ny, int nx, uint8_t *__restrict__ jtime)
 {
     const int64_t n = (int64_t)nz * ny * nx;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
@@ -84,7 +106,9 @@ uf_init_kernel(uint32_t *__restrict__ parent, InletSpec inl, int nz, int ny, int
         const int x = (int)(v % nx);
         const int64_t t = v / nx;
         const int y = (int)(t % ny), z = (int)(t / ny);
-        parent[v + 1] = is_inlet(inl, v, z, y, x, nz, ny, nx) ? 0u : (uint32_t)(v + 1);
+        const bool in = is_inlet(inl, v, z, y, x, nz, ny, nx);
+        parent[v + 1] = in ? 0u : (uint32_t)(v + 1);
+        if (jtime) jtime[v + 1] = in ? 0 : UF_TIME_UNSET;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) parent[0] = 0u;
 }
@@ -204,7 +228,20 @@ uf_union_list_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpe
             const bool lv = (int)cls[v - 1u] <= khi || is_inlet(inl, (int64_t)v - 1, z, y, x - 1, nz, ny, nx);
             if (lv && ((int)cls[u - 1] <= khi || is_inlet(inl, u - 1, zz, yy, x - 1, nz, ny, nx))) continue;
         }
-        uf_union(parent, v + 1u, (uint32_t)(u + 1), jtime, khi);
+        int64_t w = u;
+        if (dx == -1 && dy == 0 && dz == 0 && cu > klo && cu <= khi) {
+            // left neighbour activated in this launch too: link to the first voxel of the run of new
+            // voxels instead (every voxel of the run does), so the run becomes a star, not a chain
+            // as long as the run (whose finds and the final resolve would then walk end to end)
+            int xs = xx;
+            for (int steps = 0; steps < 64 && xs > 0; ++steps) {
+                const int c = (int)cls[w - 1];
+                if (!(c > klo && c <= khi)) break;
+                --w;
+                --xs;
+            }
+        }
+        uf_union(parent, v + 1u, (uint32_t)(w + 1), jtime, khi);
     }
 }
 
@@ -238,7 +275,7 @@ uf_mark_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, uint8_t *__res
 #pragma unroll
             for (int i = 0; i < 16; ++i) p[i] = (cand >> i & 1u) ? vp[v + i + 1] : 0u;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) gp[i] = (cand >> i & 1u) ? vp[p[i]] : 0u;
+            for (int i = 0; i < 16; ++i) gp[i] = ((cand >> i & 1u) && p[i] != 0u) ? vp[p[i]] : 0u;   // node 0 is never read
             bool changed = false;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {

@@ -28,21 +28,22 @@
 // -------------------------------------------------------------------------- source formats
 struct MpSrcU16 {                 // x-pass distances; >= 0x8000: no site in the line
     typedef uint16_t T;
+    typedef uint2 Raw;            // 4 columns as loaded
     __device__ static __forceinline__ uint32_t sq(uint32_t d) { return d >= 0x8000u ? MP_INF : d * d; }
-    __device__ static __forceinline__ uint4 ld4(const uint16_t *p)
+    __device__ static __forceinline__ Raw ldraw(const uint16_t *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
+    __device__ static __forceinline__ uint4 cvt(const Raw &v)
     {
-        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
         return make_uint4(sq(v.x & 0xFFFFu), sq(v.x >> 16), sq(v.y & 0xFFFFu), sq(v.y >> 16));
     }
+    __device__ static __forceinline__ uint4 ld4(const uint16_t *p) { return cvt(ldraw(p)); }
 };
 struct MpSrcU32 {                 // squared distances; PSB_INF: infinite
     typedef uint32_t T;
+    typedef uint4 Raw;
     __device__ static __forceinline__ uint32_t sq(uint32_t v) { return min(v, MP_INF); }
-    __device__ static __forceinline__ uint4 ld4(const uint32_t *p)
-    {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
-        return make_uint4(sq(v.x), sq(v.y), sq(v.z), sq(v.w));
-    }
+    __device__ static __forceinline__ Raw ldraw(const uint32_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+    __device__ static __forceinline__ uint4 cvt(const Raw &v) { return make_uint4(sq(v.x), sq(v.y), sq(v.z), sq(v.w)); }
+    __device__ static __forceinline__ uint4 ld4(const uint32_t *p) { return cvt(ldraw(p)); }
 };
 
 // 4 consecutive columns starting at column x of a row with `valid` columns; columns beyond the
@@ -82,16 +83,23 @@ template <typename Src, int OUT>
 __global__ void __launch_bounds__(MP_WARPS * 32)
 edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ dst, int n,
                    int64_t rstride, int64_t nxc, int64_t ostride, int L, int H, int vec,
-                   uint32_t *__restrict__ gmax, int split, const int *__restrict__ gate)
+                   uint32_t *__restrict__ gmax, int split, const int *__restrict__ gate,
+                   int64_t tiles_x, int nouter)
 {
     if (gate && *gate == 0) return;        // the 16-bit form of the pass (below) resolved every voxel
     extern __shared__ uint4 mp_tile[];                     // [roundup4(L) + 2H][32]
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int nrt = (n + L - 1) / L;
-    const int row0 = (int)(blockIdx.x % nrt) * L;
-    const int64_t x0 = (int64_t)(blockIdx.x / nrt) * MP_TX;
+    uint32_t lmax = 0;
+    // blocks walk the (tiles_x, nouter) tile grid: the launch is one wave of blocks, so a launch that
+    // is gated off costs microseconds
+    for (int64_t tile_id = blockIdx.x; tile_id < tiles_x * nouter; tile_id += gridDim.x) {
+    const int64_t bx = tile_id % tiles_x;
+    const int by = (int)(tile_id / tiles_x);
+    const int row0 = (int)(bx % nrt) * L;
+    const int64_t x0 = (int64_t)(bx / nrt) * MP_TX;
     const int64_t valid = nxc - x0;                        // columns of this tile inside the row
-    const typename Src::T *sbase = src + (int64_t)blockIdx.y * ostride + x0;
+    const typename Src::T *sbase = src + (int64_t)by * ostride + x0;
     const int Lr = (L + MP_R - 1) & ~(MP_R - 1);
     const int rows = Lr + 2 * H;
     const uint4 INF4 = make_uint4(MP_INF, MP_INF, MP_INF, MP_INF);
@@ -115,7 +123,6 @@ edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ d
     // Warp footprint: 32 columns x 16 rows (lane = 8 column groups x 4 row blocks) -- compact, so
     // the lanes of a warp see similar distances; every quarter-warp still reads 128 contiguous
     // bytes of one tile row (conflict-free LDS.128).  Block: 4 warps across x, 2 down.
-    uint32_t lmax = 0;
     const int cg = (warp & 3) * 8 + (lane & 7);            // column group (uint4) inside the tile row
     const int xl = 4 * cg;
     const uint4 *col = mp_tile + cg;
@@ -183,13 +190,13 @@ edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ d
         for (int i = 0; i < MP_R; ++i) {
             const int g = gr + i;
             if (g >= n || ry + i >= L) continue;
-            int64_t oi = (int64_t)blockIdx.y * ostride + x0 + (int64_t)g * rstride + xl;
+            int64_t oi = (int64_t)by * ostride + x0 + (int64_t)g * rstride + xl;
             if (split > 0) {
                 // y pass of a z-slab: all-to-all send layout [dest d][z][y - d*split][x]
                 // (dest d owns rows [d*split, min(n, (d+1)*split)) of the pencil decomposition)
                 const int d = g / split, yy = g - d * split;
                 const int nyd = min(split, n - d * split);
-                oi = ((int64_t)d * split * gridDim.y + (int64_t)blockIdx.y * nyd + yy) * rstride + x0 + xl;
+                oi = ((int64_t)d * split * nouter + (int64_t)by * nyd + yy) * rstride + x0 + xl;
             }
             const uint32_t o[4] = {B[i].x, B[i].y, B[i].z, B[i].w};
 #pragma unroll
@@ -219,6 +226,8 @@ edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ d
             }
         }
     }
+    __syncthreads();                                       // the tile is restaged by the next round
+    }
     if (gmax) {
         lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
         if (lane == 0 && lmax) atomicMax(gmax, min(lmax, MP_INF));
@@ -246,7 +255,7 @@ __device__ __forceinline__ uint32_t mp16_off(int d) { return min((uint32_t)(d * 
 
 // grid / tile geometry as edt_minplus_kernel; dyn smem = rows * 256 + (H + 2) * 16 bytes.
 template <typename Src, int OUT>
-__global__ void __launch_bounds__(MP16_WARPS * 32)
+__global__ void __launch_bounds__(MP16_WARPS * 32, 4)
 edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__ dst, int n,
                      int64_t rstride, int64_t nxc, int64_t ostride, int L, int H, int vec,
                      uint32_t *__restrict__ gmax, int split, int *__restrict__ overflow)
@@ -265,18 +274,29 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
     for (int d = tid; d < H + 2; d += MP16_WARPS * 32)
         offt[d] = make_uint4(mp16_off(d), mp16_off(d + 1), mp16_off(d + 2), mp16_off(d + 3));
     const uint4 INF4 = make_uint4(MP_INF, MP_INF, MP_INF, MP_INF);
-    for (int r0 = warp; r0 < rows; r0 += 4 * MP16_WARPS) {                // 4 independent row loads in flight
-        uint4 v[4];
+    // staging is latency-bound (the whole block waits for it): 8 independent row loads in flight per warp
+    if (vec && 4 * lane + 3 < valid) {
+        for (int r0 = warp; r0 < rows; r0 += 8 * MP16_WARPS) {
+            typename Src::Raw raw[8];
+            bool in[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = r0 + i * MP16_WARPS, gr = row0 - H + r;
-            v[i] = INF4;
-            if (r < rows && gr >= 0 && gr < n) v[i] = mp_load_row<Src>(sbase + (int64_t)gr * rstride, 4 * lane, valid, vec);
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + i * MP16_WARPS, gr = row0 - H + r;
+                in[i] = r < rows && gr >= 0 && gr < n;
+                if (in[i]) raw[i] = Src::ldraw(sbase + (int64_t)gr * rstride + 4 * lane);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + i * MP16_WARPS;
+                if (r < rows) tile[r * 32 + lane] = mp16_pack(in[i] ? Src::cvt(raw[i]) : INF4);
+            }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = r0 + i * MP16_WARPS;
-            if (r < rows) tile[r * 32 + lane] = mp16_pack(v[i]);
+    } else {
+        for (int r0 = warp; r0 < rows; r0 += MP16_WARPS) {
+            const int gr = row0 - H + r0;
+            uint4 v = INF4;
+            if (gr >= 0 && gr < n) v = mp_load_row<Src>(sbase + (int64_t)gr * rstride, 4 * lane, valid, vec);
+            tile[r0 * 32 + lane] = mp16_pack(v);
         }
     }
     __syncthreads();

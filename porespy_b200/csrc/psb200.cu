@@ -91,6 +91,9 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->launches = 0;
     c->profile = 0;
     c->bit_tmax = 200;
+    c->edt16 = 1;
+    c->flag_slot = 0;
+    CUDA_TRY(cudaMalloc(&c->flags, 64 * sizeof(int)));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_TRY(cudaFuncSetAttribute(lt_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
@@ -101,6 +104,10 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_x_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_x_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     *out = c;
@@ -109,6 +116,10 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
 
 extern "C" int psb200_destroy(psb200_ctx *ctx)
 {
+    if (ctx && ctx->flags) {
+        cudaSetDevice(ctx->device);
+        cudaFree(ctx->flags);
+    }
     delete ctx;
     return PSB200_OK;
 }
@@ -125,6 +136,10 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
     if (!strcmp(name, "bit_tmax")) {
         if (value < 0 || value > 400) return fail(PSB200_ERR_INVALID, "set_option: bit_tmax must be in [0,400]");
         ctx->bit_tmax = (int)value;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "edt16")) {
+        ctx->edt16 = value ? 1 : 0;
         return PSB200_OK;
     }
     if (!strcmp(name, "profile")) {
@@ -299,6 +314,8 @@ static int launch_xdist(psb200_ctx *ctx, const uint8_t *in, void *out, int64_t n
     return PSB200_OK;
 }
 
+static bool ntiles_check(int64_t gx, int64_t nouter) { return gx > 0 && nouter > (int64_t)0x7FFFFFFFFFFFLL / gx; }
+
 // bounded min-plus pass along y (axis 1) or z (axis 0); out_kind 0: u32 squared, 1: f32 sqrt
 template <typename Src>
 static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src, void *dst, int out_kind,
@@ -318,13 +335,39 @@ static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src,
     const int64_t gx = ((nxc + MP_TX - 1) / MP_TX) * ((n + L - 1) / L);
     if (gx > 0x7FFFFFFFLL || nouter > 65535)
         return fail(PSB200_ERR_UNSUPPORTED, "edt pass: volume too large for one launch");
-    dim3 grid((unsigned)gx, (unsigned)nouter);
+    if (ntiles_check(gx, nouter)) return fail(PSB200_ERR_UNSUPPORTED, "edt pass: too many tiles");
+    const int64_t ntiles = gx * nouter;
+    // one CTA holds (L + 2H) * 512 bytes of shared memory: 3 resident per SM; the blocks walk the tiles
+    const unsigned grid = (unsigned)(ntiles < (int64_t)ctx->sm_count * 3 ? ntiles : (int64_t)ctx->sm_count * 3);
+    const int *gate = nullptr;
+    if (ctx->edt16) {
+        // 16-bit form first (exact wherever the result is < 32767); the uint32 kernel behind it only
+        // runs when a voxel overflowed
+        int *ovf = ctx->flags + (ctx->flag_slot++ & 63u);
+        int L16, H16;
+        if (n <= 224) { L16 = n; H16 = 0; }
+        else { L16 = 128; H16 = 48; }
+        const size_t smem16 = (size_t)(((L16 + 3) & ~3) + 2 * H16) * 256 + (size_t)(H16 + 2) * 16;
+        const int64_t gx16 = ((nxc + MP_TX - 1) / MP_TX) * ((n + L16 - 1) / L16);
+        if (gx16 > 0x7FFFFFFFLL) return fail(PSB200_ERR_UNSUPPORTED, "edt pass: volume too large for one launch");
+        dim3 grid16((unsigned)gx16, (unsigned)nouter);
+        CUDA_TRY(cudaMemsetAsync(ovf, 0, sizeof(int), st));
+        {
+            ProfScope ps__(ctx, st, axis == 1 ? K_EDT_Y : K_EDT_Z);
+            if (out_kind == 0)
+                edt_minplus16_kernel<Src, 0><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
+            else
+                edt_minplus16_kernel<Src, 1><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
+        }
+        LAUNCH_CHECK(ctx);
+        gate = ovf;
+    }
     {
         ProfScope ps__(ctx, st, axis == 1 ? K_EDT_Y : K_EDT_Z);
         if (out_kind == 0)
-            edt_minplus_kernel<Src, 0><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax, split);
+            edt_minplus_kernel<Src, 0><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax, split, gate, gx, (int)nouter);
         else
-            edt_minplus_kernel<Src, 1><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax, split);
+            edt_minplus_kernel<Src, 1><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax, split, gate, gx, (int)nouter);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
@@ -933,10 +976,9 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
         int *kmin = w.gate + 1;
         CUDA_TRY(cudaMemsetAsync(w.gate, 0, sizeof(int), st));
         CUDA_TRY(cudaMemsetAsync(kmin, 0x7F, sizeof(int), st));
-        CUDA_TRY(cudaMemsetAsync(jtime, 0, (size_t)n + 1, st));
         {
             ProfScope ps__(ctx, st, K_UF_INIT);
-            uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx);
+            uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx, jtime);
         }
         LAUNCH_CHECK(ctx);
         for (int k = 0; k < nT; ++k) {
@@ -1120,7 +1162,7 @@ extern "C" int psb200_uf_begin(psb200_ctx *ctx, const uint8_t *cls, uint8_t *rcl
     LAUNCH_CHECK(ctx);
     {
         ProfScope ps__(ctx, st, K_UF_INIT);
-        uf_init_kernel<<<g, 256, 0, st>>>(parent, inl, (int)nz, (int)ny, (int)nx);
+        uf_init_kernel<<<g, 256, 0, st>>>(parent, inl, (int)nz, (int)ny, (int)nx, nullptr);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
@@ -1243,7 +1285,7 @@ extern "C" int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t 
     LAUNCH_CHECK(ctx);
     {
         ProfScope ps__(ctx, st, K_UF_INIT);
-        uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx);
+        uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx, nullptr);
     }
     LAUNCH_CHECK(ctx);
     rc = uf_step(ctx, w, inl, -1, 0, c3, nz, ny, nx, st);

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--edt-size", type=int, default=512)
     ap.add_argument("--tag", default="r1d")
     ap.add_argument("--skip-generic", action="store_true")
+    ap.add_argument("--only-edt", action="store_true", help="stop after the EDT timings (configs 1 and edt_full)")
     args = ap.parse_args()
     device = torch.device("cuda", 0)
     ctx = _lib.context(0)
@@ -91,6 +92,11 @@ def main():
     out["edt_full"] = {"shape": [S] * 3, "ms_f32": t_edt, "voxels_per_s": n / (t_edt * 1e-3),
                        "model_gbs": 21 * n / (t_edt * 1e-3) / 1e9, "model_frac": 21 * n / (t_edt * 1e-3) / 1e9 / peak}
     print(json.dumps(out["edt_full"]), flush=True)
+    _, prof_full = profile_once(ctx, lambda: dev.edt_run(ctx, im, im.shape, as_f32=True)[0])
+    out["edt_full"]["kernels"] = prof_full
+    if args.only_edt:
+        print(json.dumps(prof_full), flush=True)
+        return
 
     def check_vs_generic(fn, what):
         if args.skip_generic:

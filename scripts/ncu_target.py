@@ -17,6 +17,11 @@ if mode == "lt":
     out = psb.filters.local_thickness(im, sizes=bench.SIZES)
 elif mode == "poro":
     out = psb.filters.porosimetry(im, sizes=bench.SIZES)
+elif mode == "poro50":
+    # BASELINE config 2: access-limited drainage from the z = 0 face, 50 radii
+    inl = torch.zeros((size,) * 3, dtype=torch.uint8, device=im.device)
+    inl[0] = 1
+    out = psb.filters.porosimetry(im, sizes=50, inlets=inl, mode="dt")
 elif mode == "edt":
     out = psb.edt(im)
 torch.cuda.synchronize()

@@ -46,13 +46,23 @@ def rand_image(shape, p, seed):
 
 
 # ---------------------------------------------------------------------------------- EDT
+@pytest.fixture(params=["edt16", "edt32"])
+def edt_mode(request):
+    """Both forms of the EDT y/z passes: 16-bit kernel with the gated uint32 fallback, uint32 only."""
+    from porespy_b200 import _lib
+    ctx = _lib.context()
+    ctx.set_edt16(request.param == "edt16")
+    yield request.param
+    ctx.set_edt16(True)
+
+
 EDT_CASES = [((37, 29, 41), 0.5), ((64, 64, 64), 0.97), ((13, 37, 101), 0.9), ((1, 50, 60), 0.8),
              ((50, 1, 60), 0.8), ((50, 60, 1), 0.8), ((5, 1, 7), 0.6), ((17, 251), 0.9), ((129,), 0.95),
              ((3, 300, 5), 0.99), ((127, 31, 33), 0.995), ((2, 2, 2), 0.5), ((1,), 1.0), ((70, 130), 0.999)]
 
 
 @pytest.mark.parametrize("shape,p", EDT_CASES)
-def test_edt_random(psb, shape, p):
+def test_edt_random(psb, edt_mode, shape, p):
     im = rand_image(shape, p, seed=len(shape) * 1000 + shape[0])
     from porespy_b200.edt import edt_sq_u32
     assert_same(edt_sq_u32(im), oc.edt_sq(im), f"edt_sq {shape}")
@@ -61,7 +71,7 @@ def test_edt_random(psb, shape, p):
     assert_same(dt, oc.edt(im), f"edt {shape}")
 
 
-def test_edt_adversarial(psb):
+def test_edt_adversarial(psb, edt_mode):
     from porespy_b200.edt import edt_sq_u32
     one_bg = np.ones((33, 40, 47), bool)
     one_bg[16, 20, 23] = False
@@ -80,6 +90,17 @@ def test_edt_adversarial(psb):
     corner = np.ones((40, 41, 300), bool)
     corner[0, 0, 0] = False                             # long distances, 299^2+40^2+39^2
     assert_same(edt_sq_u32(corner), oc.edt_sq(corner), "far corner")
+    # distances that straddle the 16-bit cap (32767) of the two-voxels-per-instruction passes:
+    # y pass overflows / z pass overflows / neither
+    for shp, bg in (((3, 400, 260), (1, 0, 0)), ((260, 5, 190), (0, 2, 0)), ((200, 150, 8), (199, 149, 7))):
+        far = np.ones(shp, bool)
+        far[bg] = False
+        assert_same(edt_sq_u32(far), oc.edt_sq(far), f"cap straddle {shp}")
+        assert_same(psb.edt(far), oc.edt(far), f"cap straddle f32 {shp}")
+    tall = rand_image((300, 40, 64), 0.999, 11)           # z tiles with halo (n > 224), sparse background
+    assert_same(edt_sq_u32(tall), oc.edt_sq(tall), "tall sparse")
+    wide = rand_image((2, 700, 130), 0.9995, 12)          # y tiles with halo, scans beyond the staged halo
+    assert_same(edt_sq_u32(wide), oc.edt_sq(wide), "wide sparse")
     # kwargs PoreSpy passes (F:1186-1189, _snows.py:600-607)
     assert_same(psb.edt(data=one_bg, parallel=0), oc.edt(one_bg), "kwargs")
     assert_same(psb.edtsq(one_bg), oc.edt_sq(one_bg).astype(np.float32), "edtsq")
@@ -87,7 +108,7 @@ def test_edt_adversarial(psb):
         psb.edt(one_bg, black_border=True)
 
 
-def test_edt_golden_blobs100(psb, golden):
+def test_edt_golden_blobs100(psb, edt_mode, golden):
     from porespy_b200.edt import edt_sq_u32
     g = golden.blobs100
     d2 = edt_sq_u32(g.mask("im"))
@@ -95,7 +116,7 @@ def test_edt_golden_blobs100(psb, golden):
     assert_same(d2[:, :, 50], g.raw("d2_slice50"), "d2 slice")
 
 
-def test_edt_config1_shape_sample(psb):
+def test_edt_config1_shape_sample(psb, edt_mode):
     """BASELINE config 1 at a size the oracle finishes in seconds (256^3 of the 512^3 recipe)."""
     from porespy_b200.edt import edt_sq_u32
     im = oc.blobs([256, 256, 256], porosity=0.6, blobiness=2, seed=0)
