@@ -67,6 +67,32 @@ lt_wmask_kernel(const uint8_t *__restrict__ idx, uint32_t *__restrict__ written,
     }
 }
 
+// New voxels of one word: set their written bits and their radius-index bytes.
+__device__ __forceinline__ void bb_commit(uint32_t *__restrict__ written, uint8_t *__restrict__ idx, int64_t wi,
+                                          uint32_t A, uint32_t val)
+{
+    const uint32_t wm = written[wi];
+    const uint32_t N = A & ~wm;
+    if (N == 0u) return;
+    written[wi] = wm | N;
+    uint4 *ip = reinterpret_cast<uint4 *>(idx + 32 * wi);
+    const uint32_t val4 = val * 0x01010101u;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t nh = (N >> (16 * h)) & 0xFFFFu;
+        if (nh == 0u) continue;
+        uint4 o = ip[h];
+        uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t nib = (nh >> (4 * q)) & 0xFu;
+            const uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;   // nibble -> byte mask
+            ow[q] |= val4 & bm;        // the bytes under bm are still 0 (written bit was clear)
+        }
+        ip[h] = o;
+    }
+}
+
 // ------------------------------------------------------------------------------ dilation
 // seeds: [nz_src][ny][nw] words (nw = nx / 32); output plane z reads seed plane z + z_off, so a
 // z-slab shard passes its slab with the neighbours' halo planes in front / behind (single GPU:
@@ -121,25 +147,73 @@ lt_bitball_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ wri
     }
     const bool center = inrow && (halo == 0 || (lane >= 1 && lane <= 30));
     if (!center) return;
-    const int64_t wi = ((int64_t)z * ny + y) * nw + w;
-    const uint32_t wm = written[wi];
-    const uint32_t N = A & ~wm;
-    if (N == 0u) return;
-    written[wi] = wm | N;
-    uint4 *ip = reinterpret_cast<uint4 *>(idx + 32 * wi);
-    const uint32_t val4 = val * 0x01010101u;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const uint32_t nh = (N >> (16 * h)) & 0xFFFFu;
-        if (nh == 0u) continue;
-        uint4 o = ip[h];
-        uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t nib = (nh >> (4 * q)) & 0xFu;
-            const uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;   // nibble -> byte mask
-            ow[q] |= val4 & bm;        // the bytes under bm are still 0 (written bit was clear)
+    bb_commit(written, idx, ((int64_t)z * ny + y) * nw + w, A, val);
+}
+
+// Two words per lane: a warp owns 64 words (2048 voxels) of a row, so rows of 33..64 words need no
+// halo lanes (with 32-word warps a 2048-voxel row costs three 30-word segments, a third of the
+// lanes idle); longer rows use 60-word segments with one halo lane (two words) on each side.
+// nw must be even (8-byte loads).  grid.x = segments, otherwise as lt_bitball_kernel.
+__global__ void __launch_bounds__(1024)
+lt_bitball2_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ written,
+                   uint8_t *__restrict__ idx, int nz, int ny, int nw, int seg_words,
+                   const __grid_constant__ BallPairs bp, uint32_t val, const int *__restrict__ gate,
+                   int nz_src, int z_off)
+{
+    if (gate && *gate == 0) return;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int y = blockIdx.y * BB_TY + (warp & (BB_TY - 1)), z = blockIdx.z * BB_TZ + (warp >> 3);
+    if (y >= ny || z >= nz) return;
+    const int halo = seg_words == 64 ? 0 : 2;
+    const int w = blockIdx.x * seg_words + 2 * lane - halo;      // first of this lane's two words (even)
+    const bool inrow = w >= 0 && w < nw;
+    const uint32_t inmask = inrow ? 0xFFFFFFFFu : 0u;
+    const int zs = z + z_off;
+    const uint32_t *base = seeds + ((int64_t)zs * ny + y) * nw + (inrow ? w : 0);
+    asm volatile("" : "+l"(base));
+    const int W = bp.W;
+    const bool interior = y - W >= 0 && y + W < ny && zs - W >= 0 && zs + W < nz_src;
+
+    uint32_t A0 = 0, A1 = 0;
+    int p = 0;
+    for (int a = W; a >= 0; --a) {
+        if (a < W) {
+            uint32_t l = __shfl_up_sync(0xFFFFFFFFu, A1, 1), r = __shfl_down_sync(0xFFFFFFFFu, A0, 1);
+            if (lane == 0) l = 0;
+            if (lane == 31) r = 0;
+            const uint32_t n0 = A0 | (A0 << 1) | (l >> 31) | (A0 >> 1) | (A1 << 31);
+            const uint32_t n1 = A1 | (A1 << 1) | (A0 >> 31) | (A1 >> 1) | (r << 31);
+            A0 = n0;
+            A1 = n1;
         }
-        ip[h] = o;
+        const int pend = bp.ring_end[a];
+        if (interior) {
+            for (; p + 2 <= pend; p += 2) {
+                const uint2 s0 = __ldg(reinterpret_cast<const uint2 *>(base + bp.e[p].x));
+                const uint2 s1 = __ldg(reinterpret_cast<const uint2 *>(base + bp.e[p + 1].x));
+                A0 |= (s0.x | s1.x) & inmask;
+                A1 |= (s0.y | s1.y) & inmask;
+            }
+            for (; p < pend; ++p) {
+                const uint2 s0 = __ldg(reinterpret_cast<const uint2 *>(base + bp.e[p].x));
+                A0 |= s0.x & inmask;
+                A1 |= s0.y & inmask;
+            }
+        } else {
+            for (; p < pend; ++p) {
+                const int2 e = bp.e[p];
+                const int yy = y + (int)(short)(e.y & 0xFFFF), zz = zs + (e.y >> 16);
+                if ((unsigned)yy < (unsigned)ny && (unsigned)zz < (unsigned)nz_src) {
+                    const uint2 s0 = __ldg(reinterpret_cast<const uint2 *>(base + e.x));
+                    A0 |= s0.x & inmask;
+                    A1 |= s0.y & inmask;
+                }
+            }
+        }
     }
+    const bool center = inrow && (halo == 0 || (lane >= 1 && lane <= 30));
+    if (!center) return;
+    const int64_t wi = ((int64_t)z * ny + y) * nw + w;
+    bb_commit(written, idx, wi, A0, val);
+    bb_commit(written, idx, wi + 1, A1, val);
 }

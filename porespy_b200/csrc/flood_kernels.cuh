@@ -193,13 +193,147 @@ uf_collect_kernel(const uint8_t *__restrict__ cls, int klo, int khi, int64_t v0,
     }
 }
 
+// ---- all radii at once (single-GPU loop): the voxels are bucketed by class in one pass, so that
+// radius k links the slice  list[start[k] .. start[k + 1])  without scanning the class map again.
+//   uf_hist_kernel   : hist[c] = number of voxels of class c (c < CLS_NEVER)
+//   uf_scan_kernel   : start[] = exclusive prefix sums (257 entries), cursor[] = 0
+//   uf_bucket_kernel : a block takes 256 x 64 consecutive voxels per round (a thread 64 consecutive
+//                      ones), reserves its share of every class slice with one atomicAdd per class
+//                      and writes runs of equal class as runs of the list (x-neighbours stay
+//                      neighbours in the list, which the union kernel's loads rely on)
+__global__ void __launch_bounds__(256)
+uf_hist_kernel(const uint8_t *__restrict__ cls, int64_t n, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t ngroups = n / 16;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += step) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(cls) + g);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        // runs of equal bytes are counted with one atomic (all indices static: w stays in registers)
+        uint32_t prev = byte_of(w[0], 0), run = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t c = byte_of(w[i >> 2], i & 3);
+            if (c != prev) {
+                if (prev < CLS_NEVER) atomicAdd(&h[prev], run);
+                prev = c;
+                run = 0;
+            }
+            ++run;
+        }
+        if (prev < CLS_NEVER) atomicAdd(&h[prev], run);
+    }
+    if (blockIdx.x == 0)
+        for (int64_t v = ngroups * 16 + threadIdx.x; v < n; v += blockDim.x)
+            if (cls[v] < CLS_NEVER) atomicAdd(&h[cls[v]], 1u);
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+uf_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ start, uint32_t *__restrict__ cursor)
+{
+    __shared__ uint32_t s[256];
+    s[threadIdx.x] = hist[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int c = 0; c < 256; ++c) { const uint32_t t = s[c]; s[c] = acc; acc += t; }
+        start[256] = acc;
+    }
+    __syncthreads();
+    start[threadIdx.x] = s[threadIdx.x];
+    cursor[threadIdx.x] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+uf_bucket_kernel(const uint8_t *__restrict__ cls, int64_t n, const uint32_t *__restrict__ start,
+                 uint32_t *__restrict__ cursor, uint32_t *__restrict__ list)
+{
+    __shared__ uint32_t cnt[256];      // voxels of the round per class, then the running offset inside the reservation
+    __shared__ uint32_t base[256];     // start[c] + reserved offset of this round
+    const int64_t per_block = 256 * 64;
+    const int64_t nrounds = (n + per_block - 1) / per_block;
+    const bool aligned = (((uintptr_t)cls) & 15u) == 0;
+    for (int64_t r = blockIdx.x; r < nrounds; r += gridDim.x) {
+        cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t v0 = r * per_block + (int64_t)threadIdx.x * 64;
+        uint32_t w[16];
+        if (aligned && v0 + 64 <= n) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(cls + v0) + q);
+                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                uint32_t t = 0;
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t v = v0 + 4 * q + j;
+                    t |= (v < n ? (uint32_t)cls[v] : CLS_BG) << (8 * j);
+                }
+                w[q] = t;
+            }
+        }
+        {   // count the round per class, one atomic per run of equal bytes (static indices only)
+            uint32_t prev = byte_of(w[0], 0), run = 0;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                const uint32_t c = byte_of(w[i >> 2], i & 3);
+                if (c != prev) {
+                    if (prev < CLS_NEVER) atomicAdd(&cnt[prev], run);
+                    prev = c;
+                    run = 0;
+                }
+                ++run;
+            }
+            if (prev < CLS_NEVER) atomicAdd(&cnt[prev], run);
+        }
+        __syncthreads();
+        {
+            const uint32_t t = cnt[threadIdx.x];
+            base[threadIdx.x] = start[threadIdx.x] + (t ? atomicAdd(&cursor[threadIdx.x], t) : 0u);
+            cnt[threadIdx.x] = 0;
+        }
+        __syncthreads();
+        {   // write every run of equal class as a run of its list slice
+            uint32_t prev = byte_of(w[0], 0), run = 0, first = 0;
+#pragma unroll
+            for (int i = 0; i <= 64; ++i) {
+                const uint32_t c = i < 64 ? byte_of(w[(i < 64 ? i : 0) >> 2], i & 3) : 0x100u;
+                if (c != prev) {
+                    if (prev < CLS_NEVER) {
+                        uint32_t pos = base[prev] + atomicAdd(&cnt[prev], run);
+                        for (uint32_t t = 0; t < run; ++t) list[pos + t] = (uint32_t)(v0 + first + t);
+                    }
+                    prev = c;
+                    run = 0;
+                    first = (uint32_t)i;
+                }
+                ++run;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// list / count: the voxels to link; with `start` != NULL the slice of class khi of a bucketed list.
 __global__ void __launch_bounds__(256)
 uf_union_list_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpec inl, int klo, int khi,
                      int conn, int nz, int ny, int nx, const uint32_t *__restrict__ list,
-                     const uint32_t *__restrict__ count, uint8_t *jtime)
+                     const uint32_t *__restrict__ count, uint8_t *jtime, const uint32_t *__restrict__ start)
 {
     const int ndir = conn == 6 ? 6 : 26;
-    const int64_t jobs = (int64_t)(*count) * ndir;
+    if (start) {
+        list += start[khi];
+        count = nullptr;
+    }
+    const int64_t jobs = (int64_t)(start ? start[khi + 1] - start[khi] : *count) * ndir;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < jobs; j += step) {
         const uint32_t e = (uint32_t)(j / ndir);

@@ -584,7 +584,7 @@ static LtWorkspace carve_lt(const psb200_ctx *ctx, char *base, int64_t nz, int64
     const size_t n = (size_t)nz * ny * nx;
     Carver c{base, 0};
     LtWorkspace w{};
-    w.gate = c.take<int>(64);
+    w.gate = c.take<int>(1024);     // [0] gate, [1] first reached radius, [64..] class histogram / slice starts / cursors
     w.cls = c.take<uint8_t>(n + 16);
     w.reach = c.take<uint8_t>(n + 16);
     w.gx = c.take<uint8_t>(n + 16);
@@ -593,7 +593,7 @@ static LtWorkspace carve_lt(const psb200_ctx *ctx, char *base, int64_t nz, int64
     if (inlet_mode != PSB200_INLETS_NONE) {
         w.rcls = c.take<uint8_t>(n + 16);
         w.parent = c.take<uint32_t>(n + 1);
-        w.uf_list = c.take<uint32_t>(uf_list_entries((int64_t)n) + 64);
+        w.uf_list = c.take<uint32_t>(n + 64);        // every foreground voxel once, bucketed by class
     }
     if (ctx->algo == PSB200_ALGO_GENERIC) {
         w.gen_d2 = c.take<uint32_t>(n);
@@ -794,7 +794,7 @@ static int uf_activate_impl(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cl
         {
             ProfScope ps__(ctx, st, K_UF_ACTIVATE);
             uf_union_list_kernel<<<ctx->sm_count * 16, 256, 0, st>>>(parent, cls, inl, klo, khi, conn, (int)nz,
-                                                                     (int)ny, (int)nx, items, count, jtime);
+                                                                     (int)ny, (int)nx, items, count, jtime, nullptr);
         }
         LAUNCH_CHECK(ctx);
     }
@@ -859,12 +859,18 @@ static int lt_bitball_impl(psb200_ctx *ctx, const uint32_t *seedbits, int64_t nz
     memset(&bp, 0, sizeof(int) + sizeof(bp.ring_end));
     if (!build_ball_pairs(T, ny, nx / 32, bp)) return fail(PSB200_ERR_UNSUPPORTED, "bit path: threshold %u too large", T);
     const int nw = (int)(nx / 32);
-    const int seg = nw <= 32 ? 32 : 30;
+    // rows longer than 32 words: two words per lane when the row offsets stay 8-byte aligned
+    const bool two = nw > 32 && (nw % 2 == 0) && ((reinterpret_cast<uintptr_t>(seedbits) & 7u) == 0);
+    const int seg = two ? (nw <= 64 ? 64 : 60) : (nw <= 32 ? 32 : 30);
     dim3 grid((unsigned)((nw + seg - 1) / seg), (unsigned)((ny + BB_TY - 1) / BB_TY), (unsigned)((nz + BB_TZ - 1) / BB_TZ));
     {
         ProfScope ps__(ctx, st, K_LT_BITBALL);
-        lt_bitball_kernel<<<grid, 1024, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, nw, seg, bp,
-                                                 (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
+        if (two)
+            lt_bitball2_kernel<<<grid, 1024, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, nw, seg, bp,
+                                                      (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
+        else
+            lt_bitball_kernel<<<grid, 1024, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, nw, seg, bp,
+                                                     (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
@@ -981,9 +987,30 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
             uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx, jtime);
         }
         LAUNCH_CHECK(ctx);
+        uint32_t *hist = reinterpret_cast<uint32_t *>(w.gate) + 64, *start = hist + 256, *cursor = start + 320;
+        CUDA_TRY(cudaMemsetAsync(hist, 0, 256 * sizeof(uint32_t), st));
+        {
+            ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+            uf_hist_kernel<<<grid_for(n / 16 + 1, 256, ctx->sm_count, 8), 256, 0, st>>>(w.cls, n, hist);
+        }
+        LAUNCH_CHECK(ctx);
+        {
+            ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+            uf_scan_kernel<<<1, 256, 0, st>>>(hist, start, cursor);
+        }
+        LAUNCH_CHECK(ctx);
+        {
+            ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+            uf_bucket_kernel<<<grid_for((n + 63) / 64, 256, ctx->sm_count, 8), 256, 0, st>>>(w.cls, n, start, cursor, w.uf_list);
+        }
+        LAUNCH_CHECK(ctx);
         for (int k = 0; k < nT; ++k) {
-            rc = uf_activate_impl(ctx, w.parent, w.cls, inl, k - 1, k, 6, nz, ny, nx, w.uf_list, st, jtime);
-            if (rc) return rc;
+            {
+                ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+                uf_union_list_kernel<<<ctx->sm_count * 16, 256, 0, st>>>(w.parent, w.cls, inl, k - 1, k, 6, (int)nz, (int)ny,
+                                                                         (int)nx, w.uf_list, nullptr, jtime, start);
+            }
+            LAUNCH_CHECK(ctx);
         }
         {
             ProfScope ps__(ctx, st, K_UF_MARK);

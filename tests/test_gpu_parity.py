@@ -132,7 +132,9 @@ LT_CASES = [((40, 36, 44), 12, 0.6), ((48, 52), 9, 0.6), ((30, 30, 30), [5, 3.5,
             ((300, 1, 32), 8, 0.8), ((20, 300, 16), 12, 0.7), ((256,), 6, 0.9), ((9, 520, 144), 30, 0.8),
             # nx % 32 == 0: bit-parallel kernels (incl. rows longer than 1024 voxels: 30-word segments)
             ((40, 50, 96), 20, 0.6), ((3, 40, 1120), 14, 0.7), ((5, 4, 2048), [9, 4, 2.5, 1], 0.8),
-            ((70, 2080), 16, 0.7)]
+            ((70, 2080), 16, 0.7),
+            # even word counts above 32: two words per lane (64-word rows, 60-word segments with halo lanes)
+            ((6, 24, 2112), [9, 4, 2.5, 1], 0.8), ((2, 30, 4160), 14, 0.7), ((40, 2048), 12, 0.7)]
 
 
 @pytest.mark.parametrize("algo", ["fast", "nobit", "allbit", "generic"])
