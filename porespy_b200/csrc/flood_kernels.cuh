@@ -28,7 +28,7 @@
 #define UF_TIME_UNSET 0xFFu   // jtime of a node that never hung directly under node 0
 
 struct InletSpec {
-    int mode;                 // 1 = faces predicate, 2 = mask
+    int mode;                 // 1 = faces predicate, 2 = mask, 3 = none (already folded into the class map)
     int ndim;                 // dimensionality of the squeezed image (faces predicate)
     const uint8_t *mask;      // mode 2 (the local slab of the mask)
     int z0, nzg;              // z-slab shard: local plane z is global plane z + z0 of nzg planes
@@ -38,6 +38,7 @@ __device__ __forceinline__ bool is_inlet(const InletSpec &s, int64_t v, int z, i
                                          int nz, int ny, int nx)
 {
     if (s.mode == 2) return s.mask[v] != 0;
+    if (s.mode == 3) return false;          // inlets are folded into the class map (class 0), see uf_init_kernel
     // get_border(shape, mode='faces') (generators/_borders.py:93-100); ndim 1: all True
     if (s.ndim >= 3) return z + s.z0 == 0 || z + s.z0 == s.nzg - 1 || y == 0 || y == ny - 1 || x == 0 || x == nx - 1;
     if (s.ndim == 2) return y == 0 || y == ny - 1 || x == 0 || x == nx - 1;
@@ -98,7 +99,8 @@ __device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t 
 }
 
 __global__ void __launch_bounds__(256)
-uf_init_kernel(uint32_t *__restrict__ parent, InletSpec inl, int nz, int ny, int nx, uint8_t *__restrict__ jtime)
+uf_init_kernel(uint32_t *__restrict__ parent, InletSpec inl, int nz, int ny, int nx, uint8_t *__restrict__ jtime,
+               const uint8_t *__restrict__ cls = nullptr, uint8_t *__restrict__ acls = nullptr)
 {
     const int64_t n = (int64_t)nz * ny * nx;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
@@ -109,6 +111,9 @@ uf_init_kernel(uint32_t *__restrict__ parent, InletSpec inl, int nz, int ny, int
         const bool in = is_inlet(inl, v, z, y, x, nz, ny, nx);
         parent[v + 1] = in ? 0u : (uint32_t)(v + 1);
         if (jtime) jtime[v + 1] = in ? 0 : UF_TIME_UNSET;
+        // activation map: an inlet voxel is a graph node from the first radius on, whatever its class
+        // (F:1265), so the link kernels need neither the inlet predicate nor the inlet mask
+        if (acls) acls[v] = in ? 0 : cls[v];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) parent[0] = 0u;
 }

@@ -984,14 +984,17 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
         CUDA_TRY(cudaMemsetAsync(kmin, 0x7F, sizeof(int), st));
         {
             ProfScope ps__(ctx, st, K_UF_INIT);
-            uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx, jtime);
+            uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx, jtime, w.cls, w.rcls);
         }
         LAUNCH_CHECK(ctx);
+        // until the resolve pass the rcls buffer holds the activation map (class, inlets folded to 0)
+        const uint8_t *acls = w.rcls;
+        const InletSpec folded{3, ndim, nullptr, 0, (int)nz};
         uint32_t *hist = reinterpret_cast<uint32_t *>(w.gate) + 64, *start = hist + 256, *cursor = start + 320;
         CUDA_TRY(cudaMemsetAsync(hist, 0, 256 * sizeof(uint32_t), st));
         {
             ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-            uf_hist_kernel<<<grid_for(n / 16 + 1, 256, ctx->sm_count, 8), 256, 0, st>>>(w.cls, n, hist);
+            uf_hist_kernel<<<grid_for(n / 16 + 1, 256, ctx->sm_count, 8), 256, 0, st>>>(acls, n, hist);
         }
         LAUNCH_CHECK(ctx);
         {
@@ -1001,13 +1004,13 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
         LAUNCH_CHECK(ctx);
         {
             ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-            uf_bucket_kernel<<<grid_for((n + 63) / 64, 256, ctx->sm_count, 8), 256, 0, st>>>(w.cls, n, start, cursor, w.uf_list);
+            uf_bucket_kernel<<<grid_for((n + 63) / 64, 256, ctx->sm_count, 8), 256, 0, st>>>(acls, n, start, cursor, w.uf_list);
         }
         LAUNCH_CHECK(ctx);
         for (int k = 0; k < nT; ++k) {
             {
                 ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-                uf_union_list_kernel<<<ctx->sm_count * 16, 256, 0, st>>>(w.parent, w.cls, inl, k - 1, k, 6, (int)nz, (int)ny,
+                uf_union_list_kernel<<<ctx->sm_count * 16, 256, 0, st>>>(w.parent, acls, folded, k - 1, k, 6, (int)nz, (int)ny,
                                                                          (int)nx, w.uf_list, nullptr, jtime, start);
             }
             LAUNCH_CHECK(ctx);

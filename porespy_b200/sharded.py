@@ -278,30 +278,45 @@ class ShardedVolume:
         torch, be = self.torch, self.backend
         nz, ny, nx = self.shape
         nzl, nyl, P = self.nzl, self.nyl, self.world
+        d2p, lmax = self._edt_pencils(local_u8)
+        if P == 1:
+            return d2p, lmax
+        return self._pencils_to_slab(d2p, torch.int32), self._allreduce_max(lmax)
+
+    def _edt_pencils(self, local_u8):
+        """x / y passes on the slab, slab -> pencil all-to-all, z pass on the pencils.  Returns the
+        squared distances in pencil layout [nz][nyl][nx] (the slab itself for one rank) and the
+        local max."""
+        torch, be = self.torch, self.backend
+        nz, ny, nx = self.shape
+        nzl, nyl, P = self.nzl, self.nyl, self.world
         h_send = be.edt_xy(local_u8.reshape(-1), (nzl, ny, nx), self.ysplit if P > 1 else 0)
         if P == 1:
-            d2, mx = be.edt_z(h_send, (nz, ny, nx))
-            return d2, mx
+            return be.edt_z(h_send, (nz, ny, nx))
         # slab -> pencil: block for dest d is [nzl][ycounts[d]][nx]; I receive [zcounts[s]][nyl][nx] from s
         pencil = be.empty(nz * nyl * nx, torch.int32)
         self._all_to_all(pencil, h_send, [self.zcounts[s] * nyl * nx for s in range(P)],
                          [nzl * self.ycounts[d] * nx for d in range(P)])
         del h_send
-        d2p, lmax = be.edt_z(pencil, (nz, nyl, nx))
-        del pencil
-        # pencil -> slab: dest d gets my rows for its planes (a contiguous z range of the pencil)
-        recv = be.empty(nzl * ny * nx, torch.int32)
-        self._all_to_all(recv, d2p, [nzl * self.ycounts[s] * nx for s in range(P)],
+        return be.edt_z(pencil, (nz, nyl, nx))
+
+    def _pencils_to_slab(self, vals_p, dtype):
+        """pencil -> slab: dest d gets my rows for its planes (a contiguous z range of the pencil).
+        Works for any element type (uint32 distances, uint8 classes)."""
+        be = self.backend
+        nz, ny, nx = self.shape
+        nzl, nyl, P = self.nzl, self.nyl, self.world
+        recv = be.empty(nzl * ny * nx, dtype)
+        self._all_to_all(recv, vals_p, [nzl * self.ycounts[s] * nx for s in range(P)],
                          [self.zcounts[d] * nyl * nx for d in range(P)])
-        del d2p
-        slab = be.empty(nzl * ny * nx, torch.int32).view(nzl, ny, nx)
+        slab = be.empty(nzl * ny * nx, dtype).view(nzl, ny, nx)
         off = 0
         for s in range(P):
             cnt = nzl * self.ycounts[s] * nx
             y0 = s * self.ysplit
             slab[:, y0:y0 + self.ycounts[s], :] = recv[off:off + cnt].view(nzl, self.ycounts[s], nx)
             off += cnt
-        return slab.reshape(-1), self._allreduce_max(lmax)
+        return slab.reshape(-1)
 
     def edt(self, local_im):
         """float32 distances of the local slab (edt.edt semantics on the global volume)."""
@@ -351,7 +366,10 @@ class ShardedVolume:
         nz, ny, nx = self.shape
         nzl = self.nzl
         lshape = (nzl, ny, nx)
-        d2, max_d2 = self.edt_sq(be.to_u8(local_im))
+        # the radius loop only needs the class of every voxel, so the distances are classified on the
+        # pencils and ONE byte per voxel travels back to the slabs instead of four
+        d2p, lmax = self._edt_pencils(be.to_u8(local_im))
+        max_d2 = self._allreduce_max(lmax)
         radii = host.reference_sizes(sizes, max_d2)
         if max_d2 == host.INF_U32:
             from .filters import _result_for_no_background
@@ -364,8 +382,10 @@ class ShardedVolume:
         idx = be.zeros(n, torch.uint8)
         if len(T) == 0:
             return be.expand(idx, np.array([0.0])).view(*lshape)
-        cls = be.classify(d2, T)
-        del d2
+        cls = be.classify(d2p, T)
+        del d2p
+        if self.world > 1:
+            cls = self._pencils_to_slab(cls, torch.uint8)
         st = None
         if access_limited:
             inl = None
