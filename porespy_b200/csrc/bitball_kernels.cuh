@@ -20,9 +20,13 @@
 #include "common.cuh"
 #include "xdist_kernels.cuh"
 
-#define BB_MAX_PAIRS 1280
+#define BB_MAX_PAIRS 1408         // pi * 400 pairs + every ring padded to a multiple of 4
 #define BB_TY 8                    // output rows of a block: 8 (y) x 4 (z) -- one warp each
 #define BB_TZ 4
+// Every ring is padded to a multiple of 4 pairs with copies of its last pair (OR is idempotent), so
+// the kernels fetch the word offsets of 4 pairs with one 16-byte shared-memory load: the offsets
+// live in the kernel parameter (constant bank), and an indexed LDC per pair was 40 % of the
+// stall samples of the dilation kernel.
 struct BallPairs {                 // (dy,dz) offsets sorted by x-allowance a, descending
     int W;                         // largest allowance = ceil(sqrt(T)) - 1
     unsigned short ring_end[34];   // pairs of ring a are [ring_end[a + 1], ring_end[a]) for a = W..0
@@ -106,6 +110,9 @@ lt_bitball_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ wri
                   int nz_src, int z_off)
 {
     if (gate && *gate == 0) return;
+    __shared__ __align__(16) int s_off[BB_MAX_PAIRS];
+    for (int i = threadIdx.x; i < (int)bp.ring_end[0]; i += blockDim.x) s_off[i] = bp.e[i].x;
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int y = blockIdx.y * BB_TY + (warp & (BB_TY - 1)), z = blockIdx.z * BB_TZ + (warp >> 3);
     if (y >= ny || z >= nz) return;
@@ -131,12 +138,12 @@ lt_bitball_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ wri
         }
         const int pend = bp.ring_end[a];
         if (interior) {
-            for (; p + 4 <= pend; p += 4) {
-                const uint32_t s0 = __ldg(base + bp.e[p].x), s1 = __ldg(base + bp.e[p + 1].x);
-                const uint32_t s2 = __ldg(base + bp.e[p + 2].x), s3 = __ldg(base + bp.e[p + 3].x);
+            for (; p < pend; p += 4) {                 // rings are padded to whole groups of 4
+                const int4 o = *reinterpret_cast<const int4 *>(s_off + p);
+                const uint32_t s0 = __ldg(base + o.x), s1 = __ldg(base + o.y);
+                const uint32_t s2 = __ldg(base + o.z), s3 = __ldg(base + o.w);
                 A |= ((s0 | s1) | (s2 | s3)) & inmask;
             }
-            for (; p < pend; ++p) A |= __ldg(base + bp.e[p].x) & inmask;
         } else {
             for (; p < pend; ++p) {
                 const int2 e = bp.e[p];
@@ -161,6 +168,9 @@ lt_bitball2_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ wr
                    int nz_src, int z_off)
 {
     if (gate && *gate == 0) return;
+    __shared__ __align__(16) int s_off[BB_MAX_PAIRS];
+    for (int i = threadIdx.x; i < (int)bp.ring_end[0]; i += blockDim.x) s_off[i] = bp.e[i].x;
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int y = blockIdx.y * BB_TY + (warp & (BB_TY - 1)), z = blockIdx.z * BB_TZ + (warp >> 3);
     if (y >= ny || z >= nz) return;
@@ -188,16 +198,14 @@ lt_bitball2_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ wr
         }
         const int pend = bp.ring_end[a];
         if (interior) {
-            for (; p + 2 <= pend; p += 2) {
-                const uint2 s0 = __ldg(reinterpret_cast<const uint2 *>(base + bp.e[p].x));
-                const uint2 s1 = __ldg(reinterpret_cast<const uint2 *>(base + bp.e[p + 1].x));
-                A0 |= (s0.x | s1.x) & inmask;
-                A1 |= (s0.y | s1.y) & inmask;
-            }
-            for (; p < pend; ++p) {
-                const uint2 s0 = __ldg(reinterpret_cast<const uint2 *>(base + bp.e[p].x));
-                A0 |= s0.x & inmask;
-                A1 |= s0.y & inmask;
+            for (; p < pend; p += 4) {                 // rings are padded to whole groups of 4
+                const int4 o = *reinterpret_cast<const int4 *>(s_off + p);
+                const uint2 s0 = __ldg(reinterpret_cast<const uint2 *>(base + o.x));
+                const uint2 s1 = __ldg(reinterpret_cast<const uint2 *>(base + o.y));
+                const uint2 s2 = __ldg(reinterpret_cast<const uint2 *>(base + o.z));
+                const uint2 s3 = __ldg(reinterpret_cast<const uint2 *>(base + o.w));
+                A0 |= ((s0.x | s1.x) | (s2.x | s3.x)) & inmask;
+                A1 |= ((s0.y | s1.y) | (s2.y | s3.y)) & inmask;
             }
         } else {
             for (; p < pend; ++p) {

@@ -317,7 +317,9 @@ __device__ __forceinline__ uint32_t cone_step(uint32_t v, int (&c)[4])
 }
 
 #define ZS_UNROLL 8
-__global__ void __launch_bounds__(256)
+// 8 blocks per SM (<= 32 registers): the plane/4 threads of a 1024^2 plane then fit in ONE wave
+// (262144 <= 148 * 2048); with 48 registers the launch ran 1.4 waves and its tail idled the SMs
+__global__ void __launch_bounds__(256, 8)
 lt_zsweep_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo, int nlo,
                  const uint8_t *__restrict__ m_hi, int nhi, uint8_t *__restrict__ idx, int nz,
                  int64_t plane, uint32_t val, const int *__restrict__ gate)

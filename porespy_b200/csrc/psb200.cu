@@ -834,6 +834,13 @@ static bool build_ball_pairs(uint32_t T, int64_t ny, int64_t nw, BallPairs &bp)
                 bp.e[cnt].y = (int)(((uint32_t)dy & 0xFFFFu) | ((uint32_t)dz << 16));
                 ++cnt;
             }
+        // pad the ring to a multiple of 4 pairs with copies of its last pair (cnt stays a multiple of 4
+        // across rings, so an empty ring needs nothing)
+        while (cnt % 4 != 0) {
+            if (cnt >= BB_MAX_PAIRS) return false;
+            bp.e[cnt] = bp.e[cnt - 1];
+            ++cnt;
+        }
         bp.ring_end[a] = (unsigned short)cnt;
     }
     bp.ring_end[W + 1] = 0;
