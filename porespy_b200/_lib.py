@@ -138,6 +138,11 @@ class Context:
         """Thresholds T <= tmax run the bit-parallel dilation kernels (0 = never)."""
         check(self.lib.psb200_set_option(self.handle, b"bit_tmax", int(tmax)))
 
+    def set_bit4(self, on):
+        """Bit path: four-words-per-lane dilation kernel for rows of 1024 / 2048 / 4096 voxels (default);
+        off = the one- / two-words-per-lane kernels for every shape."""
+        check(self.lib.psb200_set_option(self.handle, b"bit4", 1 if on else 0))
+
     def set_edt16(self, on):
         """EDT y/z passes: run the 16-bit two-voxels-per-instruction kernel first (default); off =
         the uint32 kernel only."""

@@ -225,3 +225,85 @@ lt_bitball2_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ wr
     bb_commit(written, idx, wi, A0, val);
     bb_commit(written, idx, wi + 1, A1, val);
 }
+
+// Four words per lane (one 16-byte load per (dy,dz) pair and lane): a row of nw = 4 * LPR words is
+// owned by LPR lanes, a warp owns 32 / LPR rows.  Per word this issues half the instructions of
+// the one-word kernel (the OR work is the same, the address arithmetic, the load and the loop
+// overhead are shared by four words) for the same L1 wavefronts per byte.
+//   LPR = 8 (nx = 1024): warp = 4 rows, block (256 threads) = 8 (y) x 4 (z) rows
+//   LPR = 16 (nx = 2048): warp = 2 rows, block = 8 x 2;   LPR = 32 (nx = 4096): warp = 1 row, block = 8 x 1
+// grid = (1, ceil(ny / 8), ceil(nz / TZ)), TZ = 32 / LPR.  seeds / written 16-byte aligned.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+lt_bitball4_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ written,
+                   uint8_t *__restrict__ idx, int nz, int ny,
+                   const __grid_constant__ BallPairs bp, uint32_t val, const int *__restrict__ gate,
+                   int nz_src, int z_off)
+{
+    if (gate && *gate == 0) return;
+    constexpr int RPW = 32 / LPR;          // rows per warp
+    constexpr int NW = 4 * LPR;            // words per row
+    __shared__ __align__(16) int s_off[BB_MAX_PAIRS];
+    __shared__ int s_dyz[BB_MAX_PAIRS];
+    for (int i = threadIdx.x; i < (int)bp.ring_end[0]; i += blockDim.x) {
+        s_off[i] = bp.e[i].x;
+        s_dyz[i] = bp.e[i].y;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int r = warp * RPW + lane / LPR;                 // row of the block: 8 (y) x RPW (z)
+    const int lr = lane % LPR;                             // lane inside the row
+    const int y = blockIdx.y * 8 + (r & 7), z = blockIdx.z * RPW + (r >> 3);
+    const bool rowok = y < ny && z < nz;
+    const uint32_t inmask = rowok ? 0xFFFFFFFFu : 0u;
+    const int yc = rowok ? y : 0, zc = rowok ? z : 0;      // rows past the end read row (0, 0) and are masked
+    const int zs = zc + z_off;
+    const uint32_t *base = seeds + ((int64_t)zs * ny + yc) * NW + 4 * lr;
+    asm volatile("" : "+l"(base));
+    const int W = bp.W;
+    const bool interior = yc - W >= 0 && yc + W < ny && zs - W >= 0 && zs + W < nz_src;
+
+    uint32_t A0 = 0, A1 = 0, A2 = 0, A3 = 0;
+    int p = 0;
+    for (int a = W; a >= 0; --a) {
+        if (a < W) {
+            uint32_t l = __shfl_up_sync(0xFFFFFFFFu, A3, 1), rr = __shfl_down_sync(0xFFFFFFFFu, A0, 1);
+            if (lr == 0) l = 0;                            // row boundary (also a warp-internal one)
+            if (lr == LPR - 1) rr = 0;
+            const uint32_t n0 = A0 | (A0 << 1) | (l >> 31) | (A0 >> 1) | (A1 << 31);
+            const uint32_t n1 = A1 | (A1 << 1) | (A0 >> 31) | (A1 >> 1) | (A2 << 31);
+            const uint32_t n2 = A2 | (A2 << 1) | (A1 >> 31) | (A2 >> 1) | (A3 << 31);
+            const uint32_t n3 = A3 | (A3 << 1) | (A2 >> 31) | (A3 >> 1) | (rr << 31);
+            A0 = n0; A1 = n1; A2 = n2; A3 = n3;
+        }
+        const int pend = bp.ring_end[a];
+        if (interior) {
+            for (; p < pend; p += 4) {                     // rings are padded to whole groups of 4
+                const int4 o = *reinterpret_cast<const int4 *>(s_off + p);
+                const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(base + o.x));
+                const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(base + o.y));
+                const uint4 s2 = __ldg(reinterpret_cast<const uint4 *>(base + o.z));
+                const uint4 s3 = __ldg(reinterpret_cast<const uint4 *>(base + o.w));
+                A0 |= ((s0.x | s1.x) | (s2.x | s3.x)) & inmask;
+                A1 |= ((s0.y | s1.y) | (s2.y | s3.y)) & inmask;
+                A2 |= ((s0.z | s1.z) | (s2.z | s3.z)) & inmask;
+                A3 |= ((s0.w | s1.w) | (s2.w | s3.w)) & inmask;
+            }
+        } else {
+            for (; p < pend; ++p) {
+                const int e = s_dyz[p];
+                const int yy = yc + (int)(short)(e & 0xFFFF), zz = zs + (e >> 16);
+                if ((unsigned)yy < (unsigned)ny && (unsigned)zz < (unsigned)nz_src) {
+                    const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(base + s_off[p]));
+                    A0 |= s0.x & inmask; A1 |= s0.y & inmask; A2 |= s0.z & inmask; A3 |= s0.w & inmask;
+                }
+            }
+        }
+    }
+    if (!rowok) return;
+    const int64_t wi = ((int64_t)z * ny + y) * NW + 4 * lr;
+    bb_commit(written, idx, wi, A0, val);
+    bb_commit(written, idx, wi + 1, A1, val);
+    bb_commit(written, idx, wi + 2, A2, val);
+    bb_commit(written, idx, wi + 3, A3, val);
+}

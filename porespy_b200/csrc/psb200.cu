@@ -92,6 +92,7 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->profile = 0;
     c->bit_tmax = 200;
     c->edt16 = 1;
+    c->bit4 = 1;
     c->flag_slot = 0;
     CUDA_TRY(cudaMalloc(&c->flags, 64 * sizeof(int)));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -136,6 +137,10 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
     if (!strcmp(name, "bit_tmax")) {
         if (value < 0 || value > 400) return fail(PSB200_ERR_INVALID, "set_option: bit_tmax must be in [0,400]");
         ctx->bit_tmax = (int)value;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "bit4")) {
+        ctx->bit4 = value ? 1 : 0;
         return PSB200_OK;
     }
     if (!strcmp(name, "edt16")) {
@@ -870,6 +875,24 @@ static int lt_bitball_impl(psb200_ctx *ctx, const uint32_t *seedbits, int64_t nz
     const bool two = nw > 32 && (nw % 2 == 0) && ((reinterpret_cast<uintptr_t>(seedbits) & 7u) == 0);
     const int seg = two ? (nw <= 64 ? 64 : 60) : (nw <= 32 ? 32 : 30);
     dim3 grid((unsigned)((nw + seg - 1) / seg), (unsigned)((ny + BB_TY - 1) / BB_TY), (unsigned)((nz + BB_TZ - 1) / BB_TZ));
+    // rows of 32 / 64 / 128 words: four words per lane (16-byte loads)
+    const bool four = ctx->bit4 && (nw == 32 || nw == 64 || nw == 128) &&
+                      ((((uintptr_t)seedbits | (uintptr_t)written) & 15u) == 0);
+    if (four) {
+        const int lpr = nw / 4, tz = 32 / lpr;
+        dim3 g4(1, (unsigned)((ny + 7) / 8), (unsigned)((nz + tz - 1) / tz));
+        {
+            ProfScope ps__(ctx, st, K_LT_BITBALL);
+            if (lpr == 8)
+                lt_bitball4_kernel<8><<<g4, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
+            else if (lpr == 16)
+                lt_bitball4_kernel<16><<<g4, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
+            else
+                lt_bitball4_kernel<32><<<g4, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
+        }
+        LAUNCH_CHECK(ctx);
+        return PSB200_OK;
+    }
     {
         ProfScope ps__(ctx, st, K_LT_BITBALL);
         if (two)

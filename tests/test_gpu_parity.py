@@ -37,7 +37,8 @@ def set_algo(psb, name):
     from porespy_b200 import _lib
     ctx = _lib.context()
     ctx.set_algo(_lib.ALGO_GENERIC if name == "generic" else _lib.ALGO_FAST)
-    ctx.set_bit_tmax({"nobit": 0, "allbit": 400}.get(name, 200))
+    ctx.set_bit_tmax({"nobit": 0, "allbit": 400, "allbit1": 400}.get(name, 200))
+    ctx.set_bit4(name != "allbit1")          # allbit1: one- / two-words-per-lane kernels only
 
 
 def rand_image(shape, p, seed):
@@ -134,10 +135,13 @@ LT_CASES = [((40, 36, 44), 12, 0.6), ((48, 52), 9, 0.6), ((30, 30, 30), [5, 3.5,
             ((40, 50, 96), 20, 0.6), ((3, 40, 1120), 14, 0.7), ((5, 4, 2048), [9, 4, 2.5, 1], 0.8),
             ((70, 2080), 16, 0.7),
             # even word counts above 32: two words per lane (64-word rows, 60-word segments with halo lanes)
-            ((6, 24, 2112), [9, 4, 2.5, 1], 0.8), ((2, 30, 4160), 14, 0.7), ((40, 2048), 12, 0.7)]
+            ((6, 24, 2112), [9, 4, 2.5, 1], 0.8), ((2, 30, 4160), 14, 0.7), ((40, 2048), 12, 0.7),
+            # rows of exactly 1024 / 2048 / 4096 voxels: four words per lane (interior and border rows)
+            ((40, 50, 1024), 20, 0.6), ((6, 21, 1024), [9, 4, 2.5, 1], 0.8), ((3, 12, 4096), 10, 0.7),
+            ((37, 1024), 14, 0.7)]
 
 
-@pytest.mark.parametrize("algo", ["fast", "nobit", "allbit", "generic"])
+@pytest.mark.parametrize("algo", ["fast", "nobit", "allbit", "allbit1", "generic"])
 @pytest.mark.parametrize("shape,sizes,por", LT_CASES)
 def test_local_thickness_vs_oracle(psb, algo, shape, sizes, por):
     set_algo(psb, algo)
