@@ -58,6 +58,7 @@ extern "C" {
 /* flags */
 #define PSB200_FLAG_IDX_PREINIT 1     /* local_thickness_idx: idx already holds 0 / PSB200_IDX_KEEP */
 #define PSB200_FLAG_EXPAND_MERGE 1    /* expand_idx_f64: leave out[] untouched where idx is 0 or KEEP */
+#define PSB200_FLAG_HOST_PREZEROED 1  /* expand_idx_f64_to_host: out_host already holds 0.0 everywhere */
 
 typedef struct psb200_ctx psb200_ctx;
 typedef void *psb200_stream;          /* cudaStream_t */
@@ -196,7 +197,14 @@ int psb200_expand_idx_f64(psb200_ctx *ctx, const uint8_t *idx, const double *lut
 int psb200_expand_idx_f64_to_host(psb200_ctx *ctx, const uint8_t *idx, const double *lut_host,
                                   int nlut, double *out_host, int64_t n, uint8_t *stage_host,
                                   size_t stage_bytes, void *ws, size_t ws_bytes, int cpu_permille,
-                                  int nthreads, psb200_stream stream);
+                                  int nthreads, int flags, psb200_stream stream);
+/* Zero out_host[0, n) with `nthreads` background host threads (0 = all hardware threads) while the
+ * GPU computes; psb200_host_zero_wait joins them (and must be called exactly once per job, also on
+ * error paths).  With PSB200_FLAG_HOST_PREZEROED the epilogue above then skips the 64-byte lines
+ * whose eight radius indices are all 0 -- solid or never-invaded voxels, a third of a porous
+ * volume -- instead of storing 0.0 into them again. */
+int psb200_host_zero_begin(double *out_host, int64_t n, int nthreads, void **job);
+int psb200_host_zero_wait(void *job);
 /* idx[i] = out[i] != 0 ? PSB200_IDX_KEEP : 0   (continuation across >253 thresholds) */
 int psb200_mark_written(psb200_ctx *ctx, const double *out, uint8_t *idx, int64_t n,
                         psb200_stream stream);

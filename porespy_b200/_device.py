@@ -23,6 +23,11 @@ def ptr(t):
 
 
 PIN_MIN_BYTES = 1 << 20      # below this a pageable copy is as fast as a pinned one
+# Opt-in (PSB200_HOST_PREZERO=1): float64 results from 2^28 bytes on are zeroed by background host
+# threads during the GPU phase and the epilogue skips all-zero lines.  Measured on this pool's B200
+# boxes it LOSES (e2e 135 -> 154 ms at 1024^3): the host memory system is the bottleneck of the
+# epilogue, and zeroing adds 8.6 GB of stores to it for the 3 GB it saves later.
+PREZERO_MIN_BYTES = (1 << 28) if os.environ.get("PSB200_HOST_PREZERO", "0") == "1" else (1 << 62)
 
 
 def pinned_empty(shape, dtype=np.uint8):
@@ -76,20 +81,61 @@ HOST_WIDEN_PERMILLE = int(os.environ.get("PSB200_HOST_WIDEN_PERMILLE", "1000"))
 HOST_WIDEN_THREADS = int(os.environ.get("PSB200_HOST_WIDEN_THREADS", "0"))      # 0: all hardware threads
 
 
-def expand_idx_to_host(ctx, idx, lut, shape, chunk=1 << 26, cpu_permille=None, nthreads=None):
+class HostResult:
+    """The float64 result array of one call, in page-locked host memory, being zeroed by background
+    host threads of the library (psb200_host_zero_begin) while the GPU computes.  `finish()` must
+    run exactly once (it joins the threads); `array()` hands the numpy view out."""
+
+    def __init__(self, ctx, shape, nthreads=None):
+        torch = _torch()
+        self.ctx, self.shape = ctx, tuple(shape)
+        self.n = int(np.prod(self.shape)) if len(self.shape) else 1
+        self.host = torch.empty(self.n, dtype=torch.float64, pin_memory=True)
+        self.job = ctypes.c_void_p()
+        if nthreads is None:
+            # leave two hardware threads to the launching thread and the driver
+            nthreads = max(1, (os.cpu_count() or 1) - 2)
+        _lib.check(ctx.lib.psb200_host_zero_begin(ctypes.c_void_p(self.host.data_ptr()), self.n, int(nthreads),
+                                                  ctypes.byref(self.job)))
+
+    def finish(self):
+        if self.job is not None and self.job.value:
+            _lib.check(self.ctx.lib.psb200_host_zero_wait(self.job))
+        self.job = None
+
+    def array(self):
+        self.finish()
+        return self.host.numpy().reshape(self.shape)
+
+    def __del__(self):
+        try:
+            self.finish()
+        except Exception:
+            pass
+
+
+def expand_idx_to_host(ctx, idx, lut, shape, chunk=1 << 26, cpu_permille=None, nthreads=None, result=None):
     """Radius-index map (uint8, device) -> float64 numpy in page-locked memory, without ever holding
     the 8 B/voxel map in HBM (psb200_expand_idx_f64_to_host): part of the volume leaves the device
     as index bytes and is widened by host threads of the library, the rest is widened on the
-    device chunk by chunk while the previous chunk is on its way over PCIe."""
+    device chunk by chunk while the previous chunk is on its way over PCIe.  `result`: a
+    HostResult started earlier in the call (its buffer is zero by now, so all-zero lines are skipped)."""
     torch = _torch()
     n = idx.numel()
     if n * 8 < PIN_MIN_BYTES:
+        if result is not None:
+            result.finish()
         out = torch.empty(n, dtype=torch.float64, device=idx.device)
         expand_idx(ctx, idx, lut, out)
         return out.cpu().numpy().reshape(shape)
     cpu_permille = HOST_WIDEN_PERMILLE if cpu_permille is None else int(cpu_permille)
     nthreads = HOST_WIDEN_THREADS if nthreads is None else int(nthreads)
-    host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    flags = 0
+    if result is not None:
+        result.finish()
+        host, flags = result.host, _lib.FLAG_HOST_PREZEROED
+    else:
+        host = torch.empty(n, dtype=torch.float64, pin_memory=True)
     stage_n = (n * cpu_permille) // 1000
     stage = torch.empty(max(stage_n, 1), dtype=torch.uint8, pin_memory=True)
     chunk = min(chunk, n)
@@ -98,7 +144,7 @@ def expand_idx_to_host(ctx, idx, lut, shape, chunk=1 << 26, cpu_permille=None, n
     _lib.check(ctx.lib.psb200_expand_idx_f64_to_host(
         ctx.handle, ptr(idx), lut.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(lut),
         ctypes.c_void_p(host.data_ptr()), n, ctypes.c_void_p(stage.data_ptr()), stage.numel(),
-        ptr(ws), ws.numel(), cpu_permille, nthreads, stream_ptr()))
+        ptr(ws), ws.numel(), cpu_permille, nthreads, flags, stream_ptr()))
     del stage
     return host.numpy().reshape(shape)
 

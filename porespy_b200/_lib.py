@@ -18,6 +18,7 @@ INLETS_NONE, INLETS_FACES, INLETS_MASK = 0, 1, 2
 ALGO_FAST, ALGO_GENERIC = 0, 1
 FLAG_IDX_PREINIT = 1
 FLAG_EXPAND_MERGE = 1
+FLAG_HOST_PREZEROED = 1
 MAX_THRESHOLDS = 253
 MAX_DIM = 32767
 INF_U32 = 0xFFFFFFFF
@@ -78,7 +79,9 @@ SIGNATURES = {
     "psb200_lt_bitball": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _u32, _i64, _i64, _i64, _vp]),
     "psb200_expand_idx_f64": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _i32, _vp]),
     "psb200_expand_idx_f64_to_host": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _vp, _sz,
-                                             _vp, _sz, _i32, _i32, _vp]),
+                                             _vp, _sz, _i32, _i32, _i32, _vp]),
+    "psb200_host_zero_begin": (_i32, [_vp, _i64, _i32, _c.POINTER(_vp)]),
+    "psb200_host_zero_wait": (_i32, [_vp]),
     "psb200_mark_written": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "psb200_uf_begin": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _vp]),
     "psb200_uf_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),

@@ -20,13 +20,17 @@
 #include "common.cuh"
 
 // out[i] = lut[idx[i]] for i in [0, cnt); `out` 16-byte aligned, cnt even except for a tail.
-static void host_widen_slice(const uint8_t *idx, const double *lut, double *out, int64_t cnt)
+// prezeroed: out already holds 0.0 everywhere (psb200_host_zero_begin), so a group of 8 voxels whose
+// indices are all 0 (solid, or never invaded: lut[0] == 0.0) needs no store -- on a porous volume
+// about a third of the 64-byte lines.
+static void host_widen_slice(const uint8_t *idx, const double *lut, double *out, int64_t cnt, bool prezeroed)
 {
     int64_t i = 0;
     if ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
         for (; i + 8 <= cnt; i += 8) {
             uint64_t w;
             memcpy(&w, idx + i, 8);
+            if (prezeroed && w == 0) continue;
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
                 const __m128d v = _mm_set_pd(lut[(w >> (8 * j + 8)) & 0xFFu], lut[(w >> (8 * j)) & 0xFFu]);
@@ -35,6 +39,24 @@ static void host_widen_slice(const uint8_t *idx, const double *lut, double *out,
         }
     }
     for (; i < cnt; ++i) out[i] = lut[idx[i]];
+}
+
+// ---- output buffer zeroed in the background while the GPU computes
+struct HostZeroJob {
+    std::vector<std::thread> pool;
+};
+
+static void host_zero_slice(double *out, int64_t cnt)
+{
+    int64_t i = 0;
+    while (i < cnt && (reinterpret_cast<uintptr_t>(out + i) & 15u)) out[i++] = 0.0;
+    const __m128d z = _mm_setzero_pd();
+    for (; i + 8 <= cnt; i += 8) {
+        _mm_stream_pd(out + i, z); _mm_stream_pd(out + i + 2, z);
+        _mm_stream_pd(out + i + 4, z); _mm_stream_pd(out + i + 6, z);
+    }
+    for (; i < cnt; ++i) out[i] = 0.0;
+    _mm_sfence();
 }
 
 struct HostEpilogueStreams {
@@ -46,7 +68,7 @@ struct HostEpilogueStreams {
 static int host_epilogue_run(psb200_ctx *ctx, HostEpilogueStreams &hs, const uint8_t *idx_dev,
                              const double *lut_host, int nlut, double *out_host, int64_t n,
                              uint8_t *stage_host, size_t stage_bytes, void *ws_dev, size_t ws_bytes,
-                             int cpu_permille, int nthreads, cudaStream_t st, int (*launch_expand)(
+                             int cpu_permille, int nthreads, bool prezeroed, cudaStream_t st, int (*launch_expand)(
                                  psb200_ctx *, const uint8_t *, const double *, int, double *, int64_t, cudaStream_t))
 {
     if (!hs.idx_copy) CUDA_TRY(cudaStreamCreateWithFlags(&hs.idx_copy, cudaStreamNonBlocking));
@@ -86,13 +108,14 @@ static int host_epilogue_run(psb200_ctx *ctx, HostEpilogueStreams &hs, const uin
         pool.reserve(nthreads);
         for (int t = 0; t < nthreads; ++t) {
             pool.emplace_back([=, &arrived, &thread_err, &lut]() {
+                const bool pz = prezeroed && lut[0] == 0.0;
                 if (cudaSetDevice(device) != cudaSuccess) { thread_err = 1; return; }
                 const int64_t per = ((CH_A / nthreads) + 7) & ~(int64_t)7;
                 const int64_t s = (int64_t)t * per, e = s + per < CH_A ? s + per : CH_A;
                 for (int c = 0; c < ncA; ++c) {
                     if (cudaEventSynchronize(arrived[c]) != cudaSuccess) { thread_err = 1; return; }
                     if (s < e)
-                        host_widen_slice(stage_host + (int64_t)c * CH_A + s, lut, out_host + (int64_t)c * CH_A + s, e - s);
+                        host_widen_slice(stage_host + (int64_t)c * CH_A + s, lut, out_host + (int64_t)c * CH_A + s, e - s, pz);
                 }
                 _mm_sfence();
             });

@@ -1157,7 +1157,7 @@ static int launch_expand_chunk(psb200_ctx *ctx, const uint8_t *idx, const double
 extern "C" int psb200_expand_idx_f64_to_host(psb200_ctx *ctx, const uint8_t *idx, const double *lut_host, int nlut,
                                              double *out_host, int64_t n, uint8_t *stage_host, size_t stage_bytes,
                                              void *ws, size_t ws_bytes, int cpu_permille, int nthreads,
-                                             psb200_stream stream)
+                                             int flags, psb200_stream stream)
 {
     if (!ctx || !idx || !lut_host || !out_host || nlut < 1 || nlut > 254 || n < 0)
         return fail(PSB200_ERR_INVALID, "expand_idx_f64_to_host: bad argument");
@@ -1168,8 +1168,33 @@ extern "C" int psb200_expand_idx_f64_to_host(psb200_ctx *ctx, const uint8_t *idx
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (nthreads == 0) nthreads = (int)std::thread::hardware_concurrency();
     return host_epilogue_run(ctx, g_epilogue_streams[ctx->device], idx, lut_host, nlut, out_host, n, stage_host,
-                             stage_bytes, ws, ws_bytes, cpu_permille, nthreads, (cudaStream_t)stream,
-                             launch_expand_chunk);
+                             stage_bytes, ws, ws_bytes, cpu_permille, nthreads,
+                             (flags & PSB200_FLAG_HOST_PREZEROED) != 0, (cudaStream_t)stream, launch_expand_chunk);
+}
+
+extern "C" int psb200_host_zero_begin(double *out_host, int64_t n, int nthreads, void **job)
+{
+    if (!out_host || n < 0 || !job || nthreads < 0 || nthreads > 1024)
+        return fail(PSB200_ERR_INVALID, "host_zero_begin: bad argument");
+    if (nthreads == 0) nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    HostZeroJob *j = new HostZeroJob();
+    const int64_t per = ((n / nthreads) + 8) & ~(int64_t)7;
+    for (int t = 0; t < nthreads; ++t) {
+        const int64_t s = (int64_t)t * per, e = s + per < n ? s + per : n;
+        if (s < e) j->pool.emplace_back([=]() { host_zero_slice(out_host + s, e - s); });
+    }
+    *job = j;
+    return PSB200_OK;
+}
+
+extern "C" int psb200_host_zero_wait(void *job)
+{
+    if (!job) return PSB200_OK;
+    HostZeroJob *j = reinterpret_cast<HostZeroJob *>(job);
+    for (auto &th : j->pool) th.join();
+    delete j;
+    return PSB200_OK;
 }
 
 extern "C" int psb200_mark_written(psb200_ctx *ctx, const double *out, uint8_t *idx, int64_t n,

@@ -32,7 +32,7 @@ def _result_for_no_background(shape, radii):
     return out
 
 
-def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True):
+def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True, result=None):
     """Device loop over the effective thresholds (in groups of <= 253) -> float64 radius map."""
     torch = dev._torch()
     n = int(np.prod(shape))
@@ -42,7 +42,7 @@ def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True):
     if ngroups == 1 and as_numpy:
         # common case: the float64 map (F:1178) is only materialised on the host
         dev.local_thickness_idx(ctx, d2, T, idx, inlets_u8, inlet_mode, ndim, shape, 0)
-        return dev.expand_idx_to_host(ctx, idx, np.concatenate([[0.0], R]), shape)
+        return dev.expand_idx_to_host(ctx, idx, np.concatenate([[0.0], R]), shape, result=result)
     out = torch.empty(n, dtype=torch.float64, device=d2.device)
     for g in range(ngroups):
         Tg, Rg = T[g * G:(g + 1) * G], R[g * G:(g + 1) * G]
@@ -83,6 +83,19 @@ def porosimetry(im, sizes: int = 25, inlets=None, access_limited: bool = True,
     if ndim == 0 or int(np.prod(shape)) == 0:
         return np.zeros(shape)
     ctx = _lib.context()
+    # numpy result (F:1178 `imresults = np.zeros(...)`): the page-locked float64 array is zeroed by
+    # background host threads while the GPU computes, so the epilogue only stores non-zero lines
+    result = None
+    if as_numpy and int(np.prod(shape)) * 8 >= dev.PREZERO_MIN_BYTES:
+        result = dev.HostResult(ctx, shape)
+    try:
+        return _porosimetry_device(ctx, im, shape, ndim, sizes, inlets, access_limited, as_numpy, torch, result)
+    finally:
+        if result is not None:
+            result.finish()
+
+
+def _porosimetry_device(ctx, im, shape, ndim, sizes, inlets, access_limited, as_numpy, torch, result):
     im_u8 = dev.to_device_u8(im, ctx)
     d2, max_d2 = dev.edt_run(ctx, im_u8, shape, want_max=True)    # max fused into the last pass
     del im_u8
@@ -106,7 +119,7 @@ def porosimetry(im, sizes: int = 25, inlets=None, access_limited: bool = True,
         res = _result_for_no_background(shape, radii)
         return res if as_numpy else torch.from_numpy(res).to(d2.device)
     T, R = host.effective_thresholds(radii, max_d2)
-    return _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=as_numpy)
+    return _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=as_numpy, result=result)
 
 
 def local_thickness(im, sizes: int = 25, mode: str = "hybrid", divs: int = 1):

@@ -397,3 +397,45 @@ def test_host_epilogue_split(psb, permille, threads):
     out = dev.expand_idx_to_host(ctx, idx, lut, (n,), cpu_permille=permille, nthreads=threads, chunk=1 << 22)
     assert out.dtype == np.float64 and out.shape == (n,)
     assert np.array_equal(out, lut[idx.cpu().numpy()])
+
+
+def test_host_epilogue_prezeroed(psb):
+    """HostResult: the output zeroed in the background, the epilogue skipping all-zero lines -- same map
+    (the pinned buffer is recycled between calls, so stale non-zero data would show up here)."""
+    import torch
+    from porespy_b200 import _device as dev
+    from porespy_b200 import _lib
+    ctx = _lib.context()
+    n = 2 * (1 << 24) + 777
+    lut = np.concatenate([[0.0], np.linspace(30, 1, 20)])
+    for seed in (0, 1):
+        g = torch.Generator(device="cuda")
+        g.manual_seed(seed)
+        idx = torch.randint(0, 21, (n,), generator=g, device="cuda", dtype=torch.uint8)
+        idx[torch.rand(n, generator=g, device="cuda") < 0.6] = 0                     # long and short runs of zeros
+        idx[(1 << 22):(1 << 23)] = 0
+        res = dev.HostResult(ctx, (n,))
+        out = dev.expand_idx_to_host(ctx, idx, lut, (n,), result=res)
+        assert np.array_equal(out, lut[idx.cpu().numpy()])
+        del out, res
+
+
+def test_local_thickness_large_numpy_result(psb):
+    """Public API on a volume large enough for the background-zeroed host result (>= 2^28 bytes of
+    float64; opt-in, so switched on here)."""
+    from porespy_b200 import _device as dev
+    monkey = dev.PREZERO_MIN_BYTES
+    dev.PREZERO_MIN_BYTES = 1 << 28
+    try:
+        _large_numpy_result(psb)
+    finally:
+        dev.PREZERO_MIN_BYTES = monkey
+
+
+def _large_numpy_result(psb):
+    im = oc.blobs([320, 320, 352], porosity=0.6, blobiness=2, seed=3)
+    a = psb.filters.local_thickness(im, sizes=12)
+    b = psb.filters.local_thickness(im, sizes=12)            # second call reuses the recycled pinned buffer
+    want = oc.local_thickness(im, sizes=12, mode="dt")
+    assert_same(a, want, "large numpy result")
+    assert_same(b, want, "large numpy result, second call")
