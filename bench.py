@@ -304,7 +304,9 @@ def run_ours(args):
     # result bytes that cross PCIe: index bytes for the share widened by host threads, float64 for the rest
     from porespy_b200 import _device as pdev
     share = pdev.HOST_WIDEN_PERMILLE / 1000.0
-    h2d = im_host.nbytes * world
+    # input bytes that cross PCIe: volumes from UPLOAD_PACK_MIN_BYTES on are packed to one bit per voxel by host threads
+    packed = im_host.nbytes >= pdev.UPLOAD_PACK_MIN_BYTES
+    h2d = (im_host.nbytes // 8 if packed else im_host.nbytes) * world
     d2h = int(im_host.size * (share * 1 + (1.0 - share) * 8)) * world
 
     def step_e2e():
@@ -330,6 +332,8 @@ def run_ours(args):
            "ShardedVolume.local_thickness(numpy bool slab, page-locked, to_host=True) -> numpy float64 slab, every rank")
     e2e = {"value": nvox / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3, "steps": n_e2e, "api": api,
+           "input": (f"numpy bool volume of {im_host.nbytes * world} bytes in host memory, packed to bits by the library's host "
+                     f"threads before the upload (psb200_upload_mask_u8)" if packed else "numpy bool volume, uploaded as bytes"),
            "result": f"float64 map of {im_host.size * 8 * world} bytes in host memory; {pdev.HOST_WIDEN_PERMILLE / 10:.0f} % of "
                      f"the volume leaves the device as 1-byte radius indices and is widened by the library's host "
                      f"threads (psb200_expand_idx_f64_to_host)"}

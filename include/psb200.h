@@ -198,6 +198,14 @@ int psb200_expand_idx_f64_to_host(psb200_ctx *ctx, const uint8_t *idx, const dou
                                   int nlut, double *out_host, int64_t n, uint8_t *stage_host,
                                   size_t stage_bytes, void *ws, size_t ws_bytes, int cpu_permille,
                                   int nthreads, int flags, psb200_stream stream);
+/* Host prologue: upload a one-byte-per-voxel HOST volume (numpy bool / uint8, foreground <=> byte != 0,
+ * F:1126 `im > 0`) as 0/1 bytes into dst (device, n bytes).  Host threads pack it to one bit per
+ * voxel chunk by chunk, the chunks cross PCIe at an eighth of the size, a kernel spreads the bits.
+ * stage_host: page-locked, >= ceil(n/8) bytes, must stay alive until `stream` has passed the call;
+ * ws: device, >= ceil(n/8) bytes.  The host source may be reused on return. */
+int psb200_upload_mask_u8(psb200_ctx *ctx, const uint8_t *src_host, int64_t n, uint8_t *dst,
+                          uint8_t *stage_host, size_t stage_bytes, void *ws, size_t ws_bytes,
+                          int nthreads, psb200_stream stream);
 /* Zero out_host[0, n) with `nthreads` background host threads (0 = all hardware threads) while the
  * GPU computes; psb200_host_zero_wait joins them (and must be called exactly once per job, also on
  * error paths).  With PSB200_FLAG_HOST_PREZEROED the epilogue above then skips the 64-byte lines

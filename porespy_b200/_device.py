@@ -166,7 +166,34 @@ def to_device_u8(arr, ctx):
         a = np.ascontiguousarray(a).view(np.uint8)
     else:
         a = np.ascontiguousarray(a != 0).view(np.uint8)
+    if a.nbytes >= UPLOAD_PACK_MIN_BYTES:
+        return upload_mask(ctx, a)
     return torch.from_numpy(a).to(dev, non_blocking=False)      # a single DMA when `a` is page-locked
+
+
+UPLOAD_PACK_MIN_BYTES = int(os.environ.get("PSB200_UPLOAD_PACK_MIN_BYTES", str(1 << 26)))
+_upload_stage = {}
+
+
+def upload_mask(ctx, a):
+    """Large host volumes cross PCIe as one bit per voxel (psb200_upload_mask_u8): host threads of the
+    library pack `byte != 0` chunk by chunk while earlier chunks are in flight, a kernel spreads the
+    bits to 0/1 bytes.  The page-locked staging buffer is kept per device (grow-only): the copies
+    read it asynchronously, and every public call that uploads a numpy volume ends with a
+    synchronising download, so it is idle again before the next upload."""
+    torch = _torch()
+    n = a.size
+    nb = (n + 7) // 8
+    stage = _upload_stage.get(ctx.device)
+    if stage is None or stage.numel() < nb:
+        stage = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        _upload_stage[ctx.device] = stage
+    out = torch.empty(a.shape, dtype=torch.uint8, device=f"cuda:{ctx.device}")
+    ws = ctx.workspace(nb + 256)
+    _lib.check(ctx.lib.psb200_upload_mask_u8(
+        ctx.handle, ctypes.c_void_p(a.ctypes.data), n, ptr(out), ctypes.c_void_p(stage.data_ptr()), stage.numel(),
+        ptr(ws), ws.numel(), 0, stream_ptr()))
+    return out
 
 
 def edt_run(ctx, im_u8, shape, as_f32=False, want_max=False):

@@ -80,6 +80,7 @@ SIGNATURES = {
     "psb200_expand_idx_f64": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _i32, _vp]),
     "psb200_expand_idx_f64_to_host": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _vp, _sz,
                                              _vp, _sz, _i32, _i32, _i32, _vp]),
+    "psb200_upload_mask_u8": (_i32, [_vp, _vp, _i64, _vp, _vp, _sz, _vp, _sz, _i32, _vp]),
     "psb200_host_zero_begin": (_i32, [_vp, _i64, _i32, _c.POINTER(_vp)]),
     "psb200_host_zero_wait": (_i32, [_vp]),
     "psb200_mark_written": (_i32, [_vp, _vp, _vp, _i64, _vp]),

@@ -161,3 +161,84 @@ static int host_epilogue_run(psb200_ctx *ctx, HostEpilogueStreams &hs, const uin
                     cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     return PSB200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Host prologue: the input volume of the reference API is one byte per voxel (numpy bool / uint8),
+// of which the kernels use one bit (`byte != 0`, F:1126 `im > 0`).  Host threads pack the volume to
+// bits chunk by chunk (a compare and a movemask per 16 voxels), every finished chunk crosses PCIe
+// at an eighth of the size while the next ones are being packed, and one kernel on the device
+// spreads the bits back to 0/1 bytes.
+__global__ void __launch_bounds__(256)
+mask_unpack_kernel(const uint8_t *__restrict__ bits, uint8_t *__restrict__ out, int64_t nbytes_bits, int64_t n)
+{
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes_bits; i += step) {
+        const uint32_t b = bits[i];
+        // bit j of b -> byte j (0 / 1)
+        const uint32_t lo = ((b & 0xFu) * 0x00204081u) & 0x01010101u;
+        const uint32_t hi = ((b >> 4) * 0x00204081u) & 0x01010101u;
+        if (8 * i + 8 <= n) *reinterpret_cast<uint2 *>(out + 8 * i) = make_uint2(lo, hi);
+        else
+            for (int j = 0; j < 8 && 8 * i + j < n; ++j) out[8 * i + j] = (uint8_t)((b >> j) & 1u);
+    }
+}
+
+// bits[i] bit j = (src[8 i + j] != 0) for the voxels [v0, v1); v0 % 8 == 0
+static void host_pack_slice(const uint8_t *src, uint8_t *bits, int64_t v0, int64_t v1)
+{
+    int64_t v = v0;
+    const __m128i zero = _mm_setzero_si128();
+    for (; v + 16 <= v1; v += 16) {
+        const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + v));
+        const uint32_t m = ~(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(x, zero)) & 0xFFFFu;
+        bits[v >> 3] = (uint8_t)(m & 0xFFu);
+        bits[(v >> 3) + 1] = (uint8_t)(m >> 8);
+    }
+    for (; v < v1; v += 8) {
+        uint32_t m = 0;
+        for (int j = 0; j < 8 && v + j < v1; ++j) m |= (src[v + j] != 0 ? 1u : 0u) << j;
+        bits[v >> 3] = (uint8_t)m;
+    }
+}
+
+// Synchronous with respect to the host source (it may be reused on return); the device side is
+// ordered on `st`.  stage_host: page-locked, >= ceil(n / 8) bytes; bits_dev: device, same size.
+static int host_upload_mask(psb200_ctx *ctx, const uint8_t *src_host, int64_t n, uint8_t *dst_dev,
+                            uint8_t *stage_host, uint8_t *bits_dev, int nthreads, cudaStream_t st)
+{
+    const int64_t CH = 1LL << 23;                          // voxels per chunk (8 MiB in, 1 MiB of bits)
+    const int nch = (int)((n + CH - 1) / CH);
+    std::vector<std::atomic<int>> done(nch);
+    for (auto &d : done) d.store(0, std::memory_order_relaxed);
+    std::atomic<int> next{0};
+    std::vector<std::thread> pool;
+    pool.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t)
+        pool.emplace_back([&]() {
+            for (int c = next.fetch_add(1); c < nch; c = next.fetch_add(1)) {
+                const int64_t v0 = (int64_t)c * CH, v1 = v0 + CH < n ? v0 + CH : n;
+                host_pack_slice(src_host, stage_host, v0, v1);
+                done[c].store(1, std::memory_order_release);
+            }
+        });
+    cudaError_t err = cudaSuccess;
+    for (int c = 0; c < nch; ++c) {
+        while (!done[c].load(std::memory_order_acquire)) std::this_thread::yield();
+        const int64_t v0 = (int64_t)c * CH, v1 = v0 + CH < n ? v0 + CH : n;
+        const int64_t b0 = v0 >> 3, b1 = (v1 + 7) >> 3;
+        if (err == cudaSuccess)
+            err = cudaMemcpyAsync(bits_dev + b0, stage_host + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st);
+    }
+    for (auto &th : pool) th.join();
+    if (err != cudaSuccess) return fail(PSB200_ERR_CUDA, "upload_mask_u8: %s", cudaGetErrorString(err));
+    const int64_t nb = (n + 7) >> 3;
+    int g = (int)((nb + 255) / 256);
+    if (g > ctx->sm_count * 16) g = ctx->sm_count * 16;
+    mask_unpack_kernel<<<g, 256, 0, st>>>(bits_dev, dst_dev, nb, n);
+    ctx->launches++;
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(PSB200_ERR_CUDA, "upload_mask_u8: %s", cudaGetErrorString(err));
+    // the staging buffer is read by the copies still in flight: the caller keeps it alive until the
+    // stream has passed this point (the Python host synchronises on the max-d2 read-back of the EDT)
+    return PSB200_OK;
+}

@@ -1172,6 +1172,23 @@ extern "C" int psb200_expand_idx_f64_to_host(psb200_ctx *ctx, const uint8_t *idx
                              (flags & PSB200_FLAG_HOST_PREZEROED) != 0, (cudaStream_t)stream, launch_expand_chunk);
 }
 
+extern "C" int psb200_upload_mask_u8(psb200_ctx *ctx, const uint8_t *src_host, int64_t n, uint8_t *dst,
+                                     uint8_t *stage_host, size_t stage_bytes, void *ws, size_t ws_bytes,
+                                     int nthreads, psb200_stream stream)
+{
+    if (!ctx || !src_host || !dst || !stage_host || !ws || n < 0 || nthreads < 0 || nthreads > 1024)
+        return fail(PSB200_ERR_INVALID, "upload_mask_u8: bad argument");
+    const size_t nb = (size_t)((n + 7) >> 3);
+    if (stage_bytes < nb || ws_bytes < nb)
+        return fail(PSB200_ERR_WORKSPACE, "upload_mask_u8 needs %zu bytes of staging and of device workspace", nb);
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (nthreads == 0) nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    return host_upload_mask(ctx, src_host, n, dst, stage_host, reinterpret_cast<uint8_t *>(ws), nthreads,
+                            (cudaStream_t)stream);
+}
+
 extern "C" int psb200_host_zero_begin(double *out_host, int64_t n, int nthreads, void **job)
 {
     if (!out_host || n < 0 || !job || nthreads < 0 || nthreads > 1024)

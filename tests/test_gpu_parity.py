@@ -439,3 +439,22 @@ def _large_numpy_result(psb):
     want = oc.local_thickness(im, sizes=12, mode="dt")
     assert_same(a, want, "large numpy result")
     assert_same(b, want, "large numpy result, second call")
+
+
+@pytest.mark.parametrize("dtype", [np.bool_, np.uint8])
+def test_upload_mask_bit_packed(psb, dtype):
+    """psb200_upload_mask_u8: a host volume uploaded as bits arrives as (byte != 0) bytes, for sizes
+    that are not multiples of the chunk, of 16 or of 8, and for uint8 values other than 0 / 1."""
+    from porespy_b200 import _device as dev
+    from porespy_b200 import _lib
+    ctx = _lib.context()
+    rng = np.random.default_rng(5)
+    for n in (3 * (1 << 23) + 8 * 1001 + 5, (1 << 23), 77):
+        a = rng.integers(0, 4, n).astype(np.uint8)
+        a[rng.random(n) < 0.5] = 0
+        if dtype == np.bool_:
+            a = a != 0
+        got = dev.upload_mask(ctx, a.view(np.uint8)).cpu().numpy()
+        assert np.array_equal(got, (a != 0).astype(np.uint8)), n
+    big = oc.blobs([160, 640, 704], porosity=0.6, blobiness=2, seed=1)      # 72 MB: takes the packed path
+    assert_same(psb.edt(big), oc.edt(big), "edt through the bit-packed upload")
