@@ -319,9 +319,12 @@ def run_ours(args):
     del res
     barrier()
     t0 = time.perf_counter()
+    per_call = []
     for _ in range(n_e2e):
+        t1 = time.perf_counter()
         res = step_e2e()
         del res
+        per_call.append(time.perf_counter() - t1)
     barrier()
     te = (time.perf_counter() - t0) / n_e2e
     if world > 1:
@@ -331,7 +334,8 @@ def run_ours(args):
     api = ("porespy_b200.filters.local_thickness(numpy bool, page-locked) -> numpy float64" if world == 1 else
            "ShardedVolume.local_thickness(numpy bool slab, page-locked, to_host=True) -> numpy float64 slab, every rank")
     e2e = {"value": nvox / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3, "steps": n_e2e, "api": api,
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3, "steps": n_e2e,
+           "ms_per_call": [round(t * 1e3, 1) for t in per_call], "api": api,
            "input": (f"numpy bool volume of {im_host.nbytes * world} bytes in host memory, packed to bits by the library's host "
                      f"threads before the upload (psb200_upload_mask_u8)" if packed else "numpy bool volume, uploaded as bytes"),
            "result": f"float64 map of {im_host.size * 8 * world} bytes in host memory; {pdev.HOST_WIDEN_PERMILLE / 10:.0f} % of "
@@ -393,7 +397,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-edge", type=int, default=320)
     ap.add_argument("--ref-edge", type=int, default=192)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

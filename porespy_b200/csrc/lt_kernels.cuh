@@ -40,21 +40,34 @@ __device__ __forceinline__ uint32_t classify_one(uint32_t D, const uint32_t *sT,
 struct TArg { uint32_t t[256]; };      // thresholds, strictly descending, passed by value
 struct LutArg { double v[256]; };      // radius of every index, passed by value
 
+// Squared distances on this path are small (a few thousand on porous media), so the class comes from
+// a table in shared memory (one byte load per voxel); values beyond the table take the binary search.
+#define CLS_LUT 8192
 __global__ void __launch_bounds__(256)
 lt_classify_kernel(const uint32_t *__restrict__ d2, uint8_t *__restrict__ cls, int64_t n,
                    const __grid_constant__ TArg Targ, int nT)
 {
     __shared__ uint32_t sT[256];
+    __shared__ uint8_t lut[CLS_LUT];
     for (int i = threadIdx.x; i < nT; i += blockDim.x) sT[i] = Targ.t[i];
+    __syncthreads();
+    // d >= T[0] is class 0, so the table only spans [0, T[0])
+    const uint32_t T0 = nT > 0 ? sT[0] : 0u;
+    const int nlut = (int)min(T0, (uint32_t)CLS_LUT);
+    for (int i = threadIdx.x; i < nlut; i += blockDim.x) lut[i] = (uint8_t)classify_one((uint32_t)i, sT, nT);
     __syncthreads();
     const int64_t n4 = n >> 2;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t i = t0; i < n4; i += step) {
-        uint4 v = __ldg(reinterpret_cast<const uint4 *>(d2) + i);
-        uint32_t c = pack4(classify_one(v.x, sT, nT), classify_one(v.y, sT, nT),
-                           classify_one(v.z, sT, nT), classify_one(v.w, sT, nT));
-        reinterpret_cast<uint32_t *>(cls)[i] = c;
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(d2) + i);
+        const uint32_t d[4] = {v.x, v.y, v.z, v.w};
+        uint32_t c[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            c[j] = d[j] >= T0 ? (nT > 0 ? 0u : classify_one(d[j], sT, nT))
+                              : (d[j] < (uint32_t)nlut ? (uint32_t)lut[d[j]] : classify_one(d[j], sT, nT));
+        reinterpret_cast<uint32_t *>(cls)[i] = pack4(c[0], c[1], c[2], c[3]);
     }
     for (int64_t i = (n4 << 2) + t0; i < n; i += step)
         cls[i] = (uint8_t)classify_one(d2[i], sT, nT);
