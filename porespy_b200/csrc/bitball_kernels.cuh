@@ -55,6 +55,31 @@ lt_pack_kernel(const uint8_t *__restrict__ cls, uint32_t *__restrict__ bits, int
     }
 }
 
+// Two consecutive radii from one read of the class map: bits = (cls <= k), bits2 = (cls <= k + 1).
+__global__ void __launch_bounds__(256)
+lt_pack2_kernel(const uint8_t *__restrict__ cls, uint32_t *__restrict__ bits, uint32_t *__restrict__ bits2,
+                int64_t nwords, int k, const int *__restrict__ gate)
+{
+    if (gate && *gate == 0) return;
+    const uint32_t n = (uint32_t)(k + 1), n2 = n + 1u;     // non-seed <=> byte >= n (resp. n2)
+    const uint32_t nl4 = (n & 0x7Fu) * 0x01010101u, sel = n < 128u ? 0xFFFFFFFFu : 0u;
+    const uint32_t ml4 = (n2 & 0x7Fu) * 0x01010101u, sel2 = n2 < 128u ? 0xFFFFFFFFu : 0u;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += step) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(cls) + 2 * w);
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(cls) + 2 * w + 1);
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t m = 0, m2 = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            m |= gather_bit7(swar_ge(v[q], nl4, sel) ^ 0x80808080u) << (4 * q);
+            m2 |= gather_bit7(swar_ge(v[q], ml4, sel2) ^ 0x80808080u) << (4 * q);
+        }
+        bits[w] = m;
+        bits2[w] = m2;
+    }
+}
+
 // written[row][w] bit b = (idx[row][32 w + b] != 0)
 __global__ void __launch_bounds__(256)
 lt_wmask_kernel(const uint8_t *__restrict__ idx, uint32_t *__restrict__ written, int64_t nwords)
