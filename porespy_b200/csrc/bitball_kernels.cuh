@@ -259,7 +259,7 @@ lt_bitball2_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ wr
 //   LPR = 16 (nx = 2048): warp = 2 rows, block = 8 x 2;   LPR = 32 (nx = 4096): warp = 1 row, block = 8 x 1
 // grid = (1, ceil(ny / 8), ceil(nz / TZ)), TZ = 32 / LPR.  seeds / written 16-byte aligned.
 template <int LPR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 lt_bitball4_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ written,
                    uint8_t *__restrict__ idx, int nz, int ny,
                    const __grid_constant__ BallPairs bp, uint32_t val, const int *__restrict__ gate,
