@@ -396,6 +396,21 @@ class ShardedVolume:
             st = be.uf_begin(cls, inl, lshape, self.zstarts[self.rank], nz)
             self.flood_sweeps = []
         written = None
+        # Not access-limited: the seed bits of every bit-path radius are a function of the class map
+        # alone, so the class bytes of the deepest bit-path halo travel ONCE and each rank packs its
+        # extended slab itself -- one halo exchange instead of one per bit-path radius.
+        cls_ext, ext_lo, ext_hi = None, 0, 0
+        if st is None and self.world > 1:
+            wb = [host.isqrt(int(Tk) - 1) for Tk in T if be.bit_ok(lshape, int(Tk))]
+            if wb and max(wb) > 0:
+                ext_lo, ext_hi = self._halo_depths(max(wb))
+                plane_b = ny * nx
+                cls_ext = be.empty((ext_lo + nzl + ext_hi) * plane_b, torch.uint8)
+                cls_ext[ext_lo * plane_b:(ext_lo + nzl) * plane_b] = cls
+                self.exchange_halo(cls[:ext_lo * plane_b] if ext_lo else None,
+                                   cls[(nzl - ext_hi) * plane_b:] if ext_hi else None,
+                                   cls_ext[:ext_lo * plane_b] if ext_lo else None,
+                                   cls_ext[(ext_lo + nzl) * plane_b:] if ext_hi else None)
         for k, Tk in enumerate(T):
             Tk = int(Tk)
             W = host.isqrt(Tk - 1)
@@ -414,6 +429,13 @@ class ShardedVolume:
                     written = be.zeros(n // 32, torch.int32)
                     if k > 0:
                         be.wmask(idx, written, lshape)
+                if cls_ext is not None:
+                    nze = ext_lo + nzl + ext_hi
+                    ext = be.empty(nze * plane, torch.int32)
+                    be.pack(cls_ext, k, ext, (nze, ny, nx))
+                    be.bitball(ext, nze, ext_lo, written, idx, k, Tk, lshape)
+                    del ext
+                    continue
                 ext = be.empty((nlo + nzl + nhi) * plane, torch.int32)
                 mine = ext[nlo * plane:(nlo + nzl) * plane]
                 be.pack(cls, k, mine, lshape)
