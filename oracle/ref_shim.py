@@ -21,7 +21,7 @@ What is real and what is stubbed
   `np.sqrt(float32(d2))` returned -- the same `float32(sqrt(d2))` contract as the
   wheel (black_border=False: the image border is not background).
 * `skimage.morphology.{ball,disk,square,cube}` -- trivial restatements.
-* `dask.delayed/compute` -- serial; `skimage.segmentation.relabel_sequential` -- numpy.
+* `dask.delayed/compute` -- serial; `skimage.segmentation.relabel_sequential`, `clear_border` -- numpy.
 * everything else: inert MagicMock attributes (never on the hot path).
 """
 import importlib.abc
@@ -151,9 +151,24 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
             module.square, module.cube = _square, _cube
         elif name == "skimage.segmentation":
             module.relabel_sequential = _relabel_sequential
+            module.clear_border = _clear_border
         elif name == "dask":
             module.delayed = _Delayed
             module.compute = _dask_compute
+
+
+def _clear_border(labels, **kwargs):
+    """skimage.segmentation.clear_border for a label image: labels that touch any face become 0
+    (default buffer_size=0, bgval=0 -- the only form PoreSpy uses, filters/_funcs.py:411)."""
+    labels = np.array(labels, copy=True)
+    touching = set()
+    for ax in range(labels.ndim):
+        for side in (0, -1):
+            touching.update(np.unique(np.take(labels, side, axis=ax)).tolist())
+    touching.discard(0)
+    if touching:
+        labels[np.isin(labels, list(touching))] = 0
+    return labels
 
 
 _installed = False

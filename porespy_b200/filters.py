@@ -3,6 +3,8 @@
 * `porosimetry`             /root/reference/src/porespy/filters/_funcs.py:1032-1212
 * `local_thickness`         /root/reference/src/porespy/filters/_funcs.py:947-1029
 * `trim_disconnected_blobs` /root/reference/src/porespy/filters/_funcs.py:1215-1270
+* the other users of the same flood: `find_disconnected_voxels` :352-421,
+  `fill_blind_pores` :424-462, `trim_floating_solid` :465-503, `trim_nonpercolating_paths` :506-555
 
 Host code here only does what numpy does in the reference prologue (squeeze, radii, inlet
 validation); all voxel work runs in libpsb200.so on the GPU.  There is no CPU fallback.
@@ -17,7 +19,8 @@ from . import _lib
 
 logger = logging.getLogger(__name__)
 
-__all__ = ["porosimetry", "local_thickness", "trim_disconnected_blobs"]
+__all__ = ["porosimetry", "local_thickness", "trim_disconnected_blobs", "find_disconnected_voxels",
+           "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths"]
 
 
 def _result_for_no_background(shape, radii):
@@ -163,3 +166,117 @@ def trim_disconnected_blobs(im, inlets, strel=None):
     shape3 = host.shape3(im.shape)
     keep = dev.to_host(dev.flood(ctx, fg, inl, conn, shape3).view(*im.shape)).astype(bool)
     return keep * im
+
+
+# ------------------------------------------------------------------ other users of the flood
+def _conn_of(ndim, conn):
+    """F:393-406: 4 / 6 = faces only, None / 8 / 26 = full neighbourhood."""
+    small, big = (4, 8) if ndim == 2 else (6, 26)
+    if conn == small:
+        return small
+    if conn in (None, big):
+        return big
+    raise Exception("Received conn is not valid")
+
+
+def _strel_conn(ndim, strel, default):
+    """Connectivity of a 3x3(x3) structuring element as `scipy.ndimage.label` would use it."""
+    full = 26 if ndim == 3 else 8
+    cross = 6 if ndim == 3 else 4
+    if strel is None:
+        return default
+    s = np.asarray(strel) != 0
+    if s.shape != (3,) * ndim:
+        raise NotImplementedError("only 3x3(x3) connectivity structuring elements are supported")
+    grid = np.indices(s.shape) - 1
+    if np.array_equal(s, np.abs(grid).sum(axis=0) <= 1):
+        return cross
+    if s.all():
+        return full
+    raise NotImplementedError("strel must be the cross (ball(1)/disk(1)) or the full cube")
+
+
+def _face_views(t):
+    """The 2 * ndim faces of a device tensor as (index tuple) list."""
+    out = []
+    for ax in range(t.dim()):
+        for side in (0, -1):
+            out.append((slice(None),) * ax + (side,))
+    return out
+
+
+def _reached_from(ctx, fg, seeds, conn):
+    """Foreground voxels connected (within the foreground) to the non-zero voxels of `seeds` (a subset
+    of the foreground): psb200_flood with the seeds as inlets."""
+    return dev.flood(ctx, fg.reshape(-1), seeds.reshape(-1), conn, host.shape3(tuple(fg.shape))).view(fg.shape)
+
+
+def find_disconnected_voxels(im, conn=None, surface=False):
+    r"""Voxels of `im` that are not connected to the image border (F:352-421); with `surface=True`
+    the voxels of every region that does not touch ALL faces.  Same arguments, same quirks: a region
+    is a `scipy.ndimage.label` component under the `conn` neighbourhood, and with `surface=True`
+    the background is reported as well when some face holds no background voxel (its label 0 then
+    drops out of the reference's `keep` set)."""
+    torch = dev._torch()
+    im = np.asarray(im)
+    if im.ndim not in (2, 3):
+        raise Exception("Received conn is not valid")
+    c = _conn_of(im.ndim, conn)
+    if im.size == 0:
+        return np.zeros(im.shape, dtype=bool)
+    ctx = _lib.context()
+    fg = dev.to_device_u8(im != 0, ctx).view(*im.shape)
+    if not surface:
+        seeds = torch.zeros_like(fg)
+        for f in _face_views(fg):
+            seeds[f] = fg[f]
+        reached = _reached_from(ctx, fg, seeds, c)
+        holes = (fg != 0) & (reached == 0)
+        return dev.to_host(holes.to(torch.uint8)).astype(bool)
+    keep = None
+    bg_on_every_face = True
+    for f in _face_views(fg):
+        seeds = torch.zeros_like(fg)
+        seeds[f] = fg[f]
+        r = _reached_from(ctx, fg, seeds, c) != 0
+        keep = r if keep is None else (keep & r)
+        bg_on_every_face &= bool((fg[f] == 0).any().item())
+    holes = (fg != 0) & ~keep
+    if not bg_on_every_face:
+        holes |= fg == 0
+    return dev.to_host(holes.to(torch.uint8)).astype(bool)
+
+
+def fill_blind_pores(im, conn=None, surface=False):
+    r"""Fills the pores that `find_disconnected_voxels` reports (F:424-462)."""
+    im = np.copy(im)
+    im[find_disconnected_voxels(im, conn=conn, surface=surface)] = False
+    return im
+
+
+def trim_floating_solid(im, conn=None, surface=False):
+    r"""Removes the solid that `find_disconnected_voxels(~im)` reports (F:465-503)."""
+    im = np.copy(im)
+    im[find_disconnected_voxels(~im, conn=conn, surface=surface)] = True
+    return im
+
+
+def trim_nonpercolating_paths(im, inlets, outlets, strel=None):
+    r"""Keeps the regions of `im` that hold an inlet voxel and an outlet voxel (F:506-555).  `strel`
+    is the connectivity `scipy.ndimage.label` gets: None = its default, the cross (4 / 6 neighbours);
+    the cross and the full 3x3(x3) cube are recognised."""
+    torch = dev._torch()
+    im = np.asarray(im)
+    if im.ndim not in (2, 3):
+        raise ValueError("trim_nonpercolating_paths supports 2-D and 3-D images")
+    c = _strel_conn(im.ndim, strel, 6 if im.ndim == 3 else 4)
+    if im.size == 0:
+        return np.zeros(im.shape, dtype=bool)
+    ctx = _lib.context()
+    fg = dev.to_device_u8(im != 0, ctx).view(*im.shape)
+    hit = None
+    for mask in (inlets, outlets):
+        m = dev.to_device_u8(np.asarray(mask) != 0, ctx).view(*im.shape)
+        r = _reached_from(ctx, fg, m * fg, c) != 0
+        hit = r if hit is None else (hit & r)
+    return dev.to_host(hit.to(torch.uint8)).astype(bool)

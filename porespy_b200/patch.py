@@ -1,5 +1,7 @@
 """Monkey-patch points for unmodified PoreSpy scripts:
-`sys.modules['edt']`, `porespy.filters.{porosimetry, local_thickness, trim_disconnected_blobs}`
+`sys.modules['edt']`, `porespy.filters.{porosimetry, local_thickness, trim_disconnected_blobs}` (and the
+other flood users: `find_disconnected_voxels`, `fill_blind_pores`, `trim_floating_solid`,
+`trim_nonpercolating_paths`)
 and the `edt` name bound inside `porespy.filters._funcs` / `porespy.tools._funcs`."""
 import sys
 import types
@@ -21,7 +23,8 @@ def install(patch_edt_module=True):
     ps = sys.modules.get("porespy")
     if ps is not None and "porespy" not in _saved:
         _saved["porespy"] = {}
-        for name in ("porosimetry", "local_thickness", "trim_disconnected_blobs"):
+        for name in ("porosimetry", "local_thickness", "trim_disconnected_blobs", "find_disconnected_voxels",
+                     "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths"):
             for mod in (ps.filters, getattr(ps.filters, "_funcs", None)):
                 if mod is not None and hasattr(mod, name):
                     _saved["porespy"][(mod, name)] = getattr(mod, name)

@@ -458,3 +458,46 @@ def test_upload_mask_bit_packed(psb, dtype):
         assert np.array_equal(got, (a != 0).astype(np.uint8)), n
     big = oc.blobs([160, 640, 704], porosity=0.6, blobiness=2, seed=1)      # 72 MB: takes the packed path
     assert_same(psb.edt(big), oc.edt(big), "edt through the bit-packed upload")
+
+
+def test_flood_users(psb, golden):
+    """The other users of the flood kernel against the reference-generated goldens
+    and the oracle: find_disconnected_voxels (incl. surface=True and its label-0 quirk), fill_blind_pores,
+    trim_floating_solid, trim_nonpercolating_paths."""
+    f = psb.filters
+    g = golden.flood_users
+    im = g.mask("im")
+    sl = im[:, :, 0]
+    for got, key in ((f.find_disconnected_voxels(sl), "h2d8"), (f.find_disconnected_voxels(sl, conn=4), "h2d4"),
+                     (f.find_disconnected_voxels(im), "h26"), (f.find_disconnected_voxels(im, conn=6), "h6"),
+                     (f.find_disconnected_voxels(im, surface=True), "h26_surface"),
+                     (f.find_disconnected_voxels(im, conn=6, surface=True), "h6_surface"),
+                     (f.find_disconnected_voxels(sl, conn=4, surface=True), "h2d4_surface"),
+                     (f.find_disconnected_voxels(g.mask("cap"), conn=6, surface=True), "cap_surface"),
+                     (f.fill_blind_pores(im), "fill_blind"), (f.fill_blind_pores(im, conn=6, surface=True), "fill_blind6s"),
+                     (f.trim_floating_solid(im), "trim_solid"), (f.trim_floating_solid(im, conn=6), "trim_solid6")):
+        assert_same(got, g.mask(key), key)
+    assert int(f.find_disconnected_voxels(im).sum()) == 55 and int(f.find_disconnected_voxels(im, conn=6).sum()) == 202
+    with pytest.raises(Exception, match="conn is not valid"):
+        f.find_disconnected_voxels(im, conn=5)
+    for name, key, axes in (("np2d_im", "np2d_ax", (0, 1)), ("np3d_im", "np3d_ax", (0, 1, 2))):
+        b = g.mask(name)
+        for ax in axes:
+            inl, outl = np.zeros_like(b), np.zeros_like(b)
+            inl[(slice(None),) * ax + (0,)] = True
+            outl[(slice(None),) * ax + (-1,)] = True
+            assert_same(f.trim_nonpercolating_paths(im=b, inlets=inl, outlets=outl), g.mask(f"{key}{ax}"), f"{key}{ax}")
+    b3 = g.mask("np3d_im")
+    inl, outl = np.zeros_like(b3), np.zeros_like(b3)
+    inl[0], outl[-1] = True, True
+    assert_same(f.trim_nonpercolating_paths(b3, inl, outl, strel=np.ones((3, 3, 3))), g.mask("np3d_ax0_cube"), "cube strel")
+    b = g.mask("np2d_none_im")
+    inl, outl = np.zeros_like(b), np.zeros_like(b)
+    inl[:, 0], outl[:, -1] = True, True
+    assert f.trim_nonpercolating_paths(b, inl, outl).sum() == 0
+    # random media against the oracle, odd shapes
+    for shape, p, conn in (((37, 41, 29), 0.45, 6), ((37, 41, 29), 0.3, None), ((90, 77), 0.55, 4), ((64, 50), 0.5, 8)):
+        r = rand_image(shape, p, 7)
+        for surface in (False, True):
+            assert_same(f.find_disconnected_voxels(r, conn=conn, surface=surface),
+                        oc.find_disconnected_voxels(r, conn=conn, surface=surface), f"random {shape} {conn} {surface}")

@@ -140,3 +140,39 @@ def test_numpy_integer_scalar_is_one_radius(golden):
     im = golden.blobs100.mask("im")[:40, :40, :40]
     lt = oc.local_thickness(im, sizes=np.int64(2), mode="dt")
     assert set(np.unique(lt)) <= {0.0, 2.0}
+
+
+def test_flood_users_golden(golden):
+    """find_disconnected_voxels / fill_blind_pores / trim_floating_solid / trim_nonpercolating_paths
+    restatements against what the reference's own source returned (tests/golden/flood_users.npz,
+    incl. the reference's golden counts TF:107-121 and the surface=True label-0 quirk)."""
+    g = golden.flood_users
+    im = g.mask("im")
+    sl = im[:, :, 0]
+    assert [int(oc.find_disconnected_voxels(a, conn=c).sum()) for a, c in ((sl, None), (sl, 4), (im, None), (im, 6))] \
+        == [477, 652, 55, 202]
+    assert np.array_equal(oc.find_disconnected_voxels(sl), g.mask("h2d8"))
+    assert np.array_equal(oc.find_disconnected_voxels(sl, conn=4), g.mask("h2d4"))
+    assert np.array_equal(oc.find_disconnected_voxels(im), g.mask("h26"))
+    assert np.array_equal(oc.find_disconnected_voxels(im, conn=6), g.mask("h6"))
+    assert np.array_equal(oc.find_disconnected_voxels(im, surface=True), g.mask("h26_surface"))
+    assert np.array_equal(oc.find_disconnected_voxels(im, conn=6, surface=True), g.mask("h6_surface"))
+    assert np.array_equal(oc.find_disconnected_voxels(sl, conn=4, surface=True), g.mask("h2d4_surface"))
+    assert np.array_equal(oc.find_disconnected_voxels(g.mask("cap"), conn=6, surface=True), g.mask("cap_surface"))
+    assert np.array_equal(oc.fill_blind_pores(im), g.mask("fill_blind"))
+    assert np.array_equal(oc.fill_blind_pores(im, conn=6, surface=True), g.mask("fill_blind6s"))
+    assert np.array_equal(oc.trim_floating_solid(im), g.mask("trim_solid"))
+    assert np.array_equal(oc.trim_floating_solid(im, conn=6), g.mask("trim_solid6"))
+    with pytest.raises(Exception, match="conn is not valid"):
+        oc.find_disconnected_voxels(im, conn=5)
+    for name, key, axes in (("np2d_im", "np2d_ax", (0, 1)), ("np3d_im", "np3d_ax", (0, 1, 2))):
+        b = g.mask(name)
+        for ax in axes:
+            inl, outl = np.zeros_like(b), np.zeros_like(b)
+            inl[(slice(None),) * ax + (0,)] = True
+            outl[(slice(None),) * ax + (-1,)] = True
+            assert np.array_equal(oc.trim_nonpercolating_paths(b, inl, outl), g.mask(f"{key}{ax}"))
+    b = g.mask("np2d_none_im")
+    inl, outl = np.zeros_like(b), np.zeros_like(b)
+    inl[:, 0], outl[:, -1] = True, True
+    assert oc.trim_nonpercolating_paths(b, inl, outl).sum() == 0                  # TF:149-160
