@@ -71,7 +71,7 @@ def _worker(rank, world, port, shape, sizes, bit_tmax, errq):
     (2, (25, 21, 32), 8, 0),            # byte pipeline only, uneven slabs and pencils
     (3, (31, 26, 64), [5, 3.2, 2, 1], 6),   # mixed: large radii bytes, small radii bits; 3 ranks
 ])
-def test_sharded_local_thickness_gloo(world, shape, sizes, bit_tmax):
+def _run_world(world, shape, sizes, bit_tmax):
     ctx = mp.get_context("spawn")
     errq = ctx.SimpleQueue()
     port = _free_port()
@@ -87,7 +87,18 @@ def test_sharded_local_thickness_gloo(world, shape, sizes, bit_tmax):
         if p.is_alive():
             p.terminate()
             msgs.append("worker timed out")
-    assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
+    if any(p.exitcode != 0 for p in procs) and not msgs:
+        msgs.append(f"worker exit codes {[p.exitcode for p in procs]}")
+    return msgs
+
+
+def test_sharded_local_thickness_gloo(world, shape, sizes, bit_tmax):
+    msgs = _run_world(world, shape, sizes, bit_tmax)
+    if msgs and not any("differ" in m or "AssertionError" in m for m in msgs):
+        # rendezvous trouble (the probed port was taken before the workers bound it): one more try;
+        # a wrong RESULT is never retried
+        msgs = _run_world(world, shape, sizes, bit_tmax)
+    assert not msgs, "\n".join(msgs)
 
 
 def test_partition_helpers():
