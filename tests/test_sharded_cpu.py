@@ -66,11 +66,6 @@ def _worker(rank, world, port, shape, sizes, bit_tmax, errq):
         raise
 
 
-@pytest.mark.parametrize("world,shape,sizes,bit_tmax", [
-    (2, (24, 20, 32), 8, 200),          # bit pipeline for every radius
-    (2, (25, 21, 32), 8, 0),            # byte pipeline only, uneven slabs and pencils
-    (3, (31, 26, 64), [5, 3.2, 2, 1], 6),   # mixed: large radii bytes, small radii bits; 3 ranks
-])
 def _run_world(world, shape, sizes, bit_tmax):
     ctx = mp.get_context("spawn")
     errq = ctx.SimpleQueue()
@@ -92,6 +87,11 @@ def _run_world(world, shape, sizes, bit_tmax):
     return msgs
 
 
+@pytest.mark.parametrize("world,shape,sizes,bit_tmax", [
+    (2, (24, 20, 32), 8, 200),          # bit pipeline for every radius
+    (2, (25, 21, 32), 8, 0),            # byte pipeline only, uneven slabs and pencils
+    (3, (31, 26, 64), [5, 3.2, 2, 1], 6),   # mixed: large radii bytes, small radii bits; 3 ranks
+])
 def test_sharded_local_thickness_gloo(world, shape, sizes, bit_tmax):
     msgs = _run_world(world, shape, sizes, bit_tmax)
     if msgs and not any("differ" in m or "AssertionError" in m for m in msgs):
