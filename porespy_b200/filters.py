@@ -205,6 +205,23 @@ def _face_views(t):
     return out
 
 
+def _mask_to_device(a, ctx, shape):
+    """Host array -> 0/1 uint8 device tensor of `shape` without a host-side copy for bool input (the bytes of
+    a numpy bool array already are 0/1; anything else is normalised on the device)."""
+    torch = dev._torch()
+    a = np.asarray(a)
+    t = dev.to_device_u8(a, ctx).view(*shape)
+    if a.dtype != np.bool_:
+        t = (t != 0).to(torch.uint8)
+    return t
+
+
+def _mask_to_host(t):
+    """0/1 device tensor -> numpy bool (the downloaded bytes are reinterpreted, not converted)."""
+    torch = dev._torch()
+    return dev.to_host(t.to(torch.uint8)).view(np.bool_)
+
+
 def _reached_from(ctx, fg, seeds, conn):
     """Foreground voxels connected (within the foreground) to the non-zero voxels of `seeds` (a subset
     of the foreground): psb200_flood with the seeds as inlets."""
@@ -225,14 +242,14 @@ def find_disconnected_voxels(im, conn=None, surface=False):
     if im.size == 0:
         return np.zeros(im.shape, dtype=bool)
     ctx = _lib.context()
-    fg = dev.to_device_u8(im != 0, ctx).view(*im.shape)
+    fg = _mask_to_device(im, ctx, im.shape)
     if not surface:
         seeds = torch.zeros_like(fg)
         for f in _face_views(fg):
             seeds[f] = fg[f]
         reached = _reached_from(ctx, fg, seeds, c)
         holes = (fg != 0) & (reached == 0)
-        return dev.to_host(holes.to(torch.uint8)).astype(bool)
+        return _mask_to_host(holes)
     keep = None
     bg_on_every_face = True
     for f in _face_views(fg):
@@ -244,7 +261,7 @@ def find_disconnected_voxels(im, conn=None, surface=False):
     holes = (fg != 0) & ~keep
     if not bg_on_every_face:
         holes |= fg == 0
-    return dev.to_host(holes.to(torch.uint8)).astype(bool)
+    return _mask_to_host(holes)
 
 
 def fill_blind_pores(im, conn=None, surface=False):
@@ -273,10 +290,10 @@ def trim_nonpercolating_paths(im, inlets, outlets, strel=None):
     if im.size == 0:
         return np.zeros(im.shape, dtype=bool)
     ctx = _lib.context()
-    fg = dev.to_device_u8(im != 0, ctx).view(*im.shape)
+    fg = _mask_to_device(im, ctx, im.shape)
     hit = None
     for mask in (inlets, outlets):
-        m = dev.to_device_u8(np.asarray(mask) != 0, ctx).view(*im.shape)
+        m = _mask_to_device(mask, ctx, im.shape)
         r = _reached_from(ctx, fg, m * fg, c) != 0
         hit = r if hit is None else (hit & r)
-    return dev.to_host(hit.to(torch.uint8)).astype(bool)
+    return _mask_to_host(hit)
