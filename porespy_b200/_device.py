@@ -64,16 +64,6 @@ def to_host(t):
     return h.numpy()
 
 
-_copy_streams = {}
-
-
-def copy_stream(device):
-    torch = _torch()
-    if device not in _copy_streams:
-        _copy_streams[device] = torch.cuda.Stream(device=device)
-    return _copy_streams[device]
-
-
 # share (per mille) of the volume whose radius index crosses PCIe as bytes and is widened to float64
 # by the library's host threads (psb200_expand_idx_f64_to_host); the rest is widened on the device.
 # Tuned on the B200 boxes of this pool (scripts/epilogue_probe.py); 0 = all-device path.
