@@ -236,6 +236,45 @@ def trim_nonpercolating_paths(im, inlets, outlets, strel=None):
     return np.isin(labels, hits[hits > 0]) if hits.size else np.zeros(labels.shape, dtype=bool)
 
 
+def make_contiguous_symmetric(im):
+    """T:842-847 (`make_contiguous(mode='symmetric')`): positive values are ranked 1..n, negative values
+    -1..-m by magnitude, zeros stay."""
+    im = np.array(im)
+
+    def relabel(a):                      # skimage relabel_sequential: sorted unique positive values -> 1..n
+        vals = np.unique(a)
+        vals = vals[vals > 0]
+        fw = np.zeros(int(a.max()) + 1 if a.size else 1, dtype=a.dtype)
+        fw[vals] = np.arange(1, len(vals) + 1)
+        return fw[a]
+
+    return relabel(im * (im >= 0)) - relabel(-im * (im < 0))
+
+
+def find_trapped_regions(seq, outlets=None, bins=25, return_mask=True):
+    """F:115-147 -- for every bin value i (descending): the voxels with seq >= i whose component (scipy's
+    default cross connectivity) holds no outlet voxel are trapped."""
+    import scipy.ndimage as spim
+    seq = np.copy(seq)
+    if outlets is None:
+        outlets = border_faces(seq.shape)
+    trapped = np.zeros_like(outlets)
+    if bins is None:
+        bins = np.unique(seq)[-1::-1]
+        bins = bins[bins > 0]
+    elif isinstance(bins, int):
+        bins = np.linspace(seq.max(), 1, bins)
+    for i in bins:
+        temp = seq >= i
+        labels = spim.label(temp)[0]
+        keep = np.setdiff1d(np.unique(labels[outlets]), np.array([0]))
+        trapped += temp * np.isin(labels, keep, invert=True)
+    if return_mask:
+        return trapped
+    seq[trapped] = -1
+    return make_contiguous_symmetric(seq)
+
+
 def _dilate_fft(mask, strel):
     """_fftmorphology.py:75-93 -- zero-pad by 1, fftconvolve 'same' > 0.1, crop."""
     from scipy.signal import fftconvolve

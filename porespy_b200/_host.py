@@ -101,3 +101,30 @@ def normalise_inlets(inlets, shape):
     if (inlets.shape == tuple(shape)) and (inlets.max() == 1):
         return inlets.astype(bool)
     raise Exception("inlets not valid, refer to docstring for info")
+
+
+def border_faces(shape):
+    """`get_border(shape, mode='faces')` (generators/_borders.py:93-100): every voxel with an index of 0
+    or n - 1 along some axis."""
+    out = np.zeros(tuple(shape), dtype=bool)
+    for ax in range(out.ndim):
+        sl = [slice(None)] * out.ndim
+        for side in (0, -1):
+            sl[ax] = side
+            out[tuple(sl)] = True
+    return out
+
+
+def make_contiguous_symmetric(im):
+    """`make_contiguous(im, mode='symmetric')` (tools/_funcs.py:842-847): positive values become their rank
+    1..n among the positive values, negative ones -1..-m by magnitude, zeros stay."""
+    im = np.array(im)
+
+    def rank_positive(a):
+        vals = np.unique(a)
+        vals = vals[vals > 0]
+        fw = np.zeros(int(a.max()) + 1 if a.size else 1, dtype=a.dtype)
+        fw[vals] = np.arange(1, len(vals) + 1)
+        return fw[a]
+
+    return rank_positive(im * (im >= 0)) - rank_positive(-im * (im < 0))

@@ -4,7 +4,8 @@
 * `local_thickness`         /root/reference/src/porespy/filters/_funcs.py:947-1029
 * `trim_disconnected_blobs` /root/reference/src/porespy/filters/_funcs.py:1215-1270
 * the other users of the same flood: `find_disconnected_voxels` :352-421,
-  `fill_blind_pores` :424-462, `trim_floating_solid` :465-503, `trim_nonpercolating_paths` :506-555
+  `fill_blind_pores` :424-462, `trim_floating_solid` :465-503, `trim_nonpercolating_paths` :506-555,
+  `find_trapped_regions` :73-147
 
 Host code here only does what numpy does in the reference prologue (squeeze, radii, inlet
 validation); all voxel work runs in libpsb200.so on the GPU.  There is no CPU fallback.
@@ -20,7 +21,7 @@ from . import _lib
 logger = logging.getLogger(__name__)
 
 __all__ = ["porosimetry", "local_thickness", "trim_disconnected_blobs", "find_disconnected_voxels",
-           "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths"]
+           "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths", "find_trapped_regions"]
 
 
 def _result_for_no_background(shape, radii):
@@ -297,3 +298,43 @@ def trim_nonpercolating_paths(im, inlets, outlets, strel=None):
         r = _reached_from(ctx, fg, m * fg, c) != 0
         hit = r if hit is None else (hit & r)
     return _mask_to_host(hit)
+
+
+def find_trapped_regions(seq, outlets=None, bins: int = 25, return_mask: bool = True):
+    r"""Trapped regions of an invasion sequence (F:73-147): for every bin value i, descending, the
+    voxels with `seq >= i` that are not connected (cross neighbourhood, scipy's default) to an outlet
+    voxel of the same set.  One flood per bin on the device, as in the reference's loop; the bins
+    (`None`: every sequence value, int: `np.linspace(seq.max(), 1, bins)`) are the reference's own
+    numpy expressions.  `return_mask=False` relabels on the host like `make_contiguous('symmetric')`."""
+    torch = dev._torch()
+    seq = np.copy(seq)
+    if seq.ndim not in (2, 3):
+        raise ValueError("find_trapped_regions supports 2-D and 3-D images")
+    if outlets is None:
+        outlets = host.border_faces(seq.shape)
+    outlets = np.asarray(outlets)
+    if outlets.dtype != np.bool_:
+        raise NotImplementedError("outlets must be a boolean mask")
+    if bins is None:
+        bins = np.unique(seq)[-1::-1]
+        bins = bins[bins > 0]
+    elif isinstance(bins, int):
+        bins = np.linspace(seq.max(), 1, bins)
+    conn = 6 if seq.ndim == 3 else 4
+    ctx = _lib.context()
+    seq_t = torch.from_numpy(np.ascontiguousarray(seq)).to(f"cuda:{ctx.device}")
+    out_t = _mask_to_device(outlets, ctx, seq.shape)
+    trapped = torch.zeros(seq.shape, dtype=torch.bool, device=seq_t.device)
+    for i in bins:
+        # the comparison runs in numpy's result type for (seq dtype, bin value), like `seq >= i` (F:133)
+        thr = np.asarray(i)
+        cmp_dtype = np.result_type(seq.dtype, thr.dtype)
+        a = seq_t if cmp_dtype == seq.dtype else seq_t.to(getattr(torch, np.dtype(cmp_dtype).name))
+        temp = (a >= thr.astype(cmp_dtype).item()).to(torch.uint8)
+        reached = _reached_from(ctx, temp, temp * out_t, conn)
+        trapped |= (temp != 0) & (reached == 0)
+    trapped = _mask_to_host(trapped)
+    if return_mask:
+        return trapped
+    seq[trapped] = -1
+    return host.make_contiguous_symmetric(seq)

@@ -24,7 +24,7 @@ def install(patch_edt_module=True):
     if ps is not None and "porespy" not in _saved:
         _saved["porespy"] = {}
         for name in ("porosimetry", "local_thickness", "trim_disconnected_blobs", "find_disconnected_voxels",
-                     "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths"):
+                     "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths", "find_trapped_regions"):
             for mod in (ps.filters, getattr(ps.filters, "_funcs", None)):
                 if mod is not None and hasattr(mod, name):
                     _saved["porespy"][(mod, name)] = getattr(mod, name)

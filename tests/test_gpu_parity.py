@@ -501,3 +501,17 @@ def test_flood_users(psb, golden):
         for surface in (False, True):
             assert_same(f.find_disconnected_voxels(r, conn=conn, surface=surface),
                         oc.find_disconnected_voxels(r, conn=conn, surface=surface), f"random {shape} {conn} {surface}")
+
+
+def test_find_trapped_regions(psb, golden):
+    """find_trapped_regions (one device flood per bin) against the reference-generated goldens."""
+    from tests.test_oracle import _trapped_cases
+    g = golden.trapped
+    cases, seq2, outl = _trapped_cases(g)
+    for kw, key in cases:
+        got = psb.filters.find_trapped_regions(**kw)
+        assert got.dtype == np.bool_
+        assert_same(got, g.mask(key), key)
+    s = psb.filters.find_trapped_regions(seq2, outlets=outl, bins=None, return_mask=False)
+    assert np.array_equal(s, g.raw("s2d_outlet_seq"))
+    assert np.array_equal(seq2, g.raw("seq2d"))                 # input not modified

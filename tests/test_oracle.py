@@ -176,3 +176,24 @@ def test_flood_users_golden(golden):
     inl, outl = np.zeros_like(b), np.zeros_like(b)
     inl[:, 0], outl[:, -1] = True, True
     assert oc.trim_nonpercolating_paths(b, inl, outl).sum() == 0                  # TF:149-160
+
+
+def _trapped_cases(g):
+    seq2 = g.raw("seq2d").astype(np.int64)
+    outl = np.zeros(seq2.shape, bool)
+    outl[-1, :] = True
+    seq3 = g.raw("seq3d").astype(np.int64)
+    outl3 = np.zeros(seq3.shape, bool)
+    outl3[-1] = True
+    return [(dict(seq=seq2), "t2d_faces_25"), (dict(seq=seq2, outlets=outl), "t2d_outlet_25"),
+            (dict(seq=seq2, outlets=outl, bins=None), "t2d_outlet_all"), (dict(seq=seq2, outlets=outl, bins=7), "t2d_outlet_7"),
+            (dict(seq=seq3, outlets=outl3), "t3d_outlet_25"), (dict(seq=seq3, bins=None), "t3d_faces_all")], seq2, outl
+
+
+def test_find_trapped_regions_golden(golden):
+    """find_trapped_regions restatement against the reference's own output (tests/golden/trapped.npz)."""
+    g = golden.trapped
+    cases, seq2, outl = _trapped_cases(g)
+    for kw, key in cases:
+        assert np.array_equal(oc.find_trapped_regions(**kw), g.mask(key)), key
+    assert np.array_equal(oc.find_trapped_regions(seq2, outlets=outl, bins=None, return_mask=False), g.raw("s2d_outlet_seq"))
