@@ -28,6 +28,10 @@ def _run(data, squared):
     as_numpy = not isinstance(data, torch.Tensor)
     if as_numpy:
         data = np.asarray(data)
+        if data.dtype != np.bool_ and data.size and data.max() > 1:
+            # the upstream package treats every label as its own object (distances to label boundaries);
+            # PoreSpy only passes binary images, anything else must not silently turn binary
+            raise NotImplementedError("porespy_b200.edt: multi-label images are not supported (binary input only)")
     shape = tuple(int(s) for s in data.shape)
     if len(shape) == 0 or int(np.prod(shape)) == 0:
         return np.zeros(shape, dtype=np.float32)

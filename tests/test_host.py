@@ -151,3 +151,16 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(root, fn)).read()
             assert "oracle" not in src.replace("no CPU fallback", "").lower() or fn == "_lib.py", fn
+
+
+def test_edt_rejects_what_it_does_not_implement():
+    """Options / inputs of the upstream `edt` that PoreSpy never uses must not silently differ."""
+    import porespy_b200 as psb
+    im = np.ones((4, 5), bool)
+    for kw in (dict(anisotropy=(1.0, 2.0)), dict(black_border=True), dict(voxel_graph=np.zeros((4, 5), np.uint8))):
+        with pytest.raises(NotImplementedError):
+            psb.edt(im, **kw)
+    with pytest.raises(NotImplementedError):
+        psb.edt(np.array([[0, 1, 2], [3, 3, 0]]))          # multi-label image
+    with pytest.raises(ValueError):
+        psb.edt(np.ones((2, 2, 2, 2), bool))
