@@ -164,3 +164,22 @@ def test_edt_rejects_what_it_does_not_implement():
         psb.edt(np.array([[0, 1, 2], [3, 3, 0]]))          # multi-label image
     with pytest.raises(ValueError):
         psb.edt(np.ones((2, 2, 2, 2), bool))
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints one JSON line with the
+    contract's keys; it needs no GPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--ref-edge", "48"], capture_output=True, text=True, cwd=root, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "local_thickness_voxels_per_s"
+    assert line["unit"] == "voxels/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
