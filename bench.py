@@ -139,19 +139,31 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples that arrived inside the timed region [t0, t1] (the sampler itself is started long before,
+        nvidia-smi needs a few hundred ms to print its first line); if the region was shorter than one
+        sampling period, the samples nearest to it."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)                                   # let the last in-region samples arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             pass
+        rows = self.rows
+        window = "timed region"
+        if t0 is not None:
+            inside = [r for r in rows if t0 <= r[0] <= t1 + 0.06]
+            if not inside and rows:
+                inside = sorted(rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:3]
+                window = "nearest to the timed region"
+            rows = inside
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for _, r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -162,7 +174,7 @@ class ClockSampler:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -235,6 +247,9 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()              # streams from now on; only the samples inside the timed region are used
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
@@ -268,25 +283,24 @@ def run_ours(args):
         out = step()
         del out
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ctx.set_profile(True)
     ctx.profile_read()
     l0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         out = step()
         del out
     ev1.record()
     barrier()
+    wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
     prof = ctx.profile_read()
     ctx.set_profile(False)
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -391,7 +405,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=1024, help="edge S of the per-GPU S^3 volume")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
