@@ -1,7 +1,6 @@
 """world_size-2/3 gloo runs of the z-slab sharded driver (porespy_b200/sharded.py) on CPU with the
 numpy step backend: the sharded result must equal the oracle's result on the whole volume."""
 import os
-import socket
 import traceback
 
 import numpy as np
@@ -14,16 +13,19 @@ from oracle import cpu as oc
 
 
 def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+    """A rendezvous file, not a TCP port: a probed-then-released port can be taken by somebody else
+    before the workers bind it (seen as a rare failure of this test)."""
+    import tempfile
+    fd, path = tempfile.mkstemp(prefix="psb200_gloo_")
+    os.close(fd)
+    os.unlink(path)                    # FileStore creates it
+    return path
 
 
 def _worker(rank, world, port, shape, sizes, bit_tmax, errq):
     try:
-        os.environ["MASTER_ADDR"] = "127.0.0.1"
-        os.environ["MASTER_PORT"] = str(port)
-        dist.init_process_group("gloo", rank=rank, world_size=world)
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+        dist.init_process_group("gloo", init_method=f"file://{port}", rank=rank, world_size=world)
         from porespy_b200.sharded import ShardedVolume
         from tests.cpu_backend import CpuBackend
         im = oc.blobs(list(shape), porosity=0.6, blobiness=1.5, seed=3)
