@@ -58,7 +58,6 @@ extern "C" {
 /* flags */
 #define PSB200_FLAG_IDX_PREINIT 1     /* local_thickness_idx: idx already holds 0 / PSB200_IDX_KEEP */
 #define PSB200_FLAG_EXPAND_MERGE 1    /* expand_idx_f64: leave out[] untouched where idx is 0 or KEEP */
-#define PSB200_FLAG_HOST_PREZEROED 1  /* expand_idx_f64_to_host: out_host already holds 0.0 everywhere */
 
 typedef struct psb200_ctx psb200_ctx;
 typedef void *psb200_stream;          /* cudaStream_t */
@@ -201,18 +200,11 @@ int psb200_expand_idx_f64_to_host(psb200_ctx *ctx, const uint8_t *idx, const dou
 /* Host prologue: upload a one-byte-per-voxel HOST volume (numpy bool / uint8, foreground <=> byte != 0,
  * F:1126 `im > 0`) as 0/1 bytes into dst (device, n bytes).  Host threads pack it to one bit per
  * voxel chunk by chunk, the chunks cross PCIe at an eighth of the size, a kernel spreads the bits.
- * stage_host: page-locked, >= ceil(n/8) bytes, must stay alive until `stream` has passed the call;
- * ws: device, >= ceil(n/8) bytes.  The host source may be reused on return. */
+ * stage_host: page-locked, >= ceil(n/8) bytes; ws: device, >= ceil(n/8) bytes.  The host source and
+ * the staging buffer may be reused on return (the call waits for its last host-to-device copy). */
 int psb200_upload_mask_u8(psb200_ctx *ctx, const uint8_t *src_host, int64_t n, uint8_t *dst,
                           uint8_t *stage_host, size_t stage_bytes, void *ws, size_t ws_bytes,
                           int nthreads, psb200_stream stream);
-/* Zero out_host[0, n) with `nthreads` background host threads (0 = all hardware threads) while the
- * GPU computes; psb200_host_zero_wait joins them (and must be called exactly once per job, also on
- * error paths).  With PSB200_FLAG_HOST_PREZEROED the epilogue above then skips the 64-byte lines
- * whose eight radius indices are all 0 -- solid or never-invaded voxels, a third of a porous
- * volume -- instead of storing 0.0 into them again. */
-int psb200_host_zero_begin(double *out_host, int64_t n, int nthreads, void **job);
-int psb200_host_zero_wait(void *job);
 /* idx[i] = out[i] != 0 ? PSB200_IDX_KEEP : 0   (continuation across >253 thresholds) */
 int psb200_mark_written(psb200_ctx *ctx, const double *out, uint8_t *idx, int64_t n,
                         psb200_stream stream);
@@ -256,6 +248,35 @@ int psb200_uf_inject(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, cons
                      int64_t nz_global, psb200_stream stream);
 int psb200_uf_mark(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, uint8_t *rcls, int k,
                    int *any_dev, int64_t n, psb200_stream stream);
+
+/* ---- device-side `ps.generators.blobs` (generators/_imgen.py:1023-1051; norm_to_uniform T:963-969), the
+ * input generator of every benchmark configuration.  float64, scipy's arithmetic
+ * order; see porespy_b200/csrc/blobs_kernels.cuh.
+ *   psb200_noise_philox_f64 : out[i] = uniform [0,1) noise of GLOBAL element first + i (Philox4x32-10 keyed
+ *                             by seed: a pure function of the voxel, shard-invariant)
+ *   psb200_gauss_axis_f64   : one 1-D correlation of gaussian_filter (mode='reflect') along `axis` (0 = z,
+ *                             1 = y, 2 = x); w_host[0..radius] = the kernel from its outermost tap to the centre
+ *                             (host doubles).  out is [nz][ny][nx].  axis 1 / 2: in has the same shape.  axis 0:
+ *                             out holds global planes [z_out0, z_out0+nz), in holds global planes
+ *                             [z_in0, z_in0+nz_in) (the slab plus the filter reach), the global volume has
+ *                             nz_glob planes (reflection at ITS ends).  ws: psb200_gauss_workspace_bytes(radius).
+ *                             Synchronises the stream once (weight upload).
+ *   psb200_stats_f64        : part[p * psb200_stats_chunks() + c] = partial sum (mode 0), sum of (x-mean)^2
+ *                             (mode 1), min (2) or max (3) over chunk c of plane p -- fixed order, so the host
+ *                             combines the same numbers whatever the sharding.  part: device doubles.
+ *   psb200_blobs_finish     : norm_to_uniform + `< porosity` -> out_u8 (0/1), or the uniformised field ->
+ *                             out_f64 when out_u8 is NULL (porosity=None in the reference). */
+int psb200_noise_philox_f64(psb200_ctx *ctx, double *out, int64_t n, uint64_t seed, uint64_t first,
+                            psb200_stream stream);
+size_t psb200_gauss_workspace_bytes(const psb200_ctx *ctx, int radius);
+int psb200_gauss_axis_f64(psb200_ctx *ctx, const double *in, double *out, int axis, const double *w_host,
+                          int radius, int64_t nz, int64_t ny, int64_t nx, int64_t z_out0, int64_t z_in0,
+                          int64_t nz_in, int64_t nz_glob, void *ws, size_t ws_bytes, psb200_stream stream);
+int psb200_stats_chunks(void);
+int psb200_stats_f64(psb200_ctx *ctx, const double *x, int64_t nplanes, int64_t plane, double mean, int mode,
+                     double *part, psb200_stream stream);
+int psb200_blobs_finish(psb200_ctx *ctx, const double *f, int64_t n, double mean, double sd, double fmin_,
+                        double fmax_, double porosity, uint8_t *out_u8, double *out_f64, psb200_stream stream);
 
 #ifdef __cplusplus
 }

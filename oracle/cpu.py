@@ -57,6 +57,10 @@ def _lib():
                                         ctypes.c_int]
         lib.oracle_sqrt_f32.restype = ctypes.c_int
         lib.oracle_num_threads.restype = ctypes.c_int
+        lib.oracle_porosimetry_dt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                              ctypes.c_int]
+        lib.oracle_porosimetry_dt.restype = ctypes.c_int
         _LIB = lib
     return _LIB
 
@@ -323,3 +327,44 @@ def local_thickness(im, sizes=25, mode="hybrid", divs=1, nthreads=0):
     """F:1027-1029 -- porosimetry without access limitation."""
     return porosimetry(im, sizes=sizes, access_limited=False, mode=mode, divs=divs,
                        nthreads=nthreads)
+
+
+# ------------------------------------------------------- the same loop in one C call (big volumes)
+def porosimetry_c(im, sizes=25, inlets=None, access_limited=True, nthreads=0):
+    """`porosimetry(mode='dt')` with the radius loop in C (oracle_porosimetry_dt, edt_oracle.c): the same
+    statements F:1124-1192 without numpy temporaries, for volumes where the restatement above would take
+    many minutes.  The prologue (squeeze, radii) is the numpy code of F:1124-1134; tests/test_oracle.py
+    pins the C loop against `porosimetry` above.  `nthreads=0`: every hardware thread (independent of
+    OMP_NUM_THREADS, which torchrun sets to 1)."""
+    im = np.squeeze(im)
+    if nthreads <= 0:
+        nthreads = os.cpu_count() or 1
+    fg = np.ascontiguousarray(im > 0, dtype=np.uint8)
+    if isinstance(sizes, int):
+        dtmax = np.amax(edt(fg, parallel=nthreads))
+        sizes = np.logspace(start=np.log10(dtmax), stop=0, num=sizes)
+    else:
+        sizes = np.unique(sizes)[-1::-1]
+    radii = np.ascontiguousarray(sizes, dtype=np.float64)        # float32 / int64 -> float64 is exact
+    inl = None
+    if access_limited:
+        if inlets is None:
+            inlets = border_faces(im.shape)
+        if isinstance(inlets, tuple):
+            where = np.copy(inlets)
+            inlets = np.zeros_like(im, dtype=bool)
+            inlets[where] = True
+        elif not ((inlets.shape == im.shape) and (inlets.max() == 1)):
+            raise Exception("inlets not valid, refer to docstring for info")
+        inl = np.ascontiguousarray(inlets, dtype=bool).view(np.uint8)
+    out = np.empty(im.shape, dtype=np.float64)
+    nz, ny, nx = _as3d(im.shape)
+    rc = _lib().oracle_porosimetry_dt(fg.ctypes.data, radii.ctypes.data, len(radii),
+                                      inl.ctypes.data if inl is not None else None, out.ctypes.data,
+                                      nz, ny, nx, int(nthreads))
+    assert rc == 0, rc
+    return out
+
+
+def local_thickness_c(im, sizes=25, nthreads=0):
+    return porosimetry_c(im, sizes=sizes, access_limited=False, nthreads=nthreads)

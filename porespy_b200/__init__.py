@@ -9,13 +9,14 @@ exact 3-D EDT (`edt.edt`) -> `filters.local_thickness` / `filters.porosimetry`
 from . import _lib
 from . import edt as edt_module
 from . import filters
+from . import generators
 from .edt import edt, edtsq
 from .filters import local_thickness, porosimetry, trim_disconnected_blobs
 from .patch import install, uninstall
 from ._device import pinned_empty, to_pinned
 
 __version__ = "0.1.0"
-__all__ = ["edt", "edtsq", "filters", "local_thickness", "porosimetry",
+__all__ = ["edt", "edtsq", "filters", "generators", "local_thickness", "porosimetry",
            "trim_disconnected_blobs", "install", "uninstall", "build", "pinned_empty", "to_pinned"]
 
 

@@ -23,12 +23,6 @@ def ptr(t):
 
 
 PIN_MIN_BYTES = 1 << 20      # below this a pageable copy is as fast as a pinned one
-# Opt-in (PSB200_HOST_PREZERO=1): float64 results from 2^28 bytes on are zeroed by background host
-# threads during the GPU phase and the epilogue skips all-zero lines.  Measured on this pool's B200
-# boxes it LOSES (e2e 135 -> 154 ms at 1024^3): the host memory system is the bottleneck of the
-# epilogue, and zeroing adds 8.6 GB of stores to it for the 3 GB it saves later.
-PREZERO_MIN_BYTES = (1 << 28) if os.environ.get("PSB200_HOST_PREZERO", "0") == "1" else (1 << 62)
-
 
 def pinned_empty(shape, dtype=np.uint8):
     """numpy array backed by page-locked host memory (torch's caching host allocator owns it and
@@ -71,61 +65,20 @@ HOST_WIDEN_PERMILLE = int(os.environ.get("PSB200_HOST_WIDEN_PERMILLE", "1000"))
 HOST_WIDEN_THREADS = int(os.environ.get("PSB200_HOST_WIDEN_THREADS", "0"))      # 0: all hardware threads
 
 
-class HostResult:
-    """The float64 result array of one call, in page-locked host memory, being zeroed by background
-    host threads of the library (psb200_host_zero_begin) while the GPU computes.  `finish()` must
-    run exactly once (it joins the threads); `array()` hands the numpy view out."""
-
-    def __init__(self, ctx, shape, nthreads=None):
-        torch = _torch()
-        self.ctx, self.shape = ctx, tuple(shape)
-        self.n = int(np.prod(self.shape)) if len(self.shape) else 1
-        self.host = torch.empty(self.n, dtype=torch.float64, pin_memory=True)
-        self.job = ctypes.c_void_p()
-        if nthreads is None:
-            # leave two hardware threads to the launching thread and the driver
-            nthreads = max(1, (os.cpu_count() or 1) - 2)
-        _lib.check(ctx.lib.psb200_host_zero_begin(ctypes.c_void_p(self.host.data_ptr()), self.n, int(nthreads),
-                                                  ctypes.byref(self.job)))
-
-    def finish(self):
-        if self.job is not None and self.job.value:
-            _lib.check(self.ctx.lib.psb200_host_zero_wait(self.job))
-        self.job = None
-
-    def array(self):
-        self.finish()
-        return self.host.numpy().reshape(self.shape)
-
-    def __del__(self):
-        try:
-            self.finish()
-        except Exception:
-            pass
-
-
-def expand_idx_to_host(ctx, idx, lut, shape, chunk=1 << 26, cpu_permille=None, nthreads=None, result=None):
+def expand_idx_to_host(ctx, idx, lut, shape, chunk=1 << 26, cpu_permille=None, nthreads=None):
     """Radius-index map (uint8, device) -> float64 numpy in page-locked memory, without ever holding
     the 8 B/voxel map in HBM (psb200_expand_idx_f64_to_host): part of the volume leaves the device
     as index bytes and is widened by host threads of the library, the rest is widened on the
-    device chunk by chunk while the previous chunk is on its way over PCIe.  `result`: a
-    HostResult started earlier in the call (its buffer is zero by now, so all-zero lines are skipped)."""
+    device chunk by chunk while the previous chunk is on its way over PCIe."""
     torch = _torch()
     n = idx.numel()
     if n * 8 < PIN_MIN_BYTES:
-        if result is not None:
-            result.finish()
         out = torch.empty(n, dtype=torch.float64, device=idx.device)
         expand_idx(ctx, idx, lut, out)
         return out.cpu().numpy().reshape(shape)
     cpu_permille = HOST_WIDEN_PERMILLE if cpu_permille is None else int(cpu_permille)
     nthreads = HOST_WIDEN_THREADS if nthreads is None else int(nthreads)
-    flags = 0
-    if result is not None:
-        result.finish()
-        host, flags = result.host, _lib.FLAG_HOST_PREZEROED
-    else:
-        host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    host = torch.empty(n, dtype=torch.float64, pin_memory=True)
     stage_n = (n * cpu_permille) // 1000
     stage = torch.empty(max(stage_n, 1), dtype=torch.uint8, pin_memory=True)
     chunk = min(chunk, n)
@@ -134,14 +87,16 @@ def expand_idx_to_host(ctx, idx, lut, shape, chunk=1 << 26, cpu_permille=None, n
     _lib.check(ctx.lib.psb200_expand_idx_f64_to_host(
         ctx.handle, ptr(idx), lut.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(lut),
         ctypes.c_void_p(host.data_ptr()), n, ctypes.c_void_p(stage.data_ptr()), stage.numel(),
-        ptr(ws), ws.numel(), cpu_permille, nthreads, flags, stream_ptr()))
+        ptr(ws), ws.numel(), cpu_permille, nthreads, 0, stream_ptr()))
     del stage
     return host.numpy().reshape(shape)
 
 
-def to_device_u8(arr, ctx):
+def to_device_u8(arr, ctx, positive=False):
     """Host array or torch tensor -> contiguous uint8 device tensor whose non-zero bytes mark the
-    foreground (the kernels test `byte != 0`, so bool / uint8 data is passed through as is)."""
+    foreground (the kernels test `byte != 0`, so bool / uint8 data is passed through as is).
+    `positive`: the foreground of a signed / float image is `im > 0` (F:1126 `edt(im > 0)`, F:1265), not
+    `im != 0` (masks, and the `edt` module itself, where every non-zero label is an object)."""
     torch = _torch()
     dev = f"cuda:{ctx.device}"
     if isinstance(arr, torch.Tensor):
@@ -150,12 +105,12 @@ def to_device_u8(arr, ctx):
             return t.contiguous().view(torch.uint8)
         if t.dtype == torch.uint8:
             return t.contiguous()
-        return (t != 0).to(torch.uint8).contiguous()
+        return ((t > 0) if positive else (t != 0)).to(torch.uint8).contiguous()
     a = np.asarray(arr)
     if a.dtype == np.bool_ or a.dtype == np.uint8:
         a = np.ascontiguousarray(a).view(np.uint8)
     else:
-        a = np.ascontiguousarray(a != 0).view(np.uint8)
+        a = np.ascontiguousarray((a > 0) if positive else (a != 0)).view(np.uint8)
     if a.nbytes >= UPLOAD_PACK_MIN_BYTES:
         return upload_mask(ctx, a)
     return torch.from_numpy(a).to(dev, non_blocking=False)      # a single DMA when `a` is page-locked
@@ -168,9 +123,8 @@ _upload_stage = {}
 def upload_mask(ctx, a):
     """Large host volumes cross PCIe as one bit per voxel (psb200_upload_mask_u8): host threads of the
     library pack `byte != 0` chunk by chunk while earlier chunks are in flight, a kernel spreads the
-    bits to 0/1 bytes.  The page-locked staging buffer is kept per device (grow-only): the copies
-    read it asynchronously, and every public call that uploads a numpy volume ends with a
-    synchronising download, so it is idle again before the next upload."""
+    bits to 0/1 bytes.  The page-locked staging buffer is kept per device (grow-only); the call returns
+    once the last copy has left it, so back-to-back uploads (fg, inlets, outlets) may share it."""
     torch = _torch()
     n = a.size
     nb = (n + 7) // 8

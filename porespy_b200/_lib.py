@@ -18,7 +18,6 @@ INLETS_NONE, INLETS_FACES, INLETS_MASK = 0, 1, 2
 ALGO_FAST, ALGO_GENERIC = 0, 1
 FLAG_IDX_PREINIT = 1
 FLAG_EXPAND_MERGE = 1
-FLAG_HOST_PREZEROED = 1
 MAX_THRESHOLDS = 253
 MAX_DIM = 32767
 INF_U32 = 0xFFFFFFFF
@@ -81,8 +80,6 @@ SIGNATURES = {
     "psb200_expand_idx_f64_to_host": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _vp, _sz,
                                              _vp, _sz, _i32, _i32, _i32, _vp]),
     "psb200_upload_mask_u8": (_i32, [_vp, _vp, _i64, _vp, _vp, _sz, _vp, _sz, _i32, _vp]),
-    "psb200_host_zero_begin": (_i32, [_vp, _i64, _i32, _c.POINTER(_vp)]),
-    "psb200_host_zero_wait": (_i32, [_vp]),
     "psb200_mark_written": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "psb200_uf_begin": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _vp]),
     "psb200_uf_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
@@ -92,6 +89,14 @@ SIGNATURES = {
     "psb200_uf_inject": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "psb200_uf_mark": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "psb200_flood_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
+    "psb200_noise_philox_f64": (_i32, [_vp, _vp, _i64, _c.c_uint64, _c.c_uint64, _vp]),
+    "psb200_gauss_workspace_bytes": (_sz, [_vp, _i32]),
+    "psb200_gauss_axis_f64": (_i32, [_vp, _vp, _vp, _i32, _c.POINTER(_c.c_double), _i32, _i64, _i64, _i64, _i64, _i64,
+                                     _i64, _i64, _vp, _sz, _vp]),
+    "psb200_stats_chunks": (_i32, []),
+    "psb200_stats_f64": (_i32, [_vp, _vp, _i64, _i64, _c.c_double, _i32, _vp, _vp]),
+    "psb200_blobs_finish": (_i32, [_vp, _vp, _i64, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _c.c_double,
+                                   _vp, _vp, _vp]),
     "psb200_flood": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
 }
 

@@ -20,17 +20,16 @@
 #include "common.cuh"
 
 // out[i] = lut[idx[i]] for i in [0, cnt); `out` 16-byte aligned, cnt even except for a tail.
-// prezeroed: out already holds 0.0 everywhere (psb200_host_zero_begin), so a group of 8 voxels whose
-// indices are all 0 (solid, or never invaded: lut[0] == 0.0) needs no store -- on a porous volume
-// about a third of the 64-byte lines.
-static void host_widen_slice(const uint8_t *idx, const double *lut, double *out, int64_t cnt, bool prezeroed)
+// (Zeroing the output in the background during the GPU phase and skipping all-zero lines here was
+// measured and removed: the epilogue is bound by the host's memory system, and the extra 8.6 GB of
+// stores cost more than the 3 GB they saved -- e2e 135 -> 154 ms at 1024^3.)
+static void host_widen_slice(const uint8_t *idx, const double *lut, double *out, int64_t cnt)
 {
     int64_t i = 0;
     if ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
         for (; i + 8 <= cnt; i += 8) {
             uint64_t w;
             memcpy(&w, idx + i, 8);
-            if (prezeroed && w == 0) continue;
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
                 const __m128d v = _mm_set_pd(lut[(w >> (8 * j + 8)) & 0xFFu], lut[(w >> (8 * j)) & 0xFFu]);
@@ -39,24 +38,6 @@ static void host_widen_slice(const uint8_t *idx, const double *lut, double *out,
         }
     }
     for (; i < cnt; ++i) out[i] = lut[idx[i]];
-}
-
-// ---- output buffer zeroed in the background while the GPU computes
-struct HostZeroJob {
-    std::vector<std::thread> pool;
-};
-
-static void host_zero_slice(double *out, int64_t cnt)
-{
-    int64_t i = 0;
-    while (i < cnt && (reinterpret_cast<uintptr_t>(out + i) & 15u)) out[i++] = 0.0;
-    const __m128d z = _mm_setzero_pd();
-    for (; i + 8 <= cnt; i += 8) {
-        _mm_stream_pd(out + i, z); _mm_stream_pd(out + i + 2, z);
-        _mm_stream_pd(out + i + 4, z); _mm_stream_pd(out + i + 6, z);
-    }
-    for (; i < cnt; ++i) out[i] = 0.0;
-    _mm_sfence();
 }
 
 struct HostEpilogueStreams {
@@ -68,7 +49,7 @@ struct HostEpilogueStreams {
 static int host_epilogue_run(psb200_ctx *ctx, HostEpilogueStreams &hs, const uint8_t *idx_dev,
                              const double *lut_host, int nlut, double *out_host, int64_t n,
                              uint8_t *stage_host, size_t stage_bytes, void *ws_dev, size_t ws_bytes,
-                             int cpu_permille, int nthreads, bool prezeroed, cudaStream_t st, int (*launch_expand)(
+                             int cpu_permille, int nthreads, cudaStream_t st, int (*launch_expand)(
                                  psb200_ctx *, const uint8_t *, const double *, int, double *, int64_t, cudaStream_t))
 {
     if (!hs.idx_copy) CUDA_TRY(cudaStreamCreateWithFlags(&hs.idx_copy, cudaStreamNonBlocking));
@@ -108,14 +89,13 @@ static int host_epilogue_run(psb200_ctx *ctx, HostEpilogueStreams &hs, const uin
         pool.reserve(nthreads);
         for (int t = 0; t < nthreads; ++t) {
             pool.emplace_back([=, &arrived, &thread_err, &lut]() {
-                const bool pz = prezeroed && lut[0] == 0.0;
                 if (cudaSetDevice(device) != cudaSuccess) { thread_err = 1; return; }
                 const int64_t per = ((CH_A / nthreads) + 7) & ~(int64_t)7;
                 const int64_t s = (int64_t)t * per, e = s + per < CH_A ? s + per : CH_A;
                 for (int c = 0; c < ncA; ++c) {
                     if (cudaEventSynchronize(arrived[c]) != cudaSuccess) { thread_err = 1; return; }
                     if (s < e)
-                        host_widen_slice(stage_host + (int64_t)c * CH_A + s, lut, out_host + (int64_t)c * CH_A + s, e - s, pz);
+                        host_widen_slice(stage_host + (int64_t)c * CH_A + s, lut, out_host + (int64_t)c * CH_A + s, e - s);
                 }
                 _mm_sfence();
             });
@@ -201,8 +181,8 @@ static void host_pack_slice(const uint8_t *src, uint8_t *bits, int64_t v0, int64
     }
 }
 
-// Synchronous with respect to the host source (it may be reused on return); the device side is
-// ordered on `st`.  stage_host: page-locked, >= ceil(n / 8) bytes; bits_dev: device, same size.
+// Synchronous with respect to the host source AND the staging buffer (both may be reused on return);
+// the device side (unpack kernel) is ordered on `st`.  stage_host: page-locked, >= ceil(n / 8) bytes; bits_dev: device, same size.
 static int host_upload_mask(psb200_ctx *ctx, const uint8_t *src_host, int64_t n, uint8_t *dst_dev,
                             uint8_t *stage_host, uint8_t *bits_dev, int nthreads, cudaStream_t st)
 {
@@ -231,6 +211,16 @@ static int host_upload_mask(psb200_ctx *ctx, const uint8_t *src_host, int64_t n,
     }
     for (auto &th : pool) th.join();
     if (err != cudaSuccess) return fail(PSB200_ERR_CUDA, "upload_mask_u8: %s", cudaGetErrorString(err));
+    // the copies read the staging buffer asynchronously: wait until the last one has left host memory, so
+    // that the caller may repack the same buffer for its next volume right away (fg, inlets, outlets are
+    // uploaded back to back by the flood users)
+    cudaEvent_t copied;
+    if ((err = cudaEventCreateWithFlags(&copied, cudaEventDisableTiming)) == cudaSuccess) {
+        err = cudaEventRecord(copied, st);
+        if (err == cudaSuccess) err = cudaEventSynchronize(copied);
+        cudaEventDestroy(copied);
+    }
+    if (err != cudaSuccess) return fail(PSB200_ERR_CUDA, "upload_mask_u8: %s", cudaGetErrorString(err));
     const int64_t nb = (n + 7) >> 3;
     int g = (int)((nb + 255) / 256);
     if (g > ctx->sm_count * 16) g = ctx->sm_count * 16;
@@ -238,7 +228,5 @@ static int host_upload_mask(psb200_ctx *ctx, const uint8_t *src_host, int64_t n,
     ctx->launches++;
     err = cudaGetLastError();
     if (err != cudaSuccess) return fail(PSB200_ERR_CUDA, "upload_mask_u8: %s", cudaGetErrorString(err));
-    // the staging buffer is read by the copies still in flight: the caller keeps it alive until the
-    // stream has passed this point (the Python host synchronises on the max-d2 read-back of the EDT)
     return PSB200_OK;
 }

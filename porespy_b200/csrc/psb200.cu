@@ -14,6 +14,7 @@
 #include "minplus_kernels.cuh"
 #include "xdist_kernels.cuh"
 #include "bitball_kernels.cuh"
+#include "blobs_kernels.cuh"
 
 // ------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -47,13 +48,13 @@ static int fail(int code, const char *fmt, ...)
 enum KernelId {
     K_EDT_X = 0, K_EDT_Y, K_EDT_Z, K_SQRT, K_MAX, K_CLASSIFY, K_LT_XY, K_LT_X, K_LT_Y, K_LT_Z, K_LT_POINT, K_EXPAND,
     K_MARK_WRITTEN, K_UF_INIT, K_UF_ACTIVATE, K_UF_MARK, K_FLOOD_MISC, K_GEN_X, K_GEN_Y, K_GEN_Z,
-    K_FH_X, K_FH_Y, K_FH_Z, K_LT_PACK, K_LT_BITBALL, K_LT_WMASK, K_EDT_FIX, K_UF_FACE, K_COUNT
+    K_FH_X, K_FH_Y, K_FH_Z, K_LT_PACK, K_LT_BITBALL, K_LT_WMASK, K_EDT_FIX, K_UF_FACE, K_BLOBS, K_COUNT
 };
 static const char *const kKernelNames[K_COUNT] = {
     "edt_x", "edt_y", "edt_z", "sqrt_f32", "max_u32", "lt_classify", "lt_xy", "lt_x", "lt_y", "lt_z", "lt_point",
     "lt_expand", "lt_mark_written", "uf_init", "uf_activate", "uf_mark", "flood_misc",
     "generic_x", "generic_y", "generic_z", "edt_fh_x", "edt_fh_y", "edt_fh_z", "lt_pack", "lt_bitball", "lt_wmask", "edt_fix_inf",
-    "uf_face"};
+    "uf_face", "blobs"};
 
 struct ProfScope {
     psb200_ctx *c;
@@ -1185,10 +1186,11 @@ extern "C" int psb200_expand_idx_f64_to_host(psb200_ctx *ctx, const uint8_t *idx
     if (ctx->device < 0 || ctx->device >= 64) return fail(PSB200_ERR_UNSUPPORTED, "expand_idx_f64_to_host: device index");
     if (n == 0) return PSB200_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    (void)flags;
     if (nthreads == 0) nthreads = (int)std::thread::hardware_concurrency();
     return host_epilogue_run(ctx, g_epilogue_streams[ctx->device], idx, lut_host, nlut, out_host, n, stage_host,
-                             stage_bytes, ws, ws_bytes, cpu_permille, nthreads,
-                             (flags & PSB200_FLAG_HOST_PREZEROED) != 0, (cudaStream_t)stream, launch_expand_chunk);
+                             stage_bytes, ws, ws_bytes, cpu_permille, nthreads, (cudaStream_t)stream,
+                             launch_expand_chunk);
 }
 
 extern "C" int psb200_upload_mask_u8(psb200_ctx *ctx, const uint8_t *src_host, int64_t n, uint8_t *dst,
@@ -1206,31 +1208,6 @@ extern "C" int psb200_upload_mask_u8(psb200_ctx *ctx, const uint8_t *src_host, i
     if (nthreads < 1) nthreads = 1;
     return host_upload_mask(ctx, src_host, n, dst, stage_host, reinterpret_cast<uint8_t *>(ws), nthreads,
                             (cudaStream_t)stream);
-}
-
-extern "C" int psb200_host_zero_begin(double *out_host, int64_t n, int nthreads, void **job)
-{
-    if (!out_host || n < 0 || !job || nthreads < 0 || nthreads > 1024)
-        return fail(PSB200_ERR_INVALID, "host_zero_begin: bad argument");
-    if (nthreads == 0) nthreads = (int)std::thread::hardware_concurrency();
-    if (nthreads < 1) nthreads = 1;
-    HostZeroJob *j = new HostZeroJob();
-    const int64_t per = ((n / nthreads) + 8) & ~(int64_t)7;
-    for (int t = 0; t < nthreads; ++t) {
-        const int64_t s = (int64_t)t * per, e = s + per < n ? s + per : n;
-        if (s < e) j->pool.emplace_back([=]() { host_zero_slice(out_host + s, e - s); });
-    }
-    *job = j;
-    return PSB200_OK;
-}
-
-extern "C" int psb200_host_zero_wait(void *job)
-{
-    if (!job) return PSB200_OK;
-    HostZeroJob *j = reinterpret_cast<HostZeroJob *>(job);
-    for (auto &th : j->pool) th.join();
-    delete j;
-    return PSB200_OK;
 }
 
 extern "C" int psb200_mark_written(psb200_ctx *ctx, const double *out, uint8_t *idx, int64_t n,
@@ -1414,6 +1391,130 @@ extern "C" int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t 
     {
         ProfScope ps__(ctx, st, K_FLOOD_MISC);
         flood_out_kernel<<<g, 256, 0, st>>>(w.rcls, out, n);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+// ------------------------------------------------------------------------- blobs generator
+// (blobs_kernels.cuh; reference generators/_imgen.py:1023-1051, tools/_funcs.py:963-969)
+extern "C" int psb200_noise_philox_f64(psb200_ctx *ctx, double *out, int64_t n, uint64_t seed, uint64_t first,
+                                       psb200_stream stream)
+{
+    if (!ctx || !out || n < 0) return fail(PSB200_ERR_INVALID, "noise_philox_f64: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        ProfScope ps__(ctx, st, K_BLOBS);
+        noise_philox_kernel<<<grid_for(n / 2 + 1, 256, ctx->sm_count, 16), 256, 0, st>>>(out, n, seed, first);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" size_t psb200_gauss_workspace_bytes(const psb200_ctx *ctx, int radius)
+{
+    if (!ctx || radius < 0) return 0;
+    return (size_t)(radius + 1) * sizeof(double) + 256;
+}
+
+extern "C" int psb200_gauss_axis_f64(psb200_ctx *ctx, const double *in, double *out, int axis,
+                                     const double *w_host, int radius, int64_t nz, int64_t ny, int64_t nx,
+                                     int64_t z_out0, int64_t z_in0, int64_t nz_in, int64_t nz_glob, void *ws,
+                                     size_t ws_bytes, psb200_stream stream)
+{
+    if (!ctx || !in || !out || in == out || !w_host || radius < 0 || axis < 0 || axis > 2)
+        return fail(PSB200_ERR_INVALID, "gauss_axis_f64: bad argument");
+    int rc = check_dims("gauss_axis_f64", nz, ny, nx);
+    if (rc) return rc;
+    if (axis == 0 && (nz_glob < 1 || z_out0 < 0 || z_out0 + nz > nz_glob || z_in0 < 0 || z_in0 + nz_in > nz_glob))
+        return fail(PSB200_ERR_INVALID, "gauss_axis_f64: slab outside the global volume");
+    if (axis == 0) {
+        // every (reflected) tap of every output plane must lie inside the input planes
+        int64_t need_lo = nz_glob, need_hi = -1;
+        for (int64_t i = z_out0 - radius; i <= z_out0 + nz - 1 + radius; ++i) {
+            const int64_t per = 2 * nz_glob;
+            int64_t m = i % per;
+            if (m < 0) m += per;
+            if (m >= nz_glob) m = per - 1 - m;
+            if (m < need_lo) need_lo = m;
+            if (m > need_hi) need_hi = m;
+        }
+        if (need_lo < z_in0 || need_hi >= z_in0 + nz_in)
+            return fail(PSB200_ERR_INVALID, "gauss_axis_f64: input planes [%lld,%lld) do not cover the filter reach "
+                        "[%lld,%lld] of output planes [%lld,%lld)", (long long)z_in0, (long long)(z_in0 + nz_in),
+                        (long long)need_lo, (long long)need_hi, (long long)z_out0, (long long)(z_out0 + nz));
+    }
+    char *base = ws ? (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
+    const size_t wbytes = (size_t)(radius + 1) * sizeof(double);
+    if (!base || ws_bytes < wbytes + (size_t)(base - (char *)ws))
+        return fail(PSB200_ERR_WORKSPACE, "gauss_axis_f64 needs %zu workspace bytes", wbytes + 256);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double *wdev = reinterpret_cast<double *>(base);
+    CUDA_TRY(cudaMemcpyAsync(wdev, w_host, wbytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));                 // w_host may be a temporary of the caller
+    const int64_t plane = ny * nx;
+    if (axis == 2) {
+        const size_t smem = (size_t)(GX_SEG + 3 * radius + 1) * sizeof(double);
+        if ((int)smem > ctx->max_smem_optin) return fail(PSB200_ERR_UNSUPPORTED, "gauss_axis_f64: radius %d too large", radius);
+        CUDA_TRY(cudaFuncSetAttribute(gauss_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t jobs = nz * ny * ((nx + GX_SEG - 1) / GX_SEG);
+        {
+            ProfScope ps__(ctx, st, K_BLOBS);
+            gauss_x_kernel<<<grid_for(jobs, 1, ctx->sm_count, 8), 256, smem, st>>>(in, out, nz * ny, (int)nx, radius, wdev);
+        }
+        LAUNCH_CHECK(ctx);
+        return PSB200_OK;
+    }
+    int rows = 128;
+    while (rows > 8 && (size_t)(rows + 2 * radius) * 256 + wbytes + 8 > (size_t)ctx->max_smem_optin / 2) rows >>= 1;
+    const size_t smem = (size_t)(rows + 2 * radius) * 256 + wbytes + 8;
+    if ((int)smem > ctx->max_smem_optin) return fail(PSB200_ERR_UNSUPPORTED, "gauss_axis_f64: radius %d too large", radius);
+    CUDA_TRY(cudaFuncSetAttribute(gauss_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t ncols, stride, outer, os_in, os_out, g0_out, g0_in, n_glob;
+    int n_out, n_in;
+    if (axis == 1) { ncols = nx; stride = nx; n_out = n_in = (int)ny; g0_out = g0_in = 0; n_glob = ny; outer = nz; os_in = os_out = plane; }
+    else { ncols = plane; stride = plane; n_out = (int)nz; n_in = (int)nz_in; g0_out = z_out0; g0_in = z_in0; n_glob = nz_glob; outer = 1; os_in = os_out = 0; }
+    const int64_t jobs = ((ncols + 31) / 32) * ((n_out + rows - 1) / rows) * outer;
+    {
+        ProfScope ps__(ctx, st, K_BLOBS);
+        gauss_col_kernel<<<grid_for(jobs, 1, ctx->sm_count, 4), 256, smem, st>>>(in, out, ncols, stride, n_out, g0_out, n_in, g0_in,
+                                                                             n_glob, outer, os_in, os_out, radius, rows, wdev);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_stats_chunks(void) { return ST_CHUNKS; }
+
+extern "C" int psb200_stats_f64(psb200_ctx *ctx, const double *x, int64_t nplanes, int64_t plane, double mean, int mode,
+                                double *part, psb200_stream stream)
+{
+    if (!ctx || !x || !part || nplanes < 1 || plane < 1 || mode < 0 || mode > 3)
+        return fail(PSB200_ERR_INVALID, "stats_f64: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        ProfScope ps__(ctx, st, K_BLOBS);
+        stats_kernel<<<grid_for(nplanes * ST_CHUNKS, 1, ctx->sm_count, 8), 256, 0, st>>>(x, nplanes, plane, mean, mode, part);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_blobs_finish(psb200_ctx *ctx, const double *f, int64_t n, double mean, double sd, double fmin_,
+                                   double fmax_, double porosity, uint8_t *out_u8, double *out_f64, psb200_stream stream)
+{
+    if (!ctx || !f || n < 0 || (!out_u8 && !out_f64)) return fail(PSB200_ERR_INVALID, "blobs_finish: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        ProfScope ps__(ctx, st, K_BLOBS);
+        blobs_finish_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(f, n, mean, sd, fmin_, fmax_, porosity,
+                                                                              out_u8, out_u8 ? nullptr : out_f64);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;

@@ -36,7 +36,7 @@ def _result_for_no_background(shape, radii):
     return out
 
 
-def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True, result=None):
+def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True):
     """Device loop over the effective thresholds (in groups of <= 253) -> float64 radius map."""
     torch = dev._torch()
     n = int(np.prod(shape))
@@ -46,7 +46,7 @@ def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True, 
     if ngroups == 1 and as_numpy:
         # common case: the float64 map (F:1178) is only materialised on the host
         dev.local_thickness_idx(ctx, d2, T, idx, inlets_u8, inlet_mode, ndim, shape, 0)
-        return dev.expand_idx_to_host(ctx, idx, np.concatenate([[0.0], R]), shape, result=result)
+        return dev.expand_idx_to_host(ctx, idx, np.concatenate([[0.0], R]), shape)
     out = torch.empty(n, dtype=torch.float64, device=d2.device)
     for g in range(ngroups):
         Tg, Rg = T[g * G:(g + 1) * G], R[g * G:(g + 1) * G]
@@ -87,20 +87,7 @@ def porosimetry(im, sizes: int = 25, inlets=None, access_limited: bool = True,
     if ndim == 0 or int(np.prod(shape)) == 0:
         return np.zeros(shape)
     ctx = _lib.context()
-    # numpy result (F:1178 `imresults = np.zeros(...)`): the page-locked float64 array is zeroed by
-    # background host threads while the GPU computes, so the epilogue only stores non-zero lines
-    result = None
-    if as_numpy and int(np.prod(shape)) * 8 >= dev.PREZERO_MIN_BYTES:
-        result = dev.HostResult(ctx, shape)
-    try:
-        return _porosimetry_device(ctx, im, shape, ndim, sizes, inlets, access_limited, as_numpy, torch, result)
-    finally:
-        if result is not None:
-            result.finish()
-
-
-def _porosimetry_device(ctx, im, shape, ndim, sizes, inlets, access_limited, as_numpy, torch, result):
-    im_u8 = dev.to_device_u8(im, ctx)
+    im_u8 = dev.to_device_u8(im, ctx, positive=True)          # F:1126 edt(im > 0)
     d2, max_d2 = dev.edt_run(ctx, im_u8, shape, want_max=True)    # max fused into the last pass
     del im_u8
     radii = host.reference_sizes(sizes, max_d2)
@@ -123,7 +110,7 @@ def _porosimetry_device(ctx, im, shape, ndim, sizes, inlets, access_limited, as_
         res = _result_for_no_background(shape, radii)
         return res if as_numpy else torch.from_numpy(res).to(d2.device)
     T, R = host.effective_thresholds(radii, max_d2)
-    return _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=as_numpy, result=result)
+    return _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=as_numpy)
 
 
 def local_thickness(im, sizes: int = 25, mode: str = "hybrid", divs: int = 1):
@@ -322,15 +309,12 @@ def find_trapped_regions(seq, outlets=None, bins: int = 25, return_mask: bool = 
         bins = np.linspace(seq.max(), 1, bins)
     conn = 6 if seq.ndim == 3 else 4
     ctx = _lib.context()
-    seq_t = torch.from_numpy(np.ascontiguousarray(seq)).to(f"cuda:{ctx.device}")
     out_t = _mask_to_device(outlets, ctx, seq.shape)
-    trapped = torch.zeros(seq.shape, dtype=torch.bool, device=seq_t.device)
+    trapped = torch.zeros(seq.shape, dtype=torch.bool, device=out_t.device)
     for i in bins:
-        # the comparison runs in numpy's result type for (seq dtype, bin value), like `seq >= i` (F:133)
-        thr = np.asarray(i)
-        cmp_dtype = np.result_type(seq.dtype, thr.dtype)
-        a = seq_t if cmp_dtype == seq.dtype else seq_t.to(getattr(torch, np.dtype(cmp_dtype).name))
-        temp = (a >= thr.astype(cmp_dtype).item()).to(torch.uint8)
+        # `seq >= i` is numpy's own comparison (F:133: any dtype numpy accepts, its promotion rules); only
+        # the resulting mask goes to the device
+        temp = _mask_to_device(seq >= i, ctx, seq.shape)
         reached = _reached_from(ctx, temp, temp * out_t, conn)
         trapped |= (temp != 0) & (reached == 0)
     trapped = _mask_to_host(trapped)

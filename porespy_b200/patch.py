@@ -1,38 +1,52 @@
 """Monkey-patch points for unmodified PoreSpy scripts:
 `sys.modules['edt']`, `porespy.filters.{porosimetry, local_thickness, trim_disconnected_blobs}` (and the
 other flood users: `find_disconnected_voxels`, `fill_blind_pores`, `trim_floating_solid`,
-`trim_nonpercolating_paths`)
-and the `edt` name bound inside `porespy.filters._funcs` / `porespy.tools._funcs`."""
+`trim_nonpercolating_paths`, `find_trapped_regions`), and the `edt` name that every PoreSpy module bound with
+`from edt import edt` (46 call sites, SURVEY 8(f) rank 1: filters/_funcs.py:5, tools/_funcs.py:6,
+filters/_snows.py, simulations/_drainage.py, simulations/_ibip.py, networks/_getnet.py,
+metrics/_regionprops.py, generators/_imgen.py, generators/_pseudo_packings.py, io/_funcs.py, beta/*)."""
 import sys
 import types
 
 _saved = {}
 
+_FILTERS = ("porosimetry", "local_thickness", "trim_disconnected_blobs", "find_disconnected_voxels",
+            "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths", "find_trapped_regions")
+
 
 def install(patch_edt_module=True):
-    """Route PoreSpy's hot path through porespy_b200.  Safe to call before or after
-    `import porespy`."""
+    """Route PoreSpy's hot path through porespy_b200.  Safe to call before or after `import porespy`:
+    before, the `edt` shim in `sys.modules` is what PoreSpy's `from edt import edt` lines pick up; after,
+    every already imported `porespy.*` module whose `edt` attribute is the original function is rebound."""
     from . import edt as edt_mod
     from . import filters as f
     if patch_edt_module and "edt" not in _saved:
-        _saved["edt"] = sys.modules.get("edt")
+        old = sys.modules.get("edt")
+        _saved["edt"] = old
         shim = types.ModuleType("edt")
         shim.edt, shim.edtsq = edt_mod.edt, edt_mod.edtsq
         shim.__doc__ = "porespy_b200 drop-in for the `edt` package"
         sys.modules["edt"] = shim
     ps = sys.modules.get("porespy")
     if ps is not None and "porespy" not in _saved:
-        _saved["porespy"] = {}
-        for name in ("porosimetry", "local_thickness", "trim_disconnected_blobs", "find_disconnected_voxels",
-                     "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths", "find_trapped_regions"):
-            for mod in (ps.filters, getattr(ps.filters, "_funcs", None)):
+        saved = _saved["porespy"] = {}
+        for name in _FILTERS:
+            for mod in (getattr(ps, "filters", None), sys.modules.get("porespy.filters._funcs")):
                 if mod is not None and hasattr(mod, name):
-                    _saved["porespy"][(mod, name)] = getattr(mod, name)
+                    saved[(mod, name)] = getattr(mod, name)
                     setattr(mod, name, getattr(f, name))
-        for modname in ("porespy.filters._funcs", "porespy.tools._funcs"):
-            mod = sys.modules.get(modname)
-            if mod is not None and hasattr(mod, "edt"):
-                _saved["porespy"][(mod, "edt")] = mod.edt
+        old_edt = _saved.get("edt")
+        originals = {getattr(old_edt, "edt", None)} - {None}
+        for modname, mod in list(sys.modules.items()):
+            if mod is None or not (modname == "porespy" or modname.startswith("porespy.")):
+                continue
+            cur = mod.__dict__.get("edt")
+            if cur is None or isinstance(cur, types.ModuleType) or cur is edt_mod.edt:
+                continue
+            # `from edt import edt` binds the function; rebind it when it is the original package's
+            # function (or, when the original package is unknown, any callable of that name)
+            if callable(cur) and (not originals or cur in originals):
+                saved[(mod, "edt")] = cur
                 mod.edt = edt_mod.edt
 
 

@@ -61,8 +61,8 @@ class CudaBackend:
     def zeros(self, n, dtype):
         return self.torch.zeros(int(n), dtype=dtype, device=self.device)
 
-    def to_u8(self, arr):
-        return dev.to_device_u8(arr, self.ctx).reshape(-1)
+    def to_u8(self, arr, positive=False):
+        return dev.to_device_u8(arr, self.ctx, positive=positive).reshape(-1)
 
     def bit_ok(self, shape, T):
         return shape[2] % 32 == 0 and T <= self.bit_tmax
@@ -271,6 +271,65 @@ class ShardedVolume:
                              f"use fewer ranks for this volume")
         return nlo, nhi
 
+    # --------------------------------------------------------------------------- inputs
+    def blobs(self, porosity=0.5, blobiness=1, seed=0):
+        """This rank's slab (uint8 0/1 device tensor) of ONE global `ps.generators.blobs(shape, porosity,
+        blobiness)` image (generators/_imgen.py:1023-1051).  The noise is a function of the global voxel index
+        (Philox keyed by `seed`), so each rank draws its own planes plus the reach of the z filter: no data
+        exchange, and the image is the same for every number of ranks.  Only the per-plane sums of the
+        statistics are gathered (fixed order)."""
+        from . import generators as gen
+        be, torch = self.backend, self.torch
+        ctx = be.ctx
+        nz, ny, nx = self.shape
+        _, sigma = gen._prologue(self.shape, blobiness, 1)
+        z0, nzl, plane = self.zstarts[self.rank], self.nzl, ny * nx
+        rz = gen.gaussian_kernel(sigma[0])[0] if float(sigma[0]) > 1e-15 else 0
+        if rz >= nz:
+            raise ValueError("blobs: the z filter is longer than the volume")
+        # global planes the z correlation of my slab touches (reflection at the global ends folds back inside)
+        lo, hi = max(0, z0 - rz), min(nz, z0 + nzl + rz)
+        if z0 - rz < 0:
+            hi = max(hi, min(nz, rz - z0))
+        if z0 + nzl + rz > nz:
+            lo = min(lo, max(0, 2 * nz - (z0 + nzl + rz)))
+        a = gen.philox_noise(ctx, (hi - lo) * plane, seed, first=lo * plane)
+        b = torch.empty(nzl * plane, dtype=torch.float64, device=a.device)
+        if rz > 0 or float(sigma[0]) > 1e-15:
+            gen.gauss_axis(ctx, a, b, 0, sigma[0], (nzl, ny, nx), z_out0=z0, z_in0=lo, nz_in=hi - lo, nz_glob=nz)
+        else:
+            b.copy_(a[(z0 - lo) * plane:(z0 - lo + nzl) * plane])
+        a = torch.empty_like(b)
+        for axis in (1, 2):
+            if float(sigma[axis]) > 1e-15:
+                gen.gauss_axis(ctx, b, a, axis, sigma[axis], (nzl, ny, nx))
+                a, b = b, a
+        f = b
+        del a
+        s, flo, fhi = gen.field_stats(ctx, f, nzl, plane)
+        n = nz * ny * nx
+        mean = gen.combine_sum(self._gather_planes(s)) / n
+        sq = gen._stat(ctx, f, nzl, plane, mean, 1)
+        sd = float(np.sqrt(gen.combine_sum(self._gather_planes(sq)) / n))
+        flo = -self._allreduce_max_f64(-flo)
+        fhi = self._allreduce_max_f64(fhi)
+        return gen.finish(ctx, f, nzl * plane, mean, sd, flo, fhi, porosity)
+
+    def _gather_planes(self, part):
+        """Per-plane partial sums of every rank, in global plane order (numpy [nz][chunks])."""
+        if self.world == 1:
+            return part
+        out = [None] * self.world
+        _dist().all_gather_object(out, np.asarray(part), group=self.group)
+        return np.concatenate(out, axis=0)
+
+    def _allreduce_max_f64(self, value):
+        if self.world == 1:
+            return float(value)
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self._comm_device())
+        _dist().all_reduce(t, op=_dist().ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
     # ------------------------------------------------------------------------------ EDT
     def edt_sq(self, local_u8):
         """Local slab (uint8, flat or [nzl][ny][nx]) -> (uint32 squared distances of the slab as a
@@ -368,16 +427,19 @@ class ShardedVolume:
         lshape = (nzl, ny, nx)
         # the radius loop only needs the class of every voxel, so the distances are classified on the
         # pencils and ONE byte per voxel travels back to the slabs instead of four
-        d2p, lmax = self._edt_pencils(be.to_u8(local_im))
+        d2p, lmax = self._edt_pencils(be.to_u8(local_im, positive=True))       # F:1126 edt(im > 0)
         max_d2 = self._allreduce_max(lmax)
+        self.last_max_d2 = max_d2
         radii = host.reference_sizes(sizes, max_d2)
         if max_d2 == host.INF_U32:
             from .filters import _result_for_no_background
             res = _result_for_no_background(lshape, radii)
-            return torch.from_numpy(res).to(self._comm_device())
+            return res if to_host else torch.from_numpy(res).to(self._comm_device())
         T, R = host.effective_thresholds(radii, max_d2)
         if len(T) > _lib.MAX_THRESHOLDS:
             raise NotImplementedError("sharded path supports up to 253 effective radii per call")
+        if len(T) and self.world > 1:
+            self._halo_depths(host.isqrt(int(T[0]) - 1))     # the deepest reach must fit the thinnest slab: fail before any exchange
         n = nzl * ny * nx
         idx = be.zeros(n, torch.uint8)
         if len(T) == 0:

@@ -86,7 +86,8 @@ def main():
 
     # ---- the 1024^3 volume of configs 2 and 3 (and the same EDT at full size)
     S = args.size
-    im = bench.device_blobs((S,) * 3, 0.6, 2, 0, device)
+    im = psb.generators.blobs([S] * 3, porosity=0.6, blobiness=2, seed=0, rng="philox", as_numpy=False)
+    torch.cuda.empty_cache()
     n = im.numel()
     t_edt = timed(lambda: dev.edt_run(ctx, im, im.shape, as_f32=True)[0], reps=5, warm=2)
     out["edt_full"] = {"shape": [S] * 3, "ms_f32": t_edt, "voxels_per_s": n / (t_edt * 1e-3),

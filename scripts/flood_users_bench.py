@@ -17,7 +17,7 @@ from porespy_b200 import _lib
 def main():
     S = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     ctx = _lib.context(0)
-    im = bench.device_blobs((S,) * 3, 0.6, 2, 0, torch.device("cuda", 0)).cpu().numpy().astype(bool)
+    im = psb.generators.blobs([S] * 3, porosity=0.6, blobiness=2, seed=0, rng="philox")
     f = psb.filters
     inl, outl = np.zeros_like(im), np.zeros_like(im)
     inl[0], outl[-1] = True, True

@@ -11,7 +11,8 @@ import porespy_b200 as psb
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 mode = sys.argv[2] if len(sys.argv) > 2 else "lt"
-im = bench.device_blobs((size,) * 3, bench.POROSITY, bench.BLOBINESS, 0, torch.device("cuda", 0))
+im = psb.generators.blobs([size] * 3, porosity=bench.POROSITY, blobiness=bench.BLOBINESS, seed=0, rng="philox", as_numpy=False)
+torch.cuda.empty_cache()
 torch.cuda.synchronize()
 if mode == "lt":
     out = psb.filters.local_thickness(im, sizes=bench.SIZES)

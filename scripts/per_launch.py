@@ -8,7 +8,8 @@ from porespy_b200 import _lib, _host
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 dev = torch.device("cuda", 0)
-im = bench.device_blobs((size,) * 3, 0.6, 2, 0, dev)
+im = psb.generators.blobs([size] * 3, porosity=0.6, blobiness=2, seed=0, rng="philox", as_numpy=False)
+torch.cuda.empty_cache()
 ctx = _lib.context(0)
 if os.environ.get("BIT_TMAX"):
     ctx.set_bit_tmax(int(os.environ["BIT_TMAX"]))

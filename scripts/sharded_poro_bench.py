@@ -27,7 +27,8 @@ def main():
     ctx = _lib.context(local)
     shape = (world * S, S, S)
     job = ShardedVolume(shape, ctx)
-    im = bench.device_blobs(job.local_shape, 0.6, 2, seed=rank, device=device, sigma_shape=(S,) * 3)
+    im = job.blobs(porosity=0.6, blobiness=2.0 * float(np.mean(shape)) / S, seed=0).view(*job.local_shape)
+    torch.cuda.empty_cache()
     times = []
     for it in range(3):
         if world > 1:

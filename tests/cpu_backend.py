@@ -23,10 +23,12 @@ class CpuBackend:
     def zeros(self, n, dtype):
         return torch.zeros(int(n), dtype=dtype)
 
-    def to_u8(self, arr):
+    def to_u8(self, arr, positive=False):
         if isinstance(arr, torch.Tensor):
             arr = arr.numpy()
-        return torch.from_numpy(np.ascontiguousarray(np.asarray(arr) != 0).view(np.uint8).copy()).reshape(-1)
+        arr = np.asarray(arr)
+        mask = (arr > 0) if positive else (arr != 0)
+        return torch.from_numpy(np.ascontiguousarray(mask).view(np.uint8).copy()).reshape(-1)
 
     def bit_ok(self, shape, T):
         return shape[2] % 32 == 0 and T <= self.bit_tmax

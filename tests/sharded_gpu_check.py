@@ -15,14 +15,11 @@ from porespy_b200 import _lib
 from porespy_b200.sharded import ShardedVolume
 
 
-def main():
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = _lib.context(local)
-    cases = [((96, 88, 128), 12, 200), ((97, 70, 160), 10, 0), ((64, 64, 96), [9, 6.5, 4, 2.5, 1.5, 1], 20)]
+CASES = [((96, 88, 128), 12, 200), ((97, 70, 160), 10, 0), ((64, 64, 96), [9, 6.5, 4, 2.5, 1.5, 1], 20)]
+
+
+def run_cases(ctx, rank, world, cases, verbose=True):
+    """Raises AssertionError on the first mismatch."""
     for shape, sizes, bit_tmax in cases:
         im = oc.blobs(list(shape), porosity=0.6, blobiness=1.5, seed=5)
         job = ShardedVolume(shape, ctx)
@@ -54,8 +51,32 @@ def main():
                 bad = np.argwhere(mip != ref[sl])
                 raise AssertionError(f"rank {rank}: porosimetry {shape} inlets={inl}: {len(bad)} voxels differ, "
                                      f"first {bad[:5].tolist()}")
-        if rank == 0:
+        if rank == 0 and verbose:
             print(f"sharded x{world} ok: {shape} sizes={sizes} bit_tmax={bit_tmax}", flush=True)
+
+
+def check_sharded_blobs(ctx, rank, world):
+    """The sharded generator yields the slabs of the SAME image the one-GPU generator draws from Philox noise
+    (the z filter reads noise planes beyond the slab; statistics are fixed-order per-plane sums)."""
+    import porespy_b200 as psb
+    for shape, blob in (((120, 64, 96), 2), ((90, 50, 64), [1, 2, 3])):
+        whole = psb.generators.blobs(list(shape), porosity=0.6, blobiness=blob, seed=11, rng="philox")
+        job = ShardedVolume(shape, ctx)
+        mine = job.blobs(porosity=0.6, blobiness=blob, seed=11).cpu().numpy().reshape(job.local_shape).astype(bool)
+        assert np.array_equal(mine, whole[job.local_slice()]), f"rank {rank}: sharded blobs differ {shape}"
+    if rank == 0:
+        print(f"sharded x{world} blobs ok", flush=True)
+
+
+def main():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = _lib.context(local)
+    run_cases(ctx, rank, world, CASES)
+    check_sharded_blobs(ctx, rank, world)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -399,37 +399,9 @@ def test_host_epilogue_split(psb, permille, threads):
     assert np.array_equal(out, lut[idx.cpu().numpy()])
 
 
-def test_host_epilogue_prezeroed(psb):
-    """HostResult: the output zeroed in the background, the epilogue skipping all-zero lines -- same map
-    (the pinned buffer is recycled between calls, so stale non-zero data would show up here)."""
-    import torch
-    from porespy_b200 import _device as dev
-    from porespy_b200 import _lib
-    ctx = _lib.context()
-    n = 2 * (1 << 24) + 777
-    lut = np.concatenate([[0.0], np.linspace(30, 1, 20)])
-    for seed in (0, 1):
-        g = torch.Generator(device="cuda")
-        g.manual_seed(seed)
-        idx = torch.randint(0, 21, (n,), generator=g, device="cuda", dtype=torch.uint8)
-        idx[torch.rand(n, generator=g, device="cuda") < 0.6] = 0                     # long and short runs of zeros
-        idx[(1 << 22):(1 << 23)] = 0
-        res = dev.HostResult(ctx, (n,))
-        out = dev.expand_idx_to_host(ctx, idx, lut, (n,), result=res)
-        assert np.array_equal(out, lut[idx.cpu().numpy()])
-        del out, res
-
-
 def test_local_thickness_large_numpy_result(psb):
-    """Public API on a volume large enough for the background-zeroed host result (>= 2^28 bytes of
-    float64; opt-in, so switched on here)."""
-    from porespy_b200 import _device as dev
-    monkey = dev.PREZERO_MIN_BYTES
-    dev.PREZERO_MIN_BYTES = 1 << 28
-    try:
-        _large_numpy_result(psb)
-    finally:
-        dev.PREZERO_MIN_BYTES = monkey
+    """Public API on a volume whose float64 result goes through the host-result epilogue (>= 2^28 bytes)."""
+    _large_numpy_result(psb)
 
 
 def _large_numpy_result(psb):
@@ -515,3 +487,119 @@ def test_find_trapped_regions(psb, golden):
     s = psb.filters.find_trapped_regions(seq2, outlets=outl, bins=None, return_mask=False)
     assert np.array_equal(s, g.raw("s2d_outlet_seq"))
     assert np.array_equal(seq2, g.raw("seq2d"))                 # input not modified
+
+
+# -------------------------------------------------------------------- round-2 additions
+def test_back_to_back_uploads_keep_both_masks(psb):
+    """Two different >= 64 MiB host volumes uploaded through the shared page-locked staging buffer one
+    right after the other (trim_disconnected_blobs: fg then inlets) must both arrive intact."""
+    import torch
+    from porespy_b200 import _device as dev
+    from porespy_b200 import _lib
+    ctx = _lib.context()
+    n = (1 << 26) + 4099
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 2, n, dtype=np.uint8)
+    b = rng.integers(0, 2, n, dtype=np.uint8)
+    for _ in range(3):
+        ta = dev.to_device_u8(a, ctx)
+        tb = dev.to_device_u8(b, ctx)
+        tc = dev.to_device_u8(a ^ b, ctx)
+        torch.cuda.synchronize()
+        assert np.array_equal(ta.cpu().numpy(), a)
+        assert np.array_equal(tb.cpu().numpy(), b)
+        assert np.array_equal(tc.cpu().numpy(), a ^ b)
+
+
+def test_divs_tensor_inlets_and_signed_images(psb):
+    import torch
+    im = oc.blobs([48, 40, 64], porosity=0.6, blobiness=1.5, seed=21)
+    want = oc.local_thickness(im, sizes=9, mode="dt")
+    assert_same(psb.filters.local_thickness(im, sizes=9, divs=2), want, "divs=2")           # F:947-952 signature
+    assert_same(psb.filters.porosimetry(im, sizes=9, divs=[2, 1, 2], access_limited=False), want, "divs list")
+    # negative voxels are background (F:1126 `im > 0`), for numpy and for device tensors
+    signed = im.astype(np.int16)
+    signed[~im] = -1
+    assert_same(psb.filters.local_thickness(signed, sizes=9), want, "signed image")
+    got = psb.filters.local_thickness(torch.from_numpy(signed.astype(np.float32)).cuda(), sizes=9)
+    assert_same(got.cpu().numpy(), want, "signed float tensor image")
+    # inlets as a device tensor
+    inl = np.zeros(im.shape, dtype=bool)
+    inl[:, 0, :] = True
+    wantp = oc.porosimetry(im, sizes=9, inlets=inl, mode="dt")
+    assert_same(psb.filters.porosimetry(im, sizes=9, inlets=torch.from_numpy(inl).cuda()), wantp, "tensor inlets")
+    with pytest.raises(Exception, match="inlets not valid"):
+        psb.filters.porosimetry(im, inlets=torch.zeros(im.shape, dtype=torch.uint8).cuda())
+
+
+def test_patch_install_rebinds_every_module(psb):
+    """install() after the (stand-in) PoreSpy modules did `from edt import edt`: every porespy.* module that
+    holds the original function is rebound, uninstall() restores them."""
+    import sys, types
+    from porespy_b200 import patch
+
+    def original_edt(data, **kw):
+        raise AssertionError("the original edt must not be called after install()")
+
+    fake_edt = types.ModuleType("edt")
+    fake_edt.edt = original_edt
+    mods = {"edt": fake_edt}
+    for name in ("porespy", "porespy.filters", "porespy.filters._funcs", "porespy.filters._snows",
+                 "porespy.tools", "porespy.tools._funcs", "porespy.simulations", "porespy.simulations._drainage"):
+        mods[name] = types.ModuleType(name)
+    mods["porespy"].filters = mods["porespy.filters"]
+    mods["porespy.filters"]._funcs = mods["porespy.filters._funcs"]
+    for name in ("porespy.filters._funcs", "porespy.filters._snows", "porespy.tools._funcs",
+                 "porespy.simulations._drainage"):
+        mods[name].edt = original_edt                                  # `from edt import edt`
+    mods["porespy.filters._funcs"].porosimetry = lambda *a, **k: None
+    mods["porespy.filters"].porosimetry = mods["porespy.filters._funcs"].porosimetry
+
+    def ps_ball(r):                                                    # T:1149-1155, through the module's `edt`
+        probe = np.ones([2 * int(np.ceil(r)) + 1] * 3, dtype=bool)
+        probe[(int(np.ceil(r)),) * 3] = False
+        return mods["porespy.tools._funcs"].edt(probe) < r
+    saved = {k: sys.modules.get(k) for k in mods}
+    sys.modules.update(mods)
+    try:
+        patch.install()
+        assert sys.modules["edt"].edt is psb.edt
+        for name in ("porespy.filters._funcs", "porespy.filters._snows", "porespy.tools._funcs",
+                     "porespy.simulations._drainage"):
+            assert mods[name].edt is psb.edt, name
+        assert mods["porespy.filters"].porosimetry is psb.filters.porosimetry
+        assert int(ps_ball(3).sum()) == 93                             # test_tools.py:309-316
+        patch.uninstall()
+        assert sys.modules["edt"] is fake_edt
+        assert mods["porespy.filters._snows"].edt is original_edt
+    finally:
+        patch.uninstall()
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+# ---------------------------------------------------------------- blobs generator (8(f) rank 4b)
+@pytest.mark.parametrize("shape,por,blob", [((64, 64, 64), 0.6, 1), ((50, 70, 90), 0.5, 2), ((120, 130), 0.55, 1),
+                                            ((33, 40, 200), 0.7, [1, 2, 3]), ((100, 100, 100), 0.499, 2)])
+def test_blobs_generator_vs_host(psb, shape, por, blob):
+    """numpy-seeded noise: the device generator reproduces the host blobs() (scipy gaussian_filter + numpy
+    norm_to_uniform); only voxels within rounding of the threshold may differ."""
+    want = oc.blobs(list(shape), porosity=por, blobiness=blob, seed=4)
+    got = psb.generators.blobs(list(shape), porosity=por, blobiness=blob, seed=4)
+    assert got.dtype == np.bool_ and got.shape == tuple(shape)
+    assert (got != want).sum() <= max(1, got.size // 200000), f"{(got != want).sum()} voxels differ"
+    field = psb.generators.blobs(list(shape), porosity=None, blobiness=blob, seed=4)
+    wantf = oc.blobs(list(shape), porosity=None, blobiness=blob, seed=4)
+    assert field.dtype == np.float64
+    np.testing.assert_allclose(field, wantf, rtol=0, atol=1e-12)
+
+
+def test_blobs_generator_philox(psb):
+    a = psb.generators.blobs([96, 80, 128], porosity=0.6, blobiness=2, seed=7, rng="philox")
+    b = psb.generators.blobs([96, 80, 128], porosity=0.6, blobiness=2, seed=7, rng="philox")
+    c = psb.generators.blobs([96, 80, 128], porosity=0.6, blobiness=2, seed=8, rng="philox")
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert abs(a.mean() - 0.6) < 0.02

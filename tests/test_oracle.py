@@ -197,3 +197,30 @@ def test_find_trapped_regions_golden(golden):
     for kw, key in cases:
         assert np.array_equal(oc.find_trapped_regions(**kw), g.mask(key)), key
     assert np.array_equal(oc.find_trapped_regions(seq2, outlets=outl, bins=None, return_mask=False), g.raw("s2d_outlet_seq"))
+
+
+@pytest.mark.parametrize("shape,seed", [((60, 50, 70), 1), ((40, 80), 2), ((33, 31, 64), 3)])
+def test_c_loop_matches_numpy_restatement(shape, seed):
+    """oracle_porosimetry_dt (the radius loop in C, used at 1024^3) == the numpy restatement of F:1124-1212."""
+    im = oc.blobs(list(shape), porosity=0.6, blobiness=1.5, seed=seed)
+    for sizes in (12, np.linspace(1, 8, 17), [5, 3, 2], np.int64(3)):
+        assert np.array_equal(oc.porosimetry_c(im, sizes=sizes), oc.porosimetry(im, sizes=sizes, mode="dt"))
+        assert np.array_equal(oc.local_thickness_c(im, sizes=sizes), oc.local_thickness(im, sizes=sizes, mode="dt"))
+    inl = np.zeros(shape, bool)
+    inl[0] = True
+    assert np.array_equal(oc.porosimetry_c(im, sizes=10, inlets=inl), oc.porosimetry(im, sizes=10, inlets=inl, mode="dt"))
+    pt = np.zeros(shape, bool)
+    pt[tuple(s // 2 for s in shape)] = True
+    assert np.array_equal(oc.porosimetry_c(im, sizes=7, inlets=pt), oc.porosimetry(im, sizes=7, inlets=pt, mode="dt"))
+    where = (np.array([0, 1]), np.array([2, 3]), np.array([4, 5]))      # F:1252-1255 (axis-0 fancy index quirk)
+    assert np.array_equal(oc.porosimetry_c(im, sizes=5, inlets=where), oc.porosimetry(im, sizes=5, inlets=where, mode="dt"))
+
+
+def test_c_loop_golden(golden):
+    g = golden.blobs100
+    im = g.mask("im")
+    assert np.array_equal(oc.local_thickness_c(im, sizes=25), g.rmap("lt_dt_25"))
+    assert np.array_equal(oc.porosimetry_c(im, sizes=np.arange(25, 1, -1)), g.rmap("poro_dt_arange_3d"))
+    inlets = np.zeros_like(im)
+    inlets[0, ...] = True
+    assert np.array_equal(oc.porosimetry_c(im, sizes=12, inlets=inlets), g.rmap("poro_inlet0_dt_12"))
