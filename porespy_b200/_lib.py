@@ -157,6 +157,11 @@ class Context:
         the uint32 kernel only."""
         check(self.lib.psb200_set_option(self.handle, b"edt16", 1 if on else 0))
 
+    def set_foot(self, foot):
+        """Warp footprint of the 16-bit min-plus scans (EDT y/z passes, per-radius y pass): 0 = 64 columns x
+        8 rows, 1 = 32 x 16."""
+        check(self.lib.psb200_set_option(self.handle, b"foot", int(foot)))
+
     def set_profile(self, on):
         check(self.lib.psb200_set_option(self.handle, b"profile", 1 if on else 0))
 

@@ -26,6 +26,7 @@ struct psb200_ctx {
     int profile;
     int bit_tmax;      // thresholds T <= bit_tmax use the bit-parallel dilation (0: never)
     int bit4;          // bit path: four-words-per-lane kernel for rows of 32 / 64 / 128 words
+    int foot;          // warp footprint of the 16-bit min-plus scans: 0 = 64 x 8 voxels, 1 = 32 x 16
     int edt16;         // EDT y/z passes: 16-bit two-voxels-per-instruction kernel first, uint32 kernel gated behind it
     int *flags;        // 64 device ints owned by the context (overflow flags of the 16-bit passes)
     unsigned flag_slot;

@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 #define MP_TX 128
+#define MP_TS 34                // shared-memory tile row stride of the 16-bit kernels in uint2 (272 bytes, see lt_y2_kernel)
 #define MP_WARPS 8
 // Internal "infinite" squared distance: larger than any real value (3 * 32766^2), and
 // MP_INF + 32766^2 still fits 32 bits, so  f + dy^2  never wraps.
@@ -253,8 +254,9 @@ __device__ __forceinline__ uint2 mp16_pack(const uint4 &v)
 }
 __device__ __forceinline__ uint32_t mp16_off(int d) { return min((uint32_t)(d * d), MP16_CAP) * 0x00010001u; }
 
-// grid / tile geometry as edt_minplus_kernel; dyn smem = rows * 256 + (H + 2) * 16 bytes.
-template <typename Src, int OUT>
+// grid / tile geometry as edt_minplus_kernel; dyn smem = rows * MP_TS * 8 + (H + 2) * 16 bytes.
+// FOOT: warp footprint of the scan, 0 = 64 columns x 8 rows, 1 = 32 x 16 (see lt_y2_kernel).
+template <typename Src, int OUT, int FOOT>
 __global__ void __launch_bounds__(MP16_WARPS * 32, 4)
 edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__ dst, int n,
                      int64_t rstride, int64_t nxc, int64_t ostride, int L, int H, int vec,
@@ -269,8 +271,8 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
     const typename Src::T *sbase = src + (int64_t)blockIdx.y * ostride + x0;
     const int Lr = (L + 3) & ~3;
     const int rows = Lr + 2 * H;
-    uint2 *tile = reinterpret_cast<uint2 *>(mp16_smem);                   // [rows][32]: 4 x u16 per entry
-    uint4 *offt = reinterpret_cast<uint4 *>(tile + (size_t)rows * 32);    // [H + 2]: packed capped (d + i)^2, i = 0..3
+    uint2 *tile = reinterpret_cast<uint2 *>(mp16_smem);                   // [rows][MP_TS]: 4 x u16 per entry
+    uint4 *offt = reinterpret_cast<uint4 *>(tile + (size_t)rows * MP_TS);    // [H + 2]: packed capped (d + i)^2, i = 0..3
     for (int d = tid; d < H + 2; d += MP16_WARPS * 32)
         offt[d] = make_uint4(mp16_off(d), mp16_off(d + 1), mp16_off(d + 2), mp16_off(d + 3));
     const uint4 INF4 = make_uint4(MP_INF, MP_INF, MP_INF, MP_INF);
@@ -288,7 +290,7 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = r0 + i * MP16_WARPS;
-                if (r < rows) tile[r * 32 + lane] = mp16_pack(in[i] ? Src::cvt(raw[i]) : INF4);
+                if (r < rows) tile[r * MP_TS + lane] = mp16_pack(in[i] ? Src::cvt(raw[i]) : INF4);
             }
         }
     } else {
@@ -296,7 +298,7 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
             const int gr = row0 - H + r0;
             uint4 v = INF4;
             if (gr >= 0 && gr < n) v = mp_load_row<Src>(sbase + (int64_t)gr * rstride, 4 * lane, valid, vec);
-            tile[r0 * 32 + lane] = mp16_pack(v);
+            tile[r0 * MP_TS + lane] = mp16_pack(v);
         }
     }
     __syncthreads();
@@ -305,16 +307,16 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
     // blocks: every half-warp reads 128 contiguous bytes of one tile row).  Block: 2 warps across x, 4 down.
     uint32_t lmax = 0;
     bool ovf = false;
-    const int cq = (warp & 1) * 16 + (lane & 15);
+    const int cq = FOOT ? (warp & 3) * 8 + (lane & 7) : (warp & 1) * 16 + (lane & 15);
     const int xl = 4 * cq;
-    for (int ry = ((warp >> 1) * 2 + (lane >> 4)) * 4; ry < L; ry += 32) {
+    for (int ry = FOOT ? ((warp >> 2) * 4 + (lane >> 3)) * 4 : ((warp >> 1) * 2 + (lane >> 4)) * 4; ry < L; ry += 32) {
         const int gr = row0 + ry;
         if (gr >= n) break;
         const int rr = ry + H;
         uint2 O[4];
         uint32_t B0[4], B1[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) O[i] = tile[(rr + i) * 32 + cq];
+        for (int i = 0; i < 4; ++i) O[i] = tile[(rr + i) * MP_TS + cq];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             B0[i] = O[i].x;
@@ -341,8 +343,8 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
 #pragma unroll
             for (int s2 = 0; s2 < 2; ++s2) {
                 if (dy > dlim) break;
-                const uint2 top = tile[(rr - dy) * 32 + cq];
-                const uint2 bot = tile[(rr + 3 + dy) * 32 + cq];
+                const uint2 top = tile[(rr - dy) * MP_TS + cq];
+                const uint2 bot = tile[(rr + 3 + dy) * MP_TS + cq];
                 const uint4 o4 = offt[dy];
                 const uint32_t of[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
@@ -362,7 +364,7 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
             if ((uint32_t)dy * (uint32_t)dy >= bm || (!up_in && !dn_in)) break;
             const uint32_t of[4] = {mp16_off(dy), mp16_off(dy + 1), mp16_off(dy + 2), mp16_off(dy + 3)};
             if (up_in) {
-                const uint2 top = (rr - dy >= 0) ? tile[(rr - dy) * 32 + cq]
+                const uint2 top = (rr - dy >= 0) ? tile[(rr - dy) * MP_TS + cq]
                                                  : mp16_pack(mp_load_row<Src>(sbase + (int64_t)(gr - dy) * rstride, xl, valid, vec));
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -371,7 +373,7 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
             }
             if (dn_in) {
                 const int rb = rr + 3 + dy;
-                const uint2 bot = (rb < rows) ? tile[rb * 32 + cq]
+                const uint2 bot = (rb < rows) ? tile[rb * MP_TS + cq]
                                               : mp16_pack(mp_load_row<Src>(sbase + (int64_t)(gr + 3 + dy) * rstride, xl, valid, vec));
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -442,28 +444,41 @@ edt_fix_inf_kernel(uint32_t *__restrict__ d2, int64_t n, uint32_t *__restrict__ 
 }
 
 // --------------------------------------------------------------- per-radius y pass (uint16x2)
-// gx: x-distance bytes min(d, W + 1) from xdist_kernel<XD_LT>.  reach byte
+// gx: x-distance bytes min(d, W + 1) from xdist_kernel<XD_LT>, 255 (GX_BG) at background voxels.  reach byte
 //   m = #{dz >= 0 : h + dz^2 < T} = ceil(sqrt(T - h))  where h = min_y' gx(y')^2 + (y - y')^2,
 // 0 where h >= T.  Needs T <= 32767 (W <= 181).
-// grid = (ceil(nx/128), ceil(ny/Ly), nz), block 256, dyn smem = (Ly + 2W) * 256 + 16 bytes.
+// Background voxels are never filled (a seed's open ball holds no background voxel), so their h is
+// irrelevant: they enter the tile as T + 1 (a "far" source for their neighbours), start with best = 0
+// so that they never prolong the scan of their 4 x 4 block, and leave with m = 0.  Blocks that hold
+// background voxels are the ones next to the solid, i.e. the ones that used to scan the full +/- W.
+// grid = (ceil(nx/128), ceil(ny/Ly), nz), block 256, dyn smem: see lt_y2_smem_bytes().
+// Tile rows are MP_TS uint2 apart (272 bytes): rows 4 apart then start 64 bytes apart modulo 128, so the
+// 32 x 16 warp footprint (FOOT 1: 8 column groups x 4 row blocks) is as conflict-free as the 64 x 8 one.
 __device__ __forceinline__ uint32_t sq_cap2(uint32_t a, uint32_t b, uint32_t W, uint32_t T)
-{   // two x-distances -> packed capped squares
-    const uint32_t sa = a > W ? T : a * a, sb = b > W ? T : b * b;
+{   // two x-distances -> packed capped squares (far: T, background: T + 1)
+    const uint32_t sa = a > W ? (a == GX_BG ? T + 1u : T) : a * a, sb = b > W ? (b == GX_BG ? T + 1u : T) : b * b;
     return sa | (sb << 16);
 }
 
 #define LTY_LUT_MAX 8192       // reach LUT in shared memory for T <= this, sqrtf above
 
+static inline size_t lt_y2_smem_bytes(int Ly, int W, uint32_t T)
+{
+    const int rows = ((Ly + 3) & ~3) + 2 * W;
+    return (size_t)rows * MP_TS * 8 + 16 + (size_t)(W + 2) * 16 + (size_t)Ly * 128 + (T <= LTY_LUT_MAX ? ((T + 16) & ~15u) : 0);
+}
+
+template <int FOOT>
 __global__ void __launch_bounds__(256)
 lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny, int nx, uint32_t T,
              int W, int Ly, const int *__restrict__ gate)
 {
     if (gate && *gate == 0) return;
     extern __shared__ uint4 lty2_smem[];
-    uint2 *tile = reinterpret_cast<uint2 *>(lty2_smem);          // [rows][32] : 4 x u16 per lane
+    uint2 *tile = reinterpret_cast<uint2 *>(lty2_smem);          // [rows][MP_TS] : 4 x u16 per lane
     const int tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
     const int rows = ((Ly + 3) & ~3) + 2 * W;                     // Ly rounded up to whole 4-row blocks
-    int *range = reinterpret_cast<int *>(tile + (size_t)rows * 32);   // [0] = first useful row, [1] = last
+    int *range = reinterpret_cast<int *>(tile + (size_t)rows * MP_TS);   // [0] = first useful row, [1] = last
     uint4 *offt = reinterpret_cast<uint4 *>(range + 4);               // [W + 2]: offt[d] = packed capped squares of d .. d+3
     uint32_t *sout = reinterpret_cast<uint32_t *>(offt + (W + 2));    // [Ly][32] reach bytes of the tile
     uint8_t *lut = reinterpret_cast<uint8_t *>(sout + (size_t)Ly * 32);   // lut[h] = ceil(sqrt(T - h)), lut[T] = 0
@@ -473,7 +488,7 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
     if (tid == 0) { range[0] = rows; range[1] = -1; }
     if (use_lut)
         for (uint32_t h = tid; h <= T; h += 256) lut[h] = h >= T ? 0 : (uint8_t)ceil_sqrt_small(T - h);
-    // offsets are capped at T so that value + offset <= 2T stays inside 16 bits
+    // offsets are capped at T so that value + offset <= 2T + 1 stays inside 16 bits
     for (int d = tid; d < W + 2; d += 256) {
         uint32_t o[4];
 #pragma unroll
@@ -509,7 +524,7 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
                 s[2 * q] = sq_cap2(a, b, uW, T);
                 s[2 * q + 1] = sq_cap2(c, d, uW, T);
             }
-            uint4 *dst = reinterpret_cast<uint4 *>(tile + (size_t)r * 32 + 4 * ch);
+            uint4 *dst = reinterpret_cast<uint4 *>(tile + (size_t)r * MP_TS + 4 * ch);    // row stride 272 = 17 * 16 bytes
             dst[0] = make_uint4(s[0], s[1], s[2], s[3]);
             dst[1] = make_uint4(s[4], s[5], s[6], s[7]);
             if (useful) { lo = min(lo, r); hi = max(hi, r); }
@@ -522,11 +537,13 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
     const int rlo = range[0], rhi = range[1];
 
     // ---- scan, register-tiled like edt_minplus_kernel: a lane owns 4 rows x 4 columns; the two
-    // rows fetched at step dy serve all 4 outputs.  Warp footprint 64 columns x 8 rows (lane = 16
-    // column groups x 2 row blocks: every half-warp reads 128 contiguous bytes, conflict-free).
-    const uint32_t T2 = T * 0x00010001u;
-    const int cq = (warp & 1) * 16 + (lane & 15);            // uint2 index inside the tile row
-    for (int ry = ((warp >> 1) * 2 + (lane >> 4)) * 4; ry < Ly; ry += 32) {
+    // rows fetched at step dy serve all 4 outputs.  Warp footprint 64 columns x 8 rows (FOOT 0: 16 column
+    // groups x 2 row blocks) or 32 x 16 (FOOT 1: 8 x 4, compacter: the lanes of a warp end their scans closer
+    // to each other); a half-warp reads 128 bytes without bank conflicts either way.
+    const uint32_t T2 = T * 0x00010001u, BG2 = (T + 1u) * 0x00010001u;
+    const int cq = FOOT ? (warp & 3) * 8 + (lane & 7) : (warp & 1) * 16 + (lane & 15);     // uint2 index inside the tile row
+    const int ry0 = FOOT ? ((warp >> 2) * 4 + (lane >> 3)) * 4 : ((warp >> 1) * 2 + (lane >> 4)) * 4;
+    for (int ry = ry0; ry < Ly; ry += 32) {
         if (y0 + ry >= ny) break;
         const int rr = ry + W;
         uint32_t m[4][4];
@@ -538,13 +555,15 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
                 for (int j = 0; j < 4; ++j) m[i][j] = 0;
         } else {
             uint2 O[4];
-            uint32_t B0[4], B1[4];
+            uint32_t B0[4], B1[4], G0[4], G1[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) O[i] = tile[(rr + i) * 32 + cq];
+            for (int i = 0; i < 4; ++i) O[i] = tile[(rr + i) * MP_TS + cq];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                B0[i] = __vminu2(O[i].x, T2);
-                B1[i] = __vminu2(O[i].y, T2);
+                G0[i] = __vcmpeq2(O[i].x, BG2);                   // 0xFFFF per background voxel
+                G1[i] = __vcmpeq2(O[i].y, BG2);
+                B0[i] = __vminu2(O[i].x, T2) & ~G0[i];            // background: nothing to find
+                B1[i] = __vminu2(O[i].y, T2) & ~G1[i];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (j != i) {
@@ -565,8 +584,8 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
                 for (int s2 = 0; s2 < 2; ++s2) {
                     const int d = dy + s2;
                     if (d > dmax) break;
-                    const uint2 top = tile[(rr - d) * 32 + cq];
-                    const uint2 bot = tile[(rr + 3 + d) * 32 + cq];
+                    const uint2 top = tile[(rr - d) * MP_TS + cq];
+                    const uint2 bot = tile[(rr + 3 + d) * MP_TS + cq];
                     const uint4 o4 = offt[d];                      // capped (d + i)^2, i = 0..3, both halves
                     const uint32_t of[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
@@ -578,7 +597,9 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const uint32_t h[4] = {B0[i] & 0xFFFFu, B0[i] >> 16, B1[i] & 0xFFFFu, B1[i] >> 16};
+                // background voxels leave with h = T (m = 0)
+                const uint32_t b0 = B0[i] | (G0[i] & T2), b1 = B1[i] | (G1[i] & T2);
+                const uint32_t h[4] = {b0 & 0xFFFFu, b0 >> 16, b1 & 0xFFFFu, b1 >> 16};
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     m[i][j] = use_lut ? (uint32_t)lut[min(h[j], T)] : (h[j] >= T ? 0u : ceil_sqrt_small(T - h[j]));

@@ -94,22 +94,28 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->bit_tmax = 200;
     c->edt16 = 1;
     c->bit4 = 1;
+    c->foot = 0;
     c->flag_slot = 0;
     CUDA_TRY(cudaMalloc(&c->flags, 64 * sizeof(int)));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_TRY(cudaFuncSetAttribute(lt_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
-    CUDA_TRY(cudaFuncSetAttribute(lt_y2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(lt_y2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(lt_y2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(xdist_kernel<XD_EDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(xdist_kernel<XD_LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
-    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
-    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
-    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
-    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU16, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU16, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU16, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU32, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU32, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU32, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(edt_minplus16_kernel<MpSrcU32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_x_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_x_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     *out = c;
@@ -142,6 +148,10 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
     }
     if (!strcmp(name, "bit4")) {
         ctx->bit4 = value ? 1 : 0;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "foot")) {
+        ctx->foot = value ? 1 : 0;
         return PSB200_OK;
     }
     if (!strcmp(name, "edt16")) {
@@ -353,17 +363,21 @@ static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src,
         int L16, H16;
         if (n <= 224) { L16 = n; H16 = 0; }
         else { L16 = 128; H16 = 48; }
-        const size_t smem16 = (size_t)(((L16 + 3) & ~3) + 2 * H16) * 256 + (size_t)(H16 + 2) * 16;
+        const size_t smem16 = (size_t)(((L16 + 3) & ~3) + 2 * H16) * MP_TS * 8 + (size_t)(H16 + 2) * 16;
         const int64_t gx16 = ((nxc + MP_TX - 1) / MP_TX) * ((n + L16 - 1) / L16);
         if (gx16 > 0x7FFFFFFFLL) return fail(PSB200_ERR_UNSUPPORTED, "edt pass: volume too large for one launch");
         dim3 grid16((unsigned)gx16, (unsigned)nouter);
         CUDA_TRY(cudaMemsetAsync(ovf, 0, sizeof(int), st));
         {
             ProfScope ps__(ctx, st, axis == 1 ? K_EDT_Y : K_EDT_Z);
-            if (out_kind == 0)
-                edt_minplus16_kernel<Src, 0><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
+            if (out_kind == 0 && !ctx->foot)
+                edt_minplus16_kernel<Src, 0, 0><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
+            else if (out_kind == 0)
+                edt_minplus16_kernel<Src, 0, 1><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
+            else if (!ctx->foot)
+                edt_minplus16_kernel<Src, 1, 0><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
             else
-                edt_minplus16_kernel<Src, 1><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
+                edt_minplus16_kernel<Src, 1, 1><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
         }
         LAUNCH_CHECK(ctx);
         gate = ovf;
@@ -718,14 +732,14 @@ static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_
     if (rc) return rc;
     {   // y pass
         int Ly = ny < 128 ? (int)ny : 128;
-        const int rows = ((Ly + 3) & ~3) + 2 * W;
-        const size_t smem = (size_t)rows * 256 + 16 + (size_t)(W + 2) * 16 + (size_t)Ly * 128 + (T <= LTY_LUT_MAX ? ((T + 16) & ~15u) : 0);
+        const size_t smem = lt_y2_smem_bytes(Ly, W, T);
         if ((int)smem > ctx->max_smem_optin)
             return fail(PSB200_ERR_UNSUPPORTED, "lt_y: tile needs %zu bytes of shared memory", smem);
         dim3 grid((unsigned)((nx + MP_TX - 1) / MP_TX), (unsigned)((ny + Ly - 1) / Ly), (unsigned)nz);
         {
             ProfScope ps__(ctx, st, K_LT_Y);
-            lt_y2_kernel<<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate);
+            if (ctx->foot) lt_y2_kernel<1><<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate);
+            else lt_y2_kernel<0><<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate);
         }
         LAUNCH_CHECK(ctx);
     }

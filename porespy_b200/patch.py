@@ -18,8 +18,9 @@ def install(patch_edt_module=True):
     """Route PoreSpy's hot path through porespy_b200.  Safe to call before or after `import porespy`:
     before, the `edt` shim in `sys.modules` is what PoreSpy's `from edt import edt` lines pick up; after,
     every already imported `porespy.*` module whose `edt` attribute is the original function is rebound."""
-    from . import edt as edt_mod
-    from . import filters as f
+    import importlib
+    edt_mod = importlib.import_module(".edt", __package__)     # (the package attribute `edt` is the function)
+    f = importlib.import_module(".filters", __package__)
     if patch_edt_module and "edt" not in _saved:
         old = sys.modules.get("edt")
         _saved["edt"] = old

@@ -13,6 +13,8 @@ torch.cuda.empty_cache()
 ctx = _lib.context(0)
 if os.environ.get("BIT_TMAX"):
     ctx.set_bit_tmax(int(os.environ["BIT_TMAX"]))
+if os.environ.get("FOOT"):
+    ctx.set_foot(int(os.environ["FOOT"]))
 for _ in range(2):
     psb.filters.local_thickness(im, sizes=25)
 torch.cuda.synchronize()

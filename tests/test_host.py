@@ -183,3 +183,46 @@ def test_bench_reference_arm_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_patch_install_logic_without_gpu():
+    """install()/uninstall() rebinding (sys.modules['edt'], every porespy.* module that bound the original `edt`,
+    the filters) on stand-in modules; no kernel is called."""
+    import importlib
+    import sys
+    import types
+    import porespy_b200
+    from porespy_b200 import patch
+    edt_mod = importlib.import_module("porespy_b200.edt")
+
+    def orig(data, **kw):
+        return "orig"
+
+    fake = types.ModuleType("edt")
+    fake.edt = orig
+    mods = {n: types.ModuleType(n) for n in ("porespy", "porespy.filters", "porespy.filters._funcs",
+                                             "porespy.tools._funcs", "porespy.networks._getnet")}
+    mods["porespy"].filters = mods["porespy.filters"]
+    for n in ("porespy.filters._funcs", "porespy.tools._funcs", "porespy.networks._getnet"):
+        mods[n].edt = orig
+    mods["porespy.filters._funcs"].porosimetry = lambda: 0
+    mods["porespy.filters"].porosimetry = mods["porespy.filters._funcs"].porosimetry
+    mods["edt"] = fake
+    saved = {k: sys.modules.get(k) for k in mods}
+    sys.modules.update(mods)
+    try:
+        patch.install()
+        assert sys.modules["edt"].edt is edt_mod.edt
+        for n in ("porespy.filters._funcs", "porespy.tools._funcs", "porespy.networks._getnet"):
+            assert mods[n].edt is edt_mod.edt
+        assert mods["porespy.filters"].porosimetry is porespy_b200.filters.porosimetry
+        patch.uninstall()
+        assert sys.modules["edt"] is fake
+        assert mods["porespy.networks._getnet"].edt is orig
+    finally:
+        patch.uninstall()
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
