@@ -55,28 +55,41 @@ lt_pack_kernel(const uint8_t *__restrict__ cls, uint32_t *__restrict__ bits, int
     }
 }
 
-// Two consecutive radii from one read of the class map: bits = (cls <= k), bits2 = (cls <= k + 1).
+// Up to PACKN_MAX consecutive radii from ONE read of the class map, bit-sliced: the class bytes of a word's 32
+// voxels are transposed into bit planes (nb low planes + one "any higher bit" mask), and  cls <= k  is then a
+// handful of bitwise operations per radius on whole words (a most-significant-bit-first comparator) instead
+// of a byte-SWAR compare per radius and per 4 voxels.  bits of radius k0 + i go to bits + i * vol_words.
+#define PACKN_MAX 16
 __global__ void __launch_bounds__(256)
-lt_pack2_kernel(const uint8_t *__restrict__ cls, uint32_t *__restrict__ bits, uint32_t *__restrict__ bits2,
-                int64_t nwords, int k, const int *__restrict__ gate)
+lt_packn_kernel(const uint8_t *__restrict__ cls, uint32_t *__restrict__ bits, int64_t nwords, int64_t vol_words,
+                int k0, int nk, int nb)
 {
-    if (gate && *gate == 0) return;
-    const uint32_t n = (uint32_t)(k + 1), n2 = n + 1u;     // non-seed <=> byte >= n (resp. n2)
-    const uint32_t nl4 = (n & 0x7Fu) * 0x01010101u, sel = n < 128u ? 0xFFFFFFFFu : 0u;
-    const uint32_t ml4 = (n2 & 0x7Fu) * 0x01010101u, sel2 = n2 < 128u ? 0xFFFFFFFFu : 0u;
+    const uint32_t hn = nb < 8 ? (1u << nb) : 0u;                       // "high" bytes are >= 2^nb
+    const uint32_t hl4 = (hn & 0x7Fu) * 0x01010101u, hsel = hn < 128u ? 0xFFFFFFFFu : 0u;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += step) {
         const uint4 a = __ldg(reinterpret_cast<const uint4 *>(cls) + 2 * w);
         const uint4 b = __ldg(reinterpret_cast<const uint4 *>(cls) + 2 * w + 1);
         const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t m = 0, m2 = 0;
+        uint32_t p[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, hi = 0u;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            m |= gather_bit7(swar_ge(v[q], nl4, sel) ^ 0x80808080u) << (4 * q);
-            m2 |= gather_bit7(swar_ge(v[q], ml4, sel2) ^ 0x80808080u) << (4 * q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < nb) p[j] |= (((((v[q] >> j) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * q);
+            if (nb < 8) hi |= gather_bit7(swar_ge(v[q], hl4, hsel)) << (4 * q);
         }
-        bits[w] = m;
-        bits2[w] = m2;
+        for (int i = 0; i < nk; ++i) {
+            const uint32_t k = (uint32_t)(k0 + i);
+            uint32_t lt = 0u, eq = 0xFFFFFFFFu;
+#pragma unroll
+            for (int j = 7; j >= 0; --j)
+                if (j < nb) {
+                    if ((k >> j) & 1u) { lt |= eq & ~p[j]; eq &= p[j]; }
+                    else eq &= ~p[j];
+                }
+            bits[(int64_t)i * vol_words + w] = (lt | eq) & ~hi;
+        }
     }
 }
 

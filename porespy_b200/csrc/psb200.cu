@@ -588,7 +588,8 @@ static size_t uf_list_entries(int64_t n) { return (size_t)(n < UF_SEG ? n : UF_S
 
 struct LtWorkspace {
     uint8_t *cls, *rcls, *reach, *gx;
-    uint32_t *seedbits, *seedbits2, *written;   // bit path: one bit per voxel (seed bits of two consecutive radii)
+    uint32_t *seedbits, *written;   // bit path: one bit per voxel (seed bits of up to PACKN_MAX consecutive radii)
+    size_t seed_words;              // words of one seed-bit volume inside seedbits
     uint32_t *parent;
     uint32_t *uf_list;    // voxels activated at the current radius (one segment of UF_SEG voxels at a time)
     int *gate;
@@ -608,8 +609,8 @@ static LtWorkspace carve_lt(const psb200_ctx *ctx, char *base, int64_t nz, int64
     w.cls = c.take<uint8_t>(n + 16);
     w.reach = c.take<uint8_t>(n + 16);
     w.gx = c.take<uint8_t>(n + 16);
-    w.seedbits = c.take<uint32_t>(n / 32 + 4);
-    w.seedbits2 = c.take<uint32_t>(n / 32 + 4);
+    w.seed_words = (n / 32 + 4 + 63) & ~(size_t)63;                 // keeps every volume 256-byte aligned
+    w.seedbits = c.take<uint32_t>(w.seed_words * PACKN_MAX);
     w.written = c.take<uint32_t>(n / 32 + 4);
     if (inlet_mode != PSB200_INLETS_NONE) {
         w.rcls = c.take<uint8_t>(n + 16);
@@ -933,28 +934,29 @@ static int lt_wmask_impl(psb200_ctx *ctx, const uint8_t *idx, uint32_t *written,
 }
 
 // One radius of the bit path.  Thresholds descend, so every radius after the first bit radius takes the
-// bit path too: the seed bits of radius k + 1 are packed together with those of radius k (one read of
-// the class map for two radii) into the second buffer.  `packed_for` is the radius whose seed bits
-// already sit in w.seedbits2 (-1: none).
+// bit path too: the seed bits of radii k .. k + PACKN_MAX - 1 are packed together from one read of the class
+// map (lt_packn_kernel).  `packed_lo/hi`: the radii whose seed bits sit in w.seedbits.
 static int lt_bit_step(psb200_ctx *ctx, LtWorkspace &w, const uint8_t *cmap, uint8_t *idx, int k, int nT, uint32_t T,
-                       int64_t nz, int64_t ny, int64_t nx, const int *gate, cudaStream_t st, int &packed_for)
+                       int64_t nz, int64_t ny, int64_t nx, const int *gate, cudaStream_t st, int &packed_lo,
+                       int &packed_hi)
 {
     const int64_t nwords = nz * ny * nx / 32;
-    const uint32_t *bits = w.seedbits;
-    if (packed_for == k) bits = w.seedbits2;
-    else if (k + 1 < nT && k + 1 < 253) {
+    if (k < packed_lo || k >= packed_hi) {
+        const int nk = nT - k < PACKN_MAX ? nT - k : PACKN_MAX;
+        int nb = 1;
+        while (nb < 8 && (k + nk - 1) >> nb) ++nb;
         {
             ProfScope ps__(ctx, st, K_LT_PACK);
-            // not gated: the second buffer must be valid at radius k + 1 even if radius k is still before the breakthrough
-            lt_pack2_kernel<<<grid_for(nwords, 256, ctx->sm_count, 16), 256, 0, st>>>(cmap, w.seedbits, w.seedbits2, nwords, k, nullptr);
+            // not gated: the buffers must be valid at the later radii even if radius k is still before the breakthrough
+            lt_packn_kernel<<<grid_for(nwords, 256, ctx->sm_count, 8), 256, 0, st>>>(cmap, w.seedbits, nwords,
+                                                                                  (int64_t)w.seed_words, k, nk, nb);
         }
         LAUNCH_CHECK(ctx);
-        packed_for = k + 1;
-    } else {
-        int rc = lt_pack_impl(ctx, cmap, k, w.seedbits, nwords, gate, st);
-        if (rc) return rc;
+        packed_lo = k;
+        packed_hi = k + nk;
     }
-    return lt_bitball_impl(ctx, bits, nz, 0, w.written, idx, k, T, nz, ny, nx, gate, st);
+    return lt_bitball_impl(ctx, w.seedbits + (size_t)(k - packed_lo) * w.seed_words, nz, 0, w.written, idx, k, T, nz, ny, nx,
+                           gate, st);
 }
 
 // step-level entry points of the bit path (z-slab shards exchange seed-bit halo planes between them)
@@ -1090,7 +1092,7 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
     const bool bit_ok = ctx->algo == PSB200_ALGO_FAST && ctx->bit_tmax > 0 && (nx % 32 == 0) && nz <= 65535 && n < (1LL << 35) &&
                         ((((uintptr_t)idx | (uintptr_t)cmap) & 15u) == 0);
     bool wmask_ready = false;
-    int packed_for = -1;
+    int packed_lo = 0, packed_hi = 0;
     for (int k = 0; k < nT; ++k) {
         const uint32_t T = T_host[k];
         if (al) {
@@ -1109,7 +1111,7 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
                 }
                 wmask_ready = true;
             }
-            rc = lt_bit_step(ctx, w, cmap, idx, k, nT, T, nz, ny, nx, gate, st, packed_for);
+            rc = lt_bit_step(ctx, w, cmap, idx, k, nT, T, nz, ny, nx, gate, st, packed_lo, packed_hi);
             if (rc) return rc;
             continue;
         }
