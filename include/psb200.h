@@ -278,6 +278,28 @@ int psb200_stats_f64(psb200_ctx *ctx, const double *x, int64_t nplanes, int64_t 
 int psb200_blobs_finish(psb200_ctx *ctx, const double *f, int64_t n, double mean, double sd, double fmin_,
                         double fmax_, double porosity, uint8_t *out_u8, double *out_f64, psb200_stream stream);
 
+/* ---- radius-map post-processing on the INDEX form: size_to_seq / size_to_satn /
+ * seq_to_satn (filters/_size_seq_satn.py:16-221), pore_size_distribution (metrics/_funcs.py:558-632), pc_curve's
+ * sizes branch (metrics/_funcs.py:1073-1090).  A map with K <= 65536 distinct values is one index per voxel
+ * (1 byte for K <= 256, else 2) plus a table; the functions above reduce to a histogram of the index map and a
+ * table expansion (porespy_b200/sizemap.py does the arithmetic on the K values with the reference's numpy code).
+ *   psb200_hist_idx    : counts[(mask && mask[i] ? K : 0) + idx[i]] += 1; counts: K (mask NULL) or 2K device
+ *                        uint64, zeroed by the call.
+ *   psb200_expand_lut8 : out[i] = lut[(mask && mask[i] ? K : 0) + idx[i]], 8-byte payloads (float64 / int64);
+ *                        lut: device, K or 2K entries.
+ *   psb200_distinct64  : distinct 8-byte patterns of x[0,n) into an open-addressing table of `cap` (power of
+ *                        two) device uint64 (empty slots = all ones; the call initialises it); *overflow = 1 when
+ *                        the table is too small.
+ *   psb200_index_of64  : idx[i] = position of x[i] in the sorted keys[0,K) (kind 0: float64 order, 1: int64). */
+int psb200_hist_idx(psb200_ctx *ctx, const void *idx, int idx_bytes, const uint8_t *mask, int64_t n, int K,
+                    uint64_t *counts, psb200_stream stream);
+int psb200_expand_lut8(psb200_ctx *ctx, const void *idx, int idx_bytes, const uint8_t *mask, const uint64_t *lut,
+                       void *out, int64_t n, int K, psb200_stream stream);
+int psb200_distinct64(psb200_ctx *ctx, const uint64_t *x, int64_t n, uint64_t *table, uint32_t cap, int *overflow,
+                      psb200_stream stream);
+int psb200_index_of64(psb200_ctx *ctx, const uint64_t *x, int64_t n, const uint64_t *keys, int K, int kind,
+                      void *idx, int idx_bytes, psb200_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

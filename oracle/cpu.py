@@ -368,3 +368,95 @@ def porosimetry_c(im, sizes=25, inlets=None, access_limited=True, nthreads=0):
 
 def local_thickness_c(im, sizes=25, nthreads=0):
     return porosimetry_c(im, sizes=sizes, access_limited=False, nthreads=nthreads)
+
+
+# ------------------------------------------- radius-map post-processing, plain numpy
+def size_to_seq(size, im=None, bins=None, mode="drainage"):
+    """filters/_size_seq_satn.py:62-83."""
+    solid = (size == 0) if im is None else (im == 0)
+    uninvaded = size == -1
+    if bins is None:
+        bins = np.unique(size)
+    elif isinstance(bins, int):
+        bins = np.linspace(0, size.max(), bins)
+    vals = np.digitize(size, bins=bins, right=True)
+    if mode.startswith("im"):
+        vals[solid] = 0
+        vals[uninvaded] = -1
+        vals = make_contiguous_symmetric(vals)
+    if mode.startswith("dr"):
+        vals = make_contiguous_symmetric(vals)
+        vals = vals.max() + 1 - vals
+        vals[solid] = 0
+        vals[uninvaded] = -1
+    return vals
+
+
+def size_to_satn(size, im=None, bins=None, mode="drainage"):
+    """filters/_size_seq_satn.py:134-149."""
+    if bins is None:
+        bins = np.unique(size[size > 0])
+    elif isinstance(bins, int):
+        bins = np.linspace(0, size.max(), bins)
+    if im is None:
+        im = ~(size == 0)
+    void_vol = im.sum()
+    satn = -np.ones_like(size, dtype=float)
+    if mode.startswith("im"):
+        for r in bins:
+            hits = (size <= r) * (size > 0)
+            satn[hits * (satn == -1)] = hits.sum() / void_vol
+    elif mode.startswith("dr"):
+        for r in bins[-1::-1]:
+            hits = (size >= r) * (size > 0)
+            satn[hits * (satn == -1)] = hits.sum() / void_vol
+    satn *= (im > 0)
+    return satn
+
+
+def seq_to_satn(seq, im=None, mode="drainage"):
+    """filters/_size_seq_satn.py:196-221 (rankdata 'dense' - 1 as the integer dense rank, see oracle/ref_shim.py)."""
+    seq = np.copy(seq).astype(int)
+    solid_mask = (seq == 0) if im is None else (im == 0)
+    uninvaded_mask = seq == -1
+    seq[seq <= 0] = 0
+    if mode.startswith("im"):
+        seq = seq.max() - seq + 1
+        seq[solid_mask] = 0
+        seq[uninvaded_mask] = 0
+    seq = np.unique(seq, return_inverse=True)[1].reshape(-1)
+    b = np.bincount(seq)
+    if (solid_mask.sum(dtype=np.int64) > 0) or (uninvaded_mask.sum(dtype=np.int64) > 0):
+        b[0] = 0
+    c = np.cumsum(b)
+    seq = np.reshape(seq, solid_mask.shape)
+    satn = c[seq] / (seq.size - solid_mask.sum(dtype=np.int64))
+    satn[solid_mask] = 0
+    satn[uninvaded_mask] = -1
+    return satn
+
+
+def pore_size_distribution(im, bins=10, log=True, voxel_size=1):
+    """metrics/_funcs.py:619-632 + _parse_histogram :861-884 -> dict of arrays."""
+    im = im.flatten()
+    vals = im[im > 0] * voxel_size
+    if log:
+        vals = np.log10(vals)
+    P, edges = np.histogram(vals, bins=bins, density=True)
+    widths = edges[1:] - edges[:-1]
+    return dict(pdf=P, cdf=np.cumsum((P * widths)[-1::-1])[-1::-1], satn=P * widths,
+                bin_centers=((edges[1:] + edges[:-1]) / 2) * 1, bin_edges=edges * 1, bin_widths=widths * 1)
+
+
+def pc_curve_sizes(im, sizes, sigma=0.072, theta=180, voxel_size=1):
+    """metrics/_funcs.py:1073-1090."""
+    if im is None:
+        im = ~(sizes == 0)
+    sz = np.unique(sizes)[:0:-1]
+    sz = np.hstack((sz[0] * 2, sz))
+    x, y = [], []
+    for n in sz:
+        r = n * voxel_size
+        x.append(-2 * sigma * np.cos(np.deg2rad(theta)) / r)
+        y.append(((sizes >= n) * (im == 1)).sum(dtype=np.int64) / im.sum(dtype=np.int64))
+    return np.asarray(x), np.asarray(y)

@@ -22,6 +22,8 @@ What is real and what is stubbed
   wheel (black_border=False: the image border is not background).
 * `skimage.morphology.{ball,disk,square,cube}` -- trivial restatements.
 * `dask.delayed/compute` -- serial; `skimage.segmentation.relabel_sequential`, `clear_border` -- numpy.
+* `scipy.stats.rankdata(method='dense')` inside `filters/_size_seq_satn.py` -- integer return type of SciPy < 1.18
+  restored (the installed SciPy 1.18 returns float64 and `np.bincount` rejects it).
 * everything else: inert MagicMock attributes (never on the hot path).
 """
 import importlib.abc
@@ -193,5 +195,12 @@ def import_reference():
     import logging
     import porespy as ps  # noqa: the real reference source
     ps.settings.tqdm["disable"] = True
+    # SciPy >= 1.18 returns float64 from rankdata(..., 'dense'); the reference (written against older SciPy,
+    # where dense ranks were integers) feeds the result to np.bincount (filters/_size_seq_satn.py:211-212).
+    # Restore the integer return type of the dependency the reference was written for.
+    import scipy.stats as _st
+    import porespy.filters._size_seq_satn as _sss
+    _sss.rankdata = lambda a, method="average", **k: (
+        _st.rankdata(a, method=method, **k).astype(np.int64) if method == "dense" else _st.rankdata(a, method=method, **k))
     logging.getLogger().handlers.clear()
     return ps

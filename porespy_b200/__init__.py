@@ -10,13 +10,17 @@ from . import _lib
 from . import edt as edt_module
 from . import filters
 from . import generators
+from . import metrics
+from . import sizemap
 from .edt import edt, edtsq
 from .filters import local_thickness, porosimetry, trim_disconnected_blobs
+from .sizemap import IndexMap, local_thickness_index, porosimetry_index
 from .patch import install, uninstall
 from ._device import pinned_empty, to_pinned
 
 __version__ = "0.1.0"
-__all__ = ["edt", "edtsq", "filters", "generators", "local_thickness", "porosimetry",
+__all__ = ["edt", "edtsq", "filters", "generators", "metrics", "sizemap", "IndexMap", "local_thickness_index",
+           "porosimetry_index", "local_thickness", "porosimetry",
            "trim_disconnected_blobs", "install", "uninstall", "build", "pinned_empty", "to_pinned"]
 
 

@@ -15,6 +15,7 @@
 #include "xdist_kernels.cuh"
 #include "bitball_kernels.cuh"
 #include "blobs_kernels.cuh"
+#include "sizemap_kernels.cuh"
 
 // ------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -48,13 +49,13 @@ static int fail(int code, const char *fmt, ...)
 enum KernelId {
     K_EDT_X = 0, K_EDT_Y, K_EDT_Z, K_SQRT, K_MAX, K_CLASSIFY, K_LT_XY, K_LT_X, K_LT_Y, K_LT_Z, K_LT_POINT, K_EXPAND,
     K_MARK_WRITTEN, K_UF_INIT, K_UF_ACTIVATE, K_UF_MARK, K_FLOOD_MISC, K_GEN_X, K_GEN_Y, K_GEN_Z,
-    K_FH_X, K_FH_Y, K_FH_Z, K_LT_PACK, K_LT_BITBALL, K_LT_WMASK, K_EDT_FIX, K_UF_FACE, K_BLOBS, K_COUNT
+    K_FH_X, K_FH_Y, K_FH_Z, K_LT_PACK, K_LT_BITBALL, K_LT_WMASK, K_EDT_FIX, K_UF_FACE, K_BLOBS, K_SIZEMAP, K_COUNT
 };
 static const char *const kKernelNames[K_COUNT] = {
     "edt_x", "edt_y", "edt_z", "sqrt_f32", "max_u32", "lt_classify", "lt_xy", "lt_x", "lt_y", "lt_z", "lt_point",
     "lt_expand", "lt_mark_written", "uf_init", "uf_activate", "uf_mark", "flood_misc",
     "generic_x", "generic_y", "generic_z", "edt_fh_x", "edt_fh_y", "edt_fh_z", "lt_pack", "lt_bitball", "lt_wmask", "edt_fix_inf",
-    "uf_face", "blobs"};
+    "uf_face", "blobs", "sizemap"};
 
 struct ProfScope {
     psb200_ctx *c;
@@ -1531,6 +1532,93 @@ extern "C" int psb200_blobs_finish(psb200_ctx *ctx, const double *f, int64_t n, 
         ProfScope ps__(ctx, st, K_BLOBS);
         blobs_finish_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(f, n, mean, sd, fmin_, fmax_, porosity,
                                                                               out_u8, out_u8 ? nullptr : out_f64);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+// ------------------------------------------------- radius-map post-processing on the index form
+// (sizemap_kernels.cuh; reference filters/_size_seq_satn.py:16-221, metrics/_funcs.py:558-632, 1073-1090)
+extern "C" int psb200_hist_idx(psb200_ctx *ctx, const void *idx, int idx_bytes, const uint8_t *mask, int64_t n, int K,
+                               uint64_t *counts, psb200_stream stream)
+{
+    if (!ctx || !idx || !counts || n < 0 || K < 1 || K > 65536 || (idx_bytes != 1 && idx_bytes != 2) || (idx_bytes == 1 && K > 256))
+        return fail(PSB200_ERR_INVALID, "hist_idx: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(mask ? 2 * K : K) * sizeof(uint64_t), st));
+    if (n == 0) return PSB200_OK;
+    const int g = grid_for(n, 256, ctx->sm_count, 8);
+    {
+        ProfScope ps__(ctx, st, K_SIZEMAP);
+        if (idx_bytes == 1)
+            hist_idx_kernel<uint8_t><<<g, 256, 0, st>>>(reinterpret_cast<const uint8_t *>(idx), mask, n, K,
+                                                      reinterpret_cast<unsigned long long *>(counts));
+        else
+            hist_idx_kernel<uint16_t><<<g, 256, 0, st>>>(reinterpret_cast<const uint16_t *>(idx), mask, n, K,
+                                                       reinterpret_cast<unsigned long long *>(counts));
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_expand_lut8(psb200_ctx *ctx, const void *idx, int idx_bytes, const uint8_t *mask,
+                                  const uint64_t *lut, void *out, int64_t n, int K, psb200_stream stream)
+{
+    if (!ctx || !idx || !lut || !out || n < 0 || K < 1 || K > 65536 || (idx_bytes != 1 && idx_bytes != 2))
+        return fail(PSB200_ERR_INVALID, "expand_lut8: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid_for(n, 256, ctx->sm_count, 16);
+    {
+        ProfScope ps__(ctx, st, K_SIZEMAP);
+        if (idx_bytes == 1)
+            expand_lut8_kernel<uint8_t><<<g, 256, 0, st>>>(reinterpret_cast<const uint8_t *>(idx), mask, lut,
+                                                         reinterpret_cast<uint64_t *>(out), n, K);
+        else
+            expand_lut8_kernel<uint16_t><<<g, 256, 0, st>>>(reinterpret_cast<const uint16_t *>(idx), mask, lut,
+                                                          reinterpret_cast<uint64_t *>(out), n, K);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_distinct64(psb200_ctx *ctx, const uint64_t *x, int64_t n, uint64_t *table, uint32_t cap,
+                                 int *overflow, psb200_stream stream)
+{
+    if (!ctx || !x || !table || !overflow || n < 0 || cap < 2 || (cap & (cap - 1)))
+        return fail(PSB200_ERR_INVALID, "distinct64: bad argument (cap must be a power of two)");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(table, 0xFF, (size_t)cap * sizeof(uint64_t), st));
+    CUDA_TRY(cudaMemsetAsync(overflow, 0, sizeof(int), st));
+    if (n == 0) return PSB200_OK;
+    {
+        ProfScope ps__(ctx, st, K_SIZEMAP);
+        distinct64_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, st>>>(
+            x, n, reinterpret_cast<unsigned long long *>(table), cap, overflow);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_index_of64(psb200_ctx *ctx, const uint64_t *x, int64_t n, const uint64_t *keys, int K, int kind,
+                                 void *idx, int idx_bytes, psb200_stream stream)
+{
+    if (!ctx || !x || !keys || !idx || n < 0 || K < 1 || K > 65536 || (kind != 0 && kind != 1) ||
+        (idx_bytes != 1 && idx_bytes != 2) || (idx_bytes == 1 && K > 256))
+        return fail(PSB200_ERR_INVALID, "index_of64: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid_for(n, 256, ctx->sm_count, 16);
+    {
+        ProfScope ps__(ctx, st, K_SIZEMAP);
+        if (idx_bytes == 1 && kind == 0) index_of_kernel<uint8_t, 0><<<g, 256, 0, st>>>(x, n, keys, K, reinterpret_cast<uint8_t *>(idx));
+        else if (idx_bytes == 1) index_of_kernel<uint8_t, 1><<<g, 256, 0, st>>>(x, n, keys, K, reinterpret_cast<uint8_t *>(idx));
+        else if (kind == 0) index_of_kernel<uint16_t, 0><<<g, 256, 0, st>>>(x, n, keys, K, reinterpret_cast<uint16_t *>(idx));
+        else index_of_kernel<uint16_t, 1><<<g, 256, 0, st>>>(x, n, keys, K, reinterpret_cast<uint16_t *>(idx));
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;

@@ -21,7 +21,8 @@ from . import _lib
 logger = logging.getLogger(__name__)
 
 __all__ = ["porosimetry", "local_thickness", "trim_disconnected_blobs", "find_disconnected_voxels",
-           "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths", "find_trapped_regions"]
+           "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths", "find_trapped_regions",
+           "size_to_seq", "size_to_satn", "seq_to_satn"]
 
 
 def _result_for_no_background(shape, radii):
@@ -36,13 +37,20 @@ def _result_for_no_background(shape, radii):
     return out
 
 
-def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True):
-    """Device loop over the effective thresholds (in groups of <= 253) -> float64 radius map."""
+def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True, as_index=False):
+    """Device loop over the effective thresholds (in groups of <= 253) -> float64 radius map, or with
+    `as_index` the map in index form (sizemap.IndexMap: index byte per voxel + radius table)."""
     torch = dev._torch()
     n = int(np.prod(shape))
     idx = torch.empty(n, dtype=torch.uint8, device=d2.device)
     G = _lib.MAX_THRESHOLDS
     ngroups = max(1, -(-len(T) // G))
+    if as_index:
+        from .sizemap import IndexMap
+        if ngroups == 1:
+            dev.local_thickness_idx(ctx, d2, T, idx, inlets_u8, inlet_mode, ndim, shape, 0)
+            return IndexMap(ctx, idx, np.concatenate([[0.0], R]), shape)
+        return IndexMap.from_array(_run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=False), ctx)
     if ngroups == 1 and as_numpy:
         # common case: the float64 map (F:1178) is only materialised on the host
         dev.local_thickness_idx(ctx, d2, T, idx, inlets_u8, inlet_mode, ndim, shape, 0)
@@ -65,7 +73,7 @@ def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True):
 
 
 def porosimetry(im, sizes: int = 25, inlets=None, access_limited: bool = True,
-                mode: str = "hybrid", divs=1):
+                mode: str = "hybrid", divs=1, _as_index=False):
     r"""Porosimetry simulation (sphere insertion from the inlets); see the reference docstring
     (F:1040-1122) for the meaning of every argument -- they are unchanged.
 
@@ -87,6 +95,7 @@ def porosimetry(im, sizes: int = 25, inlets=None, access_limited: bool = True,
     if ndim == 0 or int(np.prod(shape)) == 0:
         return np.zeros(shape)
     ctx = _lib.context()
+    as_index = _as_index
     im_u8 = dev.to_device_u8(im, ctx, positive=True)          # F:1126 edt(im > 0)
     d2, max_d2 = dev.edt_run(ctx, im_u8, shape, want_max=True)    # max fused into the last pass
     del im_u8
@@ -108,9 +117,12 @@ def porosimetry(im, sizes: int = 25, inlets=None, access_limited: bool = True,
 
     if max_d2 == host.INF_U32:
         res = _result_for_no_background(shape, radii)
+        if as_index:
+            from .sizemap import IndexMap
+            return IndexMap.from_array(res, ctx)
         return res if as_numpy else torch.from_numpy(res).to(d2.device)
     T, R = host.effective_thresholds(radii, max_d2)
-    return _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=as_numpy)
+    return _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=as_numpy, as_index=as_index)
 
 
 def local_thickness(im, sizes: int = 25, mode: str = "hybrid", divs: int = 1):
@@ -322,3 +334,7 @@ def find_trapped_regions(seq, outlets=None, bins: int = 25, return_mask: bool = 
         return trapped
     seq[trapped] = -1
     return host.make_contiguous_symmetric(seq)
+
+
+# radius-map post-processing (filters/_size_seq_satn.py:16-221), evaluated on the index form of the map
+from .sizemap import seq_to_satn, size_to_satn, size_to_seq  # noqa: E402,F401

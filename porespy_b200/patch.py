@@ -11,7 +11,8 @@ import types
 _saved = {}
 
 _FILTERS = ("porosimetry", "local_thickness", "trim_disconnected_blobs", "find_disconnected_voxels",
-            "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths", "find_trapped_regions")
+            "fill_blind_pores", "trim_floating_solid", "trim_nonpercolating_paths", "find_trapped_regions",
+            "size_to_seq", "size_to_satn", "seq_to_satn")
 
 
 def install(patch_edt_module=True):
@@ -32,10 +33,16 @@ def install(patch_edt_module=True):
     if ps is not None and "porespy" not in _saved:
         saved = _saved["porespy"] = {}
         for name in _FILTERS:
-            for mod in (getattr(ps, "filters", None), sys.modules.get("porespy.filters._funcs")):
+            for mod in (getattr(ps, "filters", None), sys.modules.get("porespy.filters._funcs"),
+                        sys.modules.get("porespy.filters._size_seq_satn")):
                 if mod is not None and hasattr(mod, name):
                     saved[(mod, name)] = getattr(mod, name)
                     setattr(mod, name, getattr(f, name))
+        from . import metrics as m
+        for mod in (getattr(ps, "metrics", None), sys.modules.get("porespy.metrics._funcs")):
+            if mod is not None and hasattr(mod, "pore_size_distribution"):
+                saved[(mod, "pore_size_distribution")] = mod.pore_size_distribution
+                mod.pore_size_distribution = m.pore_size_distribution
         old_edt = _saved.get("edt")
         originals = {getattr(old_edt, "edt", None)} - {None}
         for modname, mod in list(sys.modules.items()):

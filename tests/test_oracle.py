@@ -224,3 +224,33 @@ def test_c_loop_golden(golden):
     inlets = np.zeros_like(im)
     inlets[0, ...] = True
     assert np.array_equal(oc.porosimetry_c(im, sizes=12, inlets=inlets), g.rmap("poro_inlet0_dt_12"))
+
+
+def test_sizemap_restatements_match_reference_goldens(golden):
+    """oracle.cpu size_to_seq / size_to_satn / seq_to_satn / pore_size_distribution / pc_curve_sizes against the
+    reference's own outputs (tests/golden/make_golden_sizemap.py)."""
+    g, b = golden.sizemap, golden.blobs100
+    im, lt, mip = b.mask("im"), b.rmap("lt_dt_25"), b.rmap("poro_inlet0_dt_12")
+    assert np.array_equal(oc.size_to_satn(lt), g.rmap("lt_satn_dr"))
+    assert np.array_equal(oc.size_to_satn(lt, mode="imbibition"), g.rmap("lt_satn_im"))
+    assert np.array_equal(oc.size_to_satn(lt, bins=12), g.rmap("lt_satn_bins12"))
+    assert np.array_equal(oc.size_to_satn(mip, im=im), g.rmap("mip_satn_im_mask"))
+    assert np.array_equal(oc.size_to_seq(lt), g.rmap("lt_seq_dr"))
+    assert np.array_equal(oc.size_to_seq(lt, mode="imbibition"), g.rmap("lt_seq_im"))
+    assert np.array_equal(oc.size_to_seq(mip, im=im), g.rmap("mip_seq_mask"))
+    assert np.array_equal(oc.size_to_seq(lt, bins=10), g.rmap("lt_seq_bins10"))
+    seq = g.rmap("lt_seq_dr")
+    assert np.array_equal(oc.seq_to_satn(seq), g.rmap("seq_satn_dr"))
+    assert np.array_equal(oc.seq_to_satn(seq, mode="imbibition"), g.rmap("seq_satn_im"))
+    assert np.array_equal(oc.seq_to_satn(g.rmap("mseq"), im=im), g.rmap("mseq_satn_mask"))
+    for name, kw in (("psd_default", {}), ("psd_lin20", dict(bins=20, log=False))):
+        r = oc.pore_size_distribution(lt, **kw)
+        for f in ("pdf", "cdf", "satn", "bin_centers", "bin_edges", "bin_widths"):
+            assert np.array_equal(r[f], g.raw(f"{name}__{f}")), (name, f)
+    x, y = oc.pc_curve_sizes(im, lt, voxel_size=1e-5)
+    assert np.array_equal(x, g.raw("pc_lt__pc")) and np.array_equal(y, g.raw("pc_lt__snwp"))
+    small = g.raw("small")
+    assert np.array_equal(oc.size_to_satn(small), g.raw("small_satn"))
+    assert np.array_equal(oc.size_to_seq(small), g.raw("small_seq"))
+    assert np.array_equal(oc.size_to_seq(small, mode="imbibition"), g.raw("small_seq_im"))
+    assert np.array_equal(oc.seq_to_satn(g.raw("small_seq")), g.raw("small_seq_satn"))
