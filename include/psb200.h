@@ -288,8 +288,8 @@ int psb200_blobs_finish(psb200_ctx *ctx, const double *f, int64_t n, double mean
  *   psb200_expand_lut8 : out[i] = lut[(mask && mask[i] ? K : 0) + idx[i]], 8-byte payloads (float64 / int64);
  *                        lut: device, K or 2K entries.
  *   psb200_distinct64  : distinct 8-byte patterns of x[0,n) into an open-addressing table of `cap` (power of
- *                        two) device uint64 (empty slots = all ones; the call initialises it); *overflow = 1 when
- *                        the table is too small.
+ *                        two) device uint64 (empty slots = 0x8000000000000000, i.e. -0.0 / INT64_MIN, which the
+ *                        input must not hold; the call initialises the table); *overflow = 1 when it is too small.
  *   psb200_index_of64  : idx[i] = position of x[i] in the sorted keys[0,K) (kind 0: float64 order, 1: int64). */
 int psb200_hist_idx(psb200_ctx *ctx, const void *idx, int idx_bytes, const uint8_t *mask, int64_t n, int K,
                     uint64_t *counts, psb200_stream stream);
@@ -299,6 +299,35 @@ int psb200_distinct64(psb200_ctx *ctx, const uint64_t *x, int64_t n, uint64_t *t
                       psb200_stream stream);
 int psb200_index_of64(psb200_ctx *ctx, const uint64_t *x, int64_t n, const uint64_t *keys, int K, int kind,
                       void *idx, int idx_bytes, psb200_stream stream);
+
+/* ---- image-based drainage: the pressure loop of simulations/_drainage.py:104-154 and the
+ * sphere painter tools/_sphere_insertions.py:327-385.  fn = pc + rho g h is evaluated per voxel in the
+ * reference's own precisions from dt (float32 EDT of im), or from a caller-supplied float64 pc map:
+ * c0 = -(ndim-1) sigma cos(theta), rho_g = delta_rho * g, inner = voxels per step of the first image axis (the
+ * direction of gravity), prec_flags bit 0/1/2: dt*voxel_size / h / rgh are float64 products (numpy scalars) instead
+ * of float32 ones (python scalars).
+ *   psb200_drain_stats     : partials[2b] = max{fn < inf}, partials[2b+1] = min{fn > -inf over im} per block b
+ *                            (F:122-123); partials: device doubles, 2 * nblocks.
+ *   psb200_drain_threshold : temp = (fn <= p) * im [+ residual]  (F:137-140), uint8 0/1.
+ *   psb200_drain_newly     : rad = int(dt) at the voxels of reached [* mask] that are not in seeds yet, 0 elsewhere;
+ *                            seeds |= reached [* mask]; *count_dev = how many, *maxr_dev = largest radius (F:142-152).
+ *   psb200_drain_paint     : inv[v] = val wherever a sphere {|o|^2 < rad(s)^2} of a voxel s with rad(s) > 0 covers v
+ *                            and inv[v] == 0 (power-diagram min-plus passes; ws: psb200_drain_paint_workspace_bytes).
+ *   psb200_set_where_u8 / psb200_set_zero_codes_u8 : code-map bookkeeping of the epilogue (F:157-161). */
+int psb200_drain_stats(psb200_ctx *ctx, const float *dt, const uint8_t *im, const double *pc_user, int64_t n,
+                       int64_t inner, double c0, double voxel_size, double rho_g, int prec_flags, double *partials,
+                       int nblocks, psb200_stream stream);
+int psb200_drain_threshold(psb200_ctx *ctx, const float *dt, const uint8_t *im, const double *pc_user,
+                           const uint8_t *residual, int64_t n, int64_t inner, double c0, double voxel_size,
+                           double rho_g, int prec_flags, double p, uint8_t *temp, psb200_stream stream);
+int psb200_drain_newly(psb200_ctx *ctx, const uint8_t *reached, const uint8_t *mask, uint8_t *seeds, const float *dt,
+                       uint16_t *rad, int64_t n, uint64_t *count_dev, int *maxr_dev, psb200_stream stream);
+size_t psb200_drain_paint_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx);
+int psb200_drain_paint(psb200_ctx *ctx, const uint16_t *rad, int rmax, uint8_t *inv, int val, int64_t nz, int64_t ny,
+                       int64_t nx, void *ws, size_t ws_bytes, psb200_stream stream);
+int psb200_set_where_u8(psb200_ctx *ctx, uint8_t *dst, const uint8_t *mask, int value, int64_t n, psb200_stream stream);
+int psb200_set_zero_codes_u8(psb200_ctx *ctx, uint8_t *codes, const uint8_t *im, const uint8_t *zero_lut_dev, int value,
+                             int64_t n, psb200_stream stream);
 
 #ifdef __cplusplus
 }

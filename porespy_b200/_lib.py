@@ -101,6 +101,14 @@ SIGNATURES = {
     "psb200_expand_lut8": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "psb200_distinct64": (_i32, [_vp, _vp, _i64, _vp, _u32, _vp, _vp]),
     "psb200_index_of64": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp]),
+    "psb200_drain_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _c.c_double, _c.c_double, _c.c_double, _i32, _vp, _i32, _vp]),
+    "psb200_drain_threshold": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _c.c_double, _c.c_double, _c.c_double, _i32,
+                                      _c.c_double, _vp, _vp]),
+    "psb200_drain_newly": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "psb200_drain_paint_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
+    "psb200_drain_paint": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "psb200_set_where_u8": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp]),
+    "psb200_set_zero_codes_u8": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "psb200_flood": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
 }
 
@@ -165,6 +173,10 @@ class Context:
         """Warp footprint of the 16-bit min-plus scans (EDT y/z passes, per-radius y pass): 0 = 64 columns x
         8 rows, 1 = 32 x 16."""
         check(self.lib.psb200_set_option(self.handle, b"foot", int(foot)))
+
+    def set_ycoarse(self, on):
+        """Per-radius y pass: hierarchical scan that skips row groups by their minima (default) / plain scan."""
+        check(self.lib.psb200_set_option(self.handle, b"ycoarse", 1 if on else 0))
 
     def set_profile(self, on):
         check(self.lib.psb200_set_option(self.handle, b"profile", 1 if on else 0))

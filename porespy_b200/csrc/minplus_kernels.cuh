@@ -444,19 +444,20 @@ edt_fix_inf_kernel(uint32_t *__restrict__ d2, int64_t n, uint32_t *__restrict__ 
 }
 
 // --------------------------------------------------------------- per-radius y pass (uint16x2)
-// gx: x-distance bytes min(d, W + 1) from xdist_kernel<XD_LT>, 255 (GX_BG) at background voxels.  reach byte
+// gx: x-distance bytes min(d, W + 1) from xdist_kernel<XD_LT>.  reach byte
 //   m = #{dz >= 0 : h + dz^2 < T} = ceil(sqrt(T - h))  where h = min_y' gx(y')^2 + (y - y')^2,
 // 0 where h >= T.  Needs T <= 32767 (W <= 181).
-// Background voxels are never filled (a seed's open ball holds no background voxel), so their h is
-// irrelevant: they enter the tile as T + 1 (a "far" source for their neighbours), start with best = 0
-// so that they never prolong the scan of their 4 x 4 block, and leave with m = 0.  Blocks that hold
-// background voxels are the ones next to the solid, i.e. the ones that used to scan the full +/- W.
+// Measured and NOT adopted (r2b): letting background voxels (never filled: a seed's open ball holds no
+// background voxel) start with best = 0 so that they do not prolong the scan of their 4 x 4 block.  It
+// removes 40 % of the per-BLOCK scan steps, but a warp scans until the last of its 32 blocks is done, and
+// nearly every 64 x 8 patch holds an unreachable pore voxel: lt_y 2.49 -> 2.79 ms at T = 344 (the marking
+// of background voxels in the x pass cost another 0.08 ms per radius).
 // grid = (ceil(nx/128), ceil(ny/Ly), nz), block 256, dyn smem: see lt_y2_smem_bytes().
 // Tile rows are MP_TS uint2 apart (272 bytes): rows 4 apart then start 64 bytes apart modulo 128, so the
 // 32 x 16 warp footprint (FOOT 1: 8 column groups x 4 row blocks) is as conflict-free as the 64 x 8 one.
 __device__ __forceinline__ uint32_t sq_cap2(uint32_t a, uint32_t b, uint32_t W, uint32_t T)
-{   // two x-distances -> packed capped squares (far: T, background: T + 1)
-    const uint32_t sa = a > W ? (a == GX_BG ? T + 1u : T) : a * a, sb = b > W ? (b == GX_BG ? T + 1u : T) : b * b;
+{   // two x-distances -> packed capped squares
+    const uint32_t sa = a > W ? T : a * a, sb = b > W ? T : b * b;
     return sa | (sb << 16);
 }
 
@@ -488,7 +489,7 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
     if (tid == 0) { range[0] = rows; range[1] = -1; }
     if (use_lut)
         for (uint32_t h = tid; h <= T; h += 256) lut[h] = h >= T ? 0 : (uint8_t)ceil_sqrt_small(T - h);
-    // offsets are capped at T so that value + offset <= 2T + 1 stays inside 16 bits
+    // offsets are capped at T so that value + offset <= 2T stays inside 16 bits
     for (int d = tid; d < W + 2; d += 256) {
         uint32_t o[4];
 #pragma unroll
@@ -540,7 +541,7 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
     // rows fetched at step dy serve all 4 outputs.  Warp footprint 64 columns x 8 rows (FOOT 0: 16 column
     // groups x 2 row blocks) or 32 x 16 (FOOT 1: 8 x 4, compacter: the lanes of a warp end their scans closer
     // to each other); a half-warp reads 128 bytes without bank conflicts either way.
-    const uint32_t T2 = T * 0x00010001u, BG2 = (T + 1u) * 0x00010001u;
+    const uint32_t T2 = T * 0x00010001u;
     const int cq = FOOT ? (warp & 3) * 8 + (lane & 7) : (warp & 1) * 16 + (lane & 15);     // uint2 index inside the tile row
     const int ry0 = FOOT ? ((warp >> 2) * 4 + (lane >> 3)) * 4 : ((warp >> 1) * 2 + (lane >> 4)) * 4;
     for (int ry = ry0; ry < Ly; ry += 32) {
@@ -555,15 +556,13 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
                 for (int j = 0; j < 4; ++j) m[i][j] = 0;
         } else {
             uint2 O[4];
-            uint32_t B0[4], B1[4], G0[4], G1[4];
+            uint32_t B0[4], B1[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) O[i] = tile[(rr + i) * MP_TS + cq];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                G0[i] = __vcmpeq2(O[i].x, BG2);                   // 0xFFFF per background voxel
-                G1[i] = __vcmpeq2(O[i].y, BG2);
-                B0[i] = __vminu2(O[i].x, T2) & ~G0[i];            // background: nothing to find
-                B1[i] = __vminu2(O[i].y, T2) & ~G1[i];
+                B0[i] = __vminu2(O[i].x, T2);
+                B1[i] = __vminu2(O[i].y, T2);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (j != i) {
@@ -597,9 +596,7 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                // background voxels leave with h = T (m = 0)
-                const uint32_t b0 = B0[i] | (G0[i] & T2), b1 = B1[i] | (G1[i] & T2);
-                const uint32_t h[4] = {b0 & 0xFFFFu, b0 >> 16, b1 & 0xFFFFu, b1 >> 16};
+                const uint32_t h[4] = {B0[i] & 0xFFFFu, B0[i] >> 16, B1[i] & 0xFFFFu, B1[i] >> 16};
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     m[i][j] = use_lut ? (uint32_t)lut[min(h[j], T)] : (h[j] >= T ? 0u : ceil_sqrt_small(T - h[j]));
@@ -608,6 +605,180 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             if (ry + i < Ly) sout[(ry + i) * 32 + cq] = pack4(m[i][0], m[i][1], m[i][2], m[i][3]);
+    }
+    __syncthreads();
+    // ---- coalesced write-out of the reach tile (16 bytes per thread)
+    for (int i = tid; i < Ly * 8; i += 256) {
+        const int r = i >> 3, ch = i & 7;
+        const int y = y0 + r, x = x0 + 16 * ch;
+        if (y < ny && x < nx)
+            *reinterpret_cast<uint4 *>(reach + (zoff + y) * nx + x) = reinterpret_cast<const uint4 *>(sout)[i];
+    }
+}
+
+// ------------------------------------------- per-radius y pass, hierarchical scan (the default)
+// Same tile, same result as lt_y2_kernel.  What bounds lt_y2 is not the scan of the voxels that find a seed
+// (it ends after about sqrt(h) steps) but the voxels that find none: they walk all W rows, nearly every
+// 64 x 8 warp patch holds one, and a warp is as slow as its slowest lane.  Here the tile also carries, for
+// every aligned group of 4 rows and every 4-column group, the minimum of its 16 values (`cm`); the steps
+// dy = 4g-3 .. 4g of a block read exactly the row groups g above and below it, so
+//       min(cm_above, cm_below) + (4g - 3)^2  >=  max(best of the block)
+// proves that those four steps cannot change anything and they are skipped (two 2-byte loads and a compare
+// instead of 8 row loads and 64 VIADDMNMX).  The decision is taken per warp (`__any_sync`), so there is no
+// divergence: a group is scanned by all lanes as soon as one lane needs it, which is harmless (a relaxation
+// with a valid candidate never hurts).  Halo = W rounded up to a multiple of 4 rows so that groups align.
+static inline size_t lt_y3_smem_bytes(int Ly, int W, uint32_t T)
+{
+    const int Hh = (W + 3) & ~3, rows = ((Ly + 3) & ~3) + 2 * Hh;
+    return (size_t)rows * MP_TS * 8 + (size_t)rows * 16 + 16 + (size_t)(Hh + 6) * 16 + (size_t)Ly * 128 +
+           (T <= LTY_LUT_MAX ? ((T + 16) & ~15u) : 0);
+}
+
+__global__ void __launch_bounds__(256)
+lt_y3_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny, int nx, uint32_t T,
+             int W, int Ly, const int *__restrict__ gate)
+{
+    if (gate && *gate == 0) return;
+    extern __shared__ uint4 lty3_smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
+    const int Hh = (W + 3) & ~3;                                  // halo rows: whole groups of 4
+    const int rows = ((Ly + 3) & ~3) + 2 * Hh, ngroups = rows >> 2;
+    uint2 *tile = reinterpret_cast<uint2 *>(lty3_smem);          // [rows][MP_TS] : 4 x u16 per entry
+    uint16_t *cm = reinterpret_cast<uint16_t *>(tile + (size_t)rows * MP_TS);   // [rows / 4][32] group minima
+    int *range = reinterpret_cast<int *>(cm + (size_t)ngroups * 32);            // [0] first useful row, [1] last
+    uint4 *offt = reinterpret_cast<uint4 *>(range + 4);          // [Hh + 6]: packed capped squares of d .. d+3
+    uint32_t *sout = reinterpret_cast<uint32_t *>(offt + (Hh + 6));             // [Ly][32] reach bytes of the tile
+    uint8_t *lut = reinterpret_cast<uint8_t *>(sout + (size_t)Ly * 32);
+    const bool use_lut = T <= LTY_LUT_MAX;
+    const int x0 = blockIdx.x * MP_TX, y0 = blockIdx.y * Ly;
+    const int64_t zoff = (int64_t)blockIdx.z * ny;
+    if (tid == 0) { range[0] = rows; range[1] = -1; }
+    if (use_lut)
+        for (uint32_t h = tid; h <= T; h += 256) lut[h] = h >= T ? 0 : (uint8_t)ceil_sqrt_small(T - h);
+    for (int d = tid; d < Hh + 6; d += 256) {
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = min((uint32_t)((d + i) * (d + i)), T) * 0x00010001u;
+        offt[d] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+
+    // ---- stage: thread = 16 voxels of one row (8 threads per row, 32 rows per sweep)
+    const uint32_t uW = (uint32_t)W;
+    int lo = rows, hi = -1;
+    for (int i0 = 0; i0 < rows * 8; i0 += 4 * 256) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 256 + tid, r = i >> 3, ch = i & 7;
+            const int y = y0 - Hh + r, x = x0 + 16 * ch;
+            v[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            if (r < rows && y >= 0 && y < ny && x < nx)
+                v[u] = __ldg(reinterpret_cast<const uint4 *>(gx + (zoff + y) * nx + x));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 256 + tid, r = i >> 3, ch = i & 7;
+            if (r >= rows) continue;
+            const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            uint32_t s[8];
+            bool useful = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t a = byte_of(w4[q], 0), b = byte_of(w4[q], 1), c = byte_of(w4[q], 2), d = byte_of(w4[q], 3);
+                useful |= (a <= uW) | (b <= uW) | (c <= uW) | (d <= uW);
+                s[2 * q] = sq_cap2(a, b, uW, T);
+                s[2 * q + 1] = sq_cap2(c, d, uW, T);
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(tile + (size_t)r * MP_TS + 4 * ch);
+            dst[0] = make_uint4(s[0], s[1], s[2], s[3]);
+            dst[1] = make_uint4(s[4], s[5], s[6], s[7]);
+            if (useful) { lo = min(lo, r); hi = max(hi, r); }
+        }
+    }
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if (lane == 0 && hi >= 0) { atomicMin(&range[0], lo); atomicMax(&range[1], hi); }
+    __syncthreads();
+    const int rlo = range[0], rhi = range[1];
+    // ---- group minima (skipped when the tile holds no seed at all: every output is 0 then)
+    if (rhi >= 0)
+        for (int i = tid; i < ngroups * 32; i += 256) {
+            const int q = i >> 5, c = i & 31;
+            const uint2 a = tile[(4 * q) * MP_TS + c], b = tile[(4 * q + 1) * MP_TS + c];
+            const uint2 e = tile[(4 * q + 2) * MP_TS + c], f = tile[(4 * q + 3) * MP_TS + c];
+            const uint32_t m2 = __vminu2(__vminu2(__vminu2(a.x, a.y), __vminu2(b.x, b.y)),
+                                         __vminu2(__vminu2(e.x, e.y), __vminu2(f.x, f.y)));
+            cm[i] = (uint16_t)min(m2 & 0xFFFFu, m2 >> 16);
+        }
+    __syncthreads();
+
+    // ---- scan: a lane owns 4 rows x 4 columns, warp footprint 64 columns x 8 rows (as lt_y2_kernel)
+    const uint32_t T2 = T * 0x00010001u;
+    const int cq = (warp & 1) * 16 + (lane & 15);
+    const int ry0 = ((warp >> 1) * 2 + (lane >> 4)) * 4;
+    const int iters = (Ly + 31) >> 5;                            // the same for every lane: the loop holds warp votes
+    for (int t = 0; t < iters; ++t) {
+        const int ry = ry0 + 32 * t;
+        const bool valid = ry < Ly && y0 + ry < ny;
+        const int rr = min(ry, ((Ly + 3) & ~3) - 4) + Hh;        // (lanes past the end scan a valid block, unused)
+        const int qb = rr >> 2;
+        const bool reachable = valid && rhi >= 0 && !(rr + 3 + W < rlo || rr - W > rhi);
+        uint2 O[4];
+        uint32_t B0[4], B1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) O[i] = tile[(rr + i) * MP_TS + cq];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            B0[i] = __vminu2(O[i].x, T2);
+            B1[i] = __vminu2(O[i].y, T2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j != i) {
+                    const uint32_t d = (uint32_t)((i - j) * (i - j)) * 0x00010001u;
+                    B0[i] = __viaddmin_u16x2(O[j].x, d, B0[i]);
+                    B1[i] = __viaddmin_u16x2(O[j].y, d, B1[i]);
+                }
+        }
+        // rows outside [rlo, rhi] hold nothing below T: clip the scan
+        const int dmax = reachable ? min(W, max(rr + 3 - rlo, rhi - rr)) : 0;
+        uint32_t m2 = __vmaxu2(__vmaxu2(__vmaxu2(B0[0], B1[0]), __vmaxu2(B0[1], B1[1])),
+                               __vmaxu2(__vmaxu2(B0[2], B1[2]), __vmaxu2(B0[3], B1[3])));
+        uint32_t bm = max(m2 & 0xFFFFu, m2 >> 16);
+        for (int g = 1; 4 * g <= Hh; ++g) {
+            const int dlo = 4 * g - 3;
+            const bool active = dlo <= dmax && (uint32_t)(dlo * dlo) < bm;
+            if (!__any_sync(0xFFFFFFFFu, active)) break;
+            const uint32_t cu = cm[(qb - g) * 32 + cq], cd = cm[(qb + g) * 32 + cq];
+            const bool need = active && min(cu, cd) + (uint32_t)(dlo * dlo) < bm;
+            if (!__any_sync(0xFFFFFFFFu, need)) continue;
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const int d = dlo + s4;
+                const uint2 top = tile[(rr - d) * MP_TS + cq];
+                const uint2 bot = tile[(rr + 3 + d) * MP_TS + cq];
+                const uint4 o4 = offt[d];                          // capped (d + i)^2, i = 0..3, both halves
+                const uint32_t of[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    B0[i] = __viaddmin_u16x2(top.x, of[i], B0[i]); B1[i] = __viaddmin_u16x2(top.y, of[i], B1[i]);
+                    B0[i] = __viaddmin_u16x2(bot.x, of[3 - i], B0[i]); B1[i] = __viaddmin_u16x2(bot.y, of[3 - i], B1[i]);
+                }
+            }
+            m2 = __vmaxu2(__vmaxu2(__vmaxu2(B0[0], B1[0]), __vmaxu2(B0[1], B1[1])),
+                          __vmaxu2(__vmaxu2(B0[2], B1[2]), __vmaxu2(B0[3], B1[3])));
+            bm = max(m2 & 0xFFFFu, m2 >> 16);
+        }
+        if (!valid) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t m[4];
+            const uint32_t h[4] = {B0[i] & 0xFFFFu, B0[i] >> 16, B1[i] & 0xFFFFu, B1[i] >> 16};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                m[j] = !reachable ? 0u : (use_lut ? (uint32_t)lut[min(h[j], T)] : (h[j] >= T ? 0u : ceil_sqrt_small(T - h[j])));
+            if (ry + i < Ly) sout[(ry + i) * 32 + cq] = pack4(m[0], m[1], m[2], m[3]);
+        }
     }
     __syncthreads();
     // ---- coalesced write-out of the reach tile (16 bytes per thread)

@@ -16,6 +16,7 @@
 #include "bitball_kernels.cuh"
 #include "blobs_kernels.cuh"
 #include "sizemap_kernels.cuh"
+#include "drainage_kernels.cuh"
 
 // ------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -49,13 +50,13 @@ static int fail(int code, const char *fmt, ...)
 enum KernelId {
     K_EDT_X = 0, K_EDT_Y, K_EDT_Z, K_SQRT, K_MAX, K_CLASSIFY, K_LT_XY, K_LT_X, K_LT_Y, K_LT_Z, K_LT_POINT, K_EXPAND,
     K_MARK_WRITTEN, K_UF_INIT, K_UF_ACTIVATE, K_UF_MARK, K_FLOOD_MISC, K_GEN_X, K_GEN_Y, K_GEN_Z,
-    K_FH_X, K_FH_Y, K_FH_Z, K_LT_PACK, K_LT_BITBALL, K_LT_WMASK, K_EDT_FIX, K_UF_FACE, K_BLOBS, K_SIZEMAP, K_COUNT
+    K_FH_X, K_FH_Y, K_FH_Z, K_LT_PACK, K_LT_BITBALL, K_LT_WMASK, K_EDT_FIX, K_UF_FACE, K_BLOBS, K_SIZEMAP, K_DRAIN, K_COUNT
 };
 static const char *const kKernelNames[K_COUNT] = {
     "edt_x", "edt_y", "edt_z", "sqrt_f32", "max_u32", "lt_classify", "lt_xy", "lt_x", "lt_y", "lt_z", "lt_point",
     "lt_expand", "lt_mark_written", "uf_init", "uf_activate", "uf_mark", "flood_misc",
     "generic_x", "generic_y", "generic_z", "edt_fh_x", "edt_fh_y", "edt_fh_z", "lt_pack", "lt_bitball", "lt_wmask", "edt_fix_inf",
-    "uf_face", "blobs", "sizemap"};
+    "uf_face", "blobs", "sizemap", "drainage"};
 
 struct ProfScope {
     psb200_ctx *c;
@@ -95,7 +96,8 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->bit_tmax = 200;
     c->edt16 = 1;
     c->bit4 = 1;
-    c->foot = 0;
+    c->foot = 1;
+    c->ycoarse = 1;
     c->flag_slot = 0;
     CUDA_TRY(cudaMalloc(&c->flags, 64 * sizeof(int)));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -103,6 +105,7 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     CUDA_TRY(cudaFuncSetAttribute(lt_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(lt_y2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(lt_y2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(lt_y3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(xdist_kernel<XD_EDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(xdist_kernel<XD_LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(edt_minplus_kernel<MpSrcU16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
@@ -149,6 +152,10 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
     }
     if (!strcmp(name, "bit4")) {
         ctx->bit4 = value ? 1 : 0;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "ycoarse")) {
+        ctx->ycoarse = value ? 1 : 0;
         return PSB200_OK;
     }
     if (!strcmp(name, "foot")) {
@@ -734,13 +741,15 @@ static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_
     if (rc) return rc;
     {   // y pass
         int Ly = ny < 128 ? (int)ny : 128;
-        const size_t smem = lt_y2_smem_bytes(Ly, W, T);
+        const bool coarse = ctx->ycoarse && (int)lt_y3_smem_bytes(Ly, W, T) <= ctx->max_smem_optin;
+        const size_t smem = coarse ? lt_y3_smem_bytes(Ly, W, T) : lt_y2_smem_bytes(Ly, W, T);
         if ((int)smem > ctx->max_smem_optin)
             return fail(PSB200_ERR_UNSUPPORTED, "lt_y: tile needs %zu bytes of shared memory", smem);
         dim3 grid((unsigned)((nx + MP_TX - 1) / MP_TX), (unsigned)((ny + Ly - 1) / Ly), (unsigned)nz);
         {
             ProfScope ps__(ctx, st, K_LT_Y);
-            if (ctx->foot) lt_y2_kernel<1><<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate);
+            // (the 32 x 16 warp footprint that helps the EDT passes is 1 % slower here: r2b)
+            if (coarse) lt_y3_kernel<<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate);
             else lt_y2_kernel<0><<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate);
         }
         LAUNCH_CHECK(ctx);
@@ -1591,7 +1600,9 @@ extern "C" int psb200_distinct64(psb200_ctx *ctx, const uint64_t *x, int64_t n, 
         return fail(PSB200_ERR_INVALID, "distinct64: bad argument (cap must be a power of two)");
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaMemsetAsync(table, 0xFF, (size_t)cap * sizeof(uint64_t), st));
+    fill_u64_kernel<<<grid_for(cap, 256, ctx->sm_count, 4), 256, 0, st>>>(reinterpret_cast<unsigned long long *>(table), cap,
+                                                                         DISTINCT_EMPTY);
+    LAUNCH_CHECK(ctx);
     CUDA_TRY(cudaMemsetAsync(overflow, 0, sizeof(int), st));
     if (n == 0) return PSB200_OK;
     {
@@ -1619,6 +1630,149 @@ extern "C" int psb200_index_of64(psb200_ctx *ctx, const uint64_t *x, int64_t n, 
         else if (idx_bytes == 1) index_of_kernel<uint8_t, 1><<<g, 256, 0, st>>>(x, n, keys, K, reinterpret_cast<uint8_t *>(idx));
         else if (kind == 0) index_of_kernel<uint16_t, 0><<<g, 256, 0, st>>>(x, n, keys, K, reinterpret_cast<uint16_t *>(idx));
         else index_of_kernel<uint16_t, 1><<<g, 256, 0, st>>>(x, n, keys, K, reinterpret_cast<uint16_t *>(idx));
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+// ------------------------------------------------------------------------------ drainage
+// (drainage_kernels.cuh; reference simulations/_drainage.py:104-154, tools/_sphere_insertions.py:327-385)
+static DrainFn make_drain_fn(double c0, double voxel_size, double rho_g, int prec_flags, int64_t inner, bool use_pc)
+{
+    DrainFn q;
+    q.c0 = c0; q.vs64 = voxel_size; q.vs32 = (float)voxel_size; q.rg64 = rho_g; q.rg32 = (float)rho_g;
+    q.den64 = (prec_flags & 1) ? 1 : 0; q.h64 = (prec_flags & 2) ? 1 : 0; q.rgh64 = (prec_flags & 4) ? 1 : 0;
+    q.use_pc = use_pc ? 1 : 0; q.inner = inner;
+    return q;
+}
+
+extern "C" int psb200_drain_stats(psb200_ctx *ctx, const float *dt, const uint8_t *im, const double *pc_user, int64_t n,
+                                  int64_t inner, double c0, double voxel_size, double rho_g, int prec_flags,
+                                  double *partials, int nblocks, psb200_stream stream)
+{
+    if (!ctx || !dt || !im || !partials || n < 1 || inner < 1 || nblocks < 1) return fail(PSB200_ERR_INVALID, "drain_stats: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DrainFn q = make_drain_fn(c0, voxel_size, rho_g, prec_flags, inner, pc_user != nullptr);
+    {
+        ProfScope ps__(ctx, st, K_DRAIN);
+        drain_stats_kernel<<<nblocks, 256, 0, st>>>(dt, im, pc_user, n, q, partials);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_drain_threshold(psb200_ctx *ctx, const float *dt, const uint8_t *im, const double *pc_user,
+                                      const uint8_t *residual, int64_t n, int64_t inner, double c0, double voxel_size,
+                                      double rho_g, int prec_flags, double p, uint8_t *temp, psb200_stream stream)
+{
+    if (!ctx || !dt || !im || !temp || n < 1 || inner < 1) return fail(PSB200_ERR_INVALID, "drain_threshold: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DrainFn q = make_drain_fn(c0, voxel_size, rho_g, prec_flags, inner, pc_user != nullptr);
+    {
+        ProfScope ps__(ctx, st, K_DRAIN);
+        drain_threshold_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(dt, im, pc_user, residual, n, q, p, temp);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_drain_newly(psb200_ctx *ctx, const uint8_t *reached, const uint8_t *mask, uint8_t *seeds,
+                                  const float *dt, uint16_t *rad, int64_t n, uint64_t *count_dev, int *maxr_dev,
+                                  psb200_stream stream)
+{
+    if (!ctx || !reached || !seeds || !dt || !rad || !count_dev || !maxr_dev || n < 1)
+        return fail(PSB200_ERR_INVALID, "drain_newly: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(count_dev, 0, sizeof(uint64_t), st));
+    CUDA_TRY(cudaMemsetAsync(maxr_dev, 0, sizeof(int), st));
+    {
+        ProfScope ps__(ctx, st, K_DRAIN);
+        drain_newly_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(
+            reached, mask, seeds, dt, rad, n, reinterpret_cast<unsigned long long *>(count_dev), maxr_dev);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" size_t psb200_drain_paint_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx)
+{
+    if (!ctx) return 0;
+    return 2 * align256((size_t)nz * ny * nx * 4) + 512;
+}
+
+// Paint the spheres of the newly invaded voxels (rad > 0) into inv with the value `val` (power-diagram passes).
+extern "C" int psb200_drain_paint(psb200_ctx *ctx, const uint16_t *rad, int rmax, uint8_t *inv, int val, int64_t nz,
+                                  int64_t ny, int64_t nx, void *ws, size_t ws_bytes, psb200_stream stream)
+{
+    if (!ctx || !rad || !inv || val < 1 || val > 255 || rmax < 0) return fail(PSB200_ERR_INVALID, "drain_paint: bad argument");
+    int rc = check_dims("drain_paint", nz, ny, nx);
+    if (rc) return rc;
+    if (rmax == 0) return PSB200_OK;                         // radius-0 spheres are empty (thresh = r - 0.001 < 0)
+    if (rmax > 46340) return fail(PSB200_ERR_UNSUPPORTED, "drain_paint: radius too large");
+    const int64_t n = nz * ny * nx;
+    char *base = ws ? (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
+    if (!base || ws_bytes < 2 * align256((size_t)n * 4) + (size_t)(base - (char *)ws))
+        return fail(PSB200_ERR_WORKSPACE, "drain_paint needs %zu workspace bytes", 2 * align256((size_t)n * 4) + 256);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *a = reinterpret_cast<uint32_t *>(base), *b = reinterpret_cast<uint32_t *>(base + align256((size_t)n * 4));
+    const uint32_t C = (uint32_t)rmax * (uint32_t)rmax;
+    {
+        const size_t smem = (size_t)(PX_SEG + 2 * rmax) * 4;
+        if ((int)smem > ctx->max_smem_optin) return fail(PSB200_ERR_UNSUPPORTED, "drain_paint: radius too large for the x pass");
+        CUDA_TRY(cudaFuncSetAttribute(power_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t jobs = nz * ny * ((nx + PX_SEG - 1) / PX_SEG);
+        ProfScope ps__(ctx, st, K_DRAIN);
+        power_x_kernel<<<grid_for(jobs, 1, ctx->sm_count, 8), 256, smem, st>>>(rad, a, nz * ny, (int)nx, C, rmax);
+    }
+    LAUNCH_CHECK(ctx);
+    uint32_t *cur = a, *other = b;
+    if (ny > 1) {
+        rc = launch_minplus<MpSrcU32>(ctx, 1, cur, other, 0, nullptr, nz, ny, nx, st);
+        if (rc) return rc;
+        uint32_t *t = cur; cur = other; other = t;
+    }
+    if (nz > 1) {
+        rc = launch_minplus<MpSrcU32>(ctx, 0, cur, other, 0, nullptr, nz, ny, nx, st);
+        if (rc) return rc;
+        uint32_t *t = cur; cur = other; other = t;
+    }
+    {
+        ProfScope ps__(ctx, st, K_DRAIN);
+        drain_paint_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(cur, inv, n, C, (uint32_t)val);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_set_where_u8(psb200_ctx *ctx, uint8_t *dst, const uint8_t *mask, int value, int64_t n,
+                                   psb200_stream stream)
+{
+    if (!ctx || !dst || !mask || n < 0 || value < 0 || value > 255) return fail(PSB200_ERR_INVALID, "set_where_u8: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    {
+        ProfScope ps__(ctx, (cudaStream_t)stream, K_DRAIN);
+        set_where_u8_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, (cudaStream_t)stream>>>(dst, mask, (uint8_t)value, n);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_set_zero_codes_u8(psb200_ctx *ctx, uint8_t *codes, const uint8_t *im, const uint8_t *zero_lut_dev,
+                                        int value, int64_t n, psb200_stream stream)
+{
+    if (!ctx || !codes || !im || !zero_lut_dev || n < 0 || value < 0 || value > 255)
+        return fail(PSB200_ERR_INVALID, "set_zero_codes_u8: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    {
+        ProfScope ps__(ctx, (cudaStream_t)stream, K_DRAIN);
+        set_zero_codes_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, (cudaStream_t)stream>>>(codes, im, zero_lut_dev,
+                                                                                                 (uint8_t)value, n);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;

@@ -54,9 +54,15 @@ expand_lut8_kernel(const I *__restrict__ idx, const uint8_t *__restrict__ mask, 
 }
 
 // ---- arbitrary 8-byte arrays -> index form
-// Distinct bit patterns of x[] into an open-addressing table (cap = power of two; empty = all ones).
-// For float64 input the caller canonicalises -0.0 to +0.0 beforehand if it wants numpy's `unique` semantics.
-#define DISTINCT_EMPTY 0xFFFFFFFFFFFFFFFFull
+// Distinct bit patterns of x[] into an open-addressing table (cap = power of two).  The empty marker is
+// 0x8000...0: as float64 it is -0.0, which the caller canonicalises to +0.0 beforehand (numpy's `unique` treats
+// them as one value anyway); as int64 it is INT64_MIN, which no sequence / label map holds.
+#define DISTINCT_EMPTY 0x8000000000000000ull
+__global__ void __launch_bounds__(256)
+fill_u64_kernel(unsigned long long *__restrict__ p, uint32_t n, unsigned long long v)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
 __device__ __forceinline__ uint32_t hash64(uint64_t k)
 {
     k ^= k >> 33; k *= 0xFF51AFD7ED558CCDull; k ^= k >> 33; k *= 0xC4CEB9FE1A85EC53ull; k ^= k >> 33;

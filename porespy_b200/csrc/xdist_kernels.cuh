@@ -4,8 +4,7 @@
 //   XD_EDT : site <=> in[x] == 0            -> uint16 distance, >= 0x8000 when the line has no
 //            site (first pass of edt.edt, /root/reference/src/porespy/filters/_funcs.py:1126)
 //   XD_LT  : site <=> in[x] <= k (class map: seeds of radius k, F:1180/1196)
-//                                            -> uint8 min(distance, cap), cap = W + 1 <= 254;
-//                                               255 (GX_BG) at background voxels (class byte 255)
+//                                            -> uint8 min(distance, cap), cap = W + 1 <= 254
 //            (first pass of the per-radius dilation that replaces edt(~seeds) < r, F:1191)
 //
 // One warp per line, a lane owns 16-voxel chunks (one 16-byte load).  Sites are found with
@@ -184,10 +183,6 @@ xdist_kernel(const uint8_t *__restrict__ in, void *__restrict__ outp, int64_t nl
                 uint4 o;
                 o.x = __byte_perm(t01, t23, 0x5410); o.y = __byte_perm(t45, t67, 0x5410);
                 o.z = __byte_perm(t01, t23, 0x7632); o.w = __byte_perm(t45, t67, 0x7632);
-                // background voxels (class byte 255) are marked GX_BG: they can never be filled (lemma ii),
-                // so the y pass does not scan for them (their distance still reads as "far" to their neighbours)
-                o.x |= (swar_ge(v.x, 0x7F7F7F7Fu, 0u) >> 7) * 0xFFu; o.y |= (swar_ge(v.y, 0x7F7F7F7Fu, 0u) >> 7) * 0xFFu;
-                o.z |= (swar_ge(v.z, 0x7F7F7F7Fu, 0u) >> 7) * 0xFFu; o.w |= (swar_ge(v.w, 0x7F7F7F7Fu, 0u) >> 7) * 0xFFu;
                 if (vec) reinterpret_cast<uint4 *>(orow)[c] = o;
                 else {
                     const uint32_t w4[4] = {o.x, o.y, o.z, o.w};

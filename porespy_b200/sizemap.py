@@ -27,7 +27,7 @@ from . import _lib
 __all__ = ["IndexMap", "local_thickness_index", "porosimetry_index", "size_to_seq", "size_to_satn", "seq_to_satn",
            "pore_size_distribution", "pc_curve", "Results"]
 
-_EMPTY = np.uint64(0xFFFFFFFFFFFFFFFF)
+_EMPTY = np.uint64(0x8000000000000000)      # -0.0 / INT64_MIN: never a key (floats are canonicalised with + 0.0)
 _TABLE_CAP = 1 << 18
 MAX_VALUES = 65536
 
