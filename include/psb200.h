@@ -295,6 +295,9 @@ int psb200_hist_idx(psb200_ctx *ctx, const void *idx, int idx_bytes, const uint8
                     uint64_t *counts, psb200_stream stream);
 int psb200_expand_lut8(psb200_ctx *ctx, const void *idx, int idx_bytes, const uint8_t *mask, const uint64_t *lut,
                        void *out, int64_t n, int K, psb200_stream stream);
+/* the same with one-byte payloads (masks such as `seq >= i`); lut: device bytes, K or 2K entries */
+int psb200_expand_lut1(psb200_ctx *ctx, const void *idx, int idx_bytes, const uint8_t *mask, const uint8_t *lut,
+                       uint8_t *out, int64_t n, int K, psb200_stream stream);
 int psb200_distinct64(psb200_ctx *ctx, const uint64_t *x, int64_t n, uint64_t *table, uint32_t cap, int *overflow,
                       psb200_stream stream);
 int psb200_index_of64(psb200_ctx *ctx, const uint64_t *x, int64_t n, const uint64_t *keys, int K, int kind,

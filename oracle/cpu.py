@@ -460,3 +460,118 @@ def pc_curve_sizes(im, sizes, sigma=0.072, theta=180, voxel_size=1):
         x.append(-2 * sigma * np.cos(np.deg2rad(theta)) / r)
         y.append(((sizes >= n) * (im == 1)).sum(dtype=np.int64) / im.sum(dtype=np.int64))
     return np.asarray(x), np.asarray(y)
+
+
+# ----------------------------------------------------- simulations.drainage, plain numpy
+def pc_to_satn(pc, im, mode="drainage"):
+    """filters/_size_seq_satn.py:338-342."""
+    a = np.digitize(pc, bins=np.unique(pc))
+    a[~im] = 0
+    a[np.where(pc == np.inf)] = -1
+    return seq_to_satn(seq=a, im=im, mode=mode)
+
+
+def satn_to_seq(satn, im=None, mode="drainage"):
+    """filters/_size_seq_satn.py:384-399."""
+    if im is None:
+        im = satn > 0
+    uninvaded = satn == -1
+    values = np.unique(satn)
+    seq = np.digitize(satn, bins=values)
+    seq[satn == -1] = -1
+    seq[~im] = 0
+    seq = make_contiguous_symmetric(seq)
+    if mode.startswith("im"):
+        seq = (seq.max() + 1) - seq
+        seq[~im] = 0
+    seq[uninvaded] = -1
+    return seq
+
+
+def pc_curve_pc(im, pc):
+    """metrics/_funcs.py:1091-1108 (the `pc` branch of pc_curve) -> (Ps, snwp)."""
+    Ps = np.unique(pc[im])
+    if Ps[-1] == np.inf:
+        Ps[-1] = Ps[-2] * 2
+    if Ps[0] == -np.inf:
+        Ps[0] = Ps[1] - np.abs(Ps[1] / 2)
+    else:
+        Ps = np.hstack((Ps[0] - np.abs(Ps[0] / 2), Ps))
+    Vp = im.sum(dtype=np.int64)
+    temp = pc[im]
+    return Ps, [(temp <= p).sum(dtype=np.int64) / Vp for p in Ps]
+
+
+def _insert_spheres(inv, new, radii_map, v):
+    """tools/_sphere_insertions.py:327-385 for all new points at once: the union of the balls
+    {o : sqrt(|o|^2) <= r - 0.001} around the points of radius r, written where inv == 0."""
+    import scipy.ndimage as spim
+    for r in np.unique(radii_map[new]):
+        r = int(r)
+        if r < 1:
+            continue
+        ax = np.arange(-r, r + 1)
+        grids = np.meshgrid(*([ax] * inv.ndim), indexing="ij")
+        ball = np.sqrt(sum(gg.astype(float) ** 2 for gg in grids)) <= r - 0.001
+        cover = spim.binary_dilation(new & (radii_map == r), structure=ball)
+        inv[cover & (inv == 0)] = v
+    return inv
+
+
+def drainage(im, voxel_size, pc=None, inlets=None, outlets=None, residual=None, bins=25, delta_rho=1000, g=9.81,
+             sigma=0.072, theta=180):
+    """simulations/_drainage.py:104-185 -> dict(im_pc, im_satn, im_trapped, pc, snwp)."""
+    im = np.array(im, dtype=bool)
+    dt = edt(im)
+    if pc is None:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            pc = -(im.ndim - 1) * sigma * np.cos(np.deg2rad(theta)) / (dt * voxel_size)
+    else:
+        pc = np.array(pc, dtype=np.float64)
+    pc[~im] = 0
+    h = np.ones_like(im, dtype=bool)
+    h[0, ...] = False
+    h = (edt(h) + 1) * voxel_size
+    rgh = delta_rho * g * h
+    fn = pc + rgh
+    if inlets is None:
+        inlets = np.zeros_like(im)
+        inlets[0, ...] = True
+    if isinstance(bins, int):
+        vmax = fn[fn < np.inf].max()
+        vmin = fn[im][fn[im] > -np.inf].min()
+        Ps = np.linspace(vmin, vmax * 1.1, bins)
+    else:
+        Ps = bins
+    inv = np.zeros_like(im, dtype=float)
+    seeds = np.zeros_like(im, dtype=bool)
+    radii_map = dt.astype(int)
+    mask = None
+    if (residual is not None) and (outlets is not None):
+        mask = im * (~residual)
+        mask = trim_disconnected_blobs(mask, inlets=inlets)
+    for p in Ps:
+        temp = (fn <= p) * im
+        if residual is not None:
+            temp = temp + residual
+        new_seeds = trim_disconnected_blobs(temp, inlets=inlets)
+        if mask is not None:
+            new_seeds = new_seeds * mask
+        temp = new_seeds * (~seeds)
+        seeds += new_seeds
+        inv = _insert_spheres(inv, temp, radii_map, p)
+    inv[(inv == 0) * im] = np.inf
+    if residual is not None:
+        inv[residual] = -np.inf
+    trapped = None
+    satn = pc_to_satn(pc=inv, im=im)
+    if outlets is not None:
+        seq = satn_to_seq(satn=satn, im=im)
+        trapped = find_trapped_regions(seq=seq, outlets=outlets)
+        trapped[seq == -1] = True
+        inv[trapped] = np.inf
+        if residual is not None:
+            inv[residual] = -np.inf
+        satn = pc_to_satn(pc=inv, im=im)
+    Pc, snwp = pc_curve_pc(im, inv)
+    return dict(im_pc=inv, im_satn=satn, im_trapped=trapped, pc=Pc, snwp=snwp)

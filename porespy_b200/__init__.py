@@ -11,6 +11,7 @@ from . import edt as edt_module
 from . import filters
 from . import generators
 from . import metrics
+from . import simulations
 from . import sizemap
 from .edt import edt, edtsq
 from .filters import local_thickness, porosimetry, trim_disconnected_blobs
@@ -19,7 +20,7 @@ from .patch import install, uninstall
 from ._device import pinned_empty, to_pinned
 
 __version__ = "0.1.0"
-__all__ = ["edt", "edtsq", "filters", "generators", "metrics", "sizemap", "IndexMap", "local_thickness_index",
+__all__ = ["edt", "edtsq", "filters", "generators", "metrics", "simulations", "sizemap", "IndexMap", "local_thickness_index",
            "porosimetry_index", "local_thickness", "porosimetry",
            "trim_disconnected_blobs", "install", "uninstall", "build", "pinned_empty", "to_pinned"]
 

@@ -99,6 +99,7 @@ SIGNATURES = {
                                    _vp, _vp, _vp]),
     "psb200_hist_idx": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _vp, _vp]),
     "psb200_expand_lut8": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "psb200_expand_lut1": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "psb200_distinct64": (_i32, [_vp, _vp, _i64, _vp, _u32, _vp, _vp]),
     "psb200_index_of64": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp]),
     "psb200_drain_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _c.c_double, _c.c_double, _c.c_double, _i32, _vp, _i32, _vp]),

@@ -695,6 +695,7 @@ static int lt_xy_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, ui
 }
 
 #define LT_LZ 32
+#define LTY3_MAX_W 26
 
 static int lt_z_impl(psb200_ctx *ctx, const uint8_t *reach, const uint8_t *m_lo, int nlo,
                      const uint8_t *m_hi, int nhi, uint8_t *idx, int k, uint32_t T, int64_t nz,
@@ -741,7 +742,9 @@ static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_
     if (rc) return rc;
     {   // y pass
         int Ly = ny < 128 ? (int)ny : 128;
-        const bool coarse = ctx->ycoarse && (int)lt_y3_smem_bytes(Ly, W, T) <= ctx->max_smem_optin;
+        // hierarchical scan for the denser radii (measured r2c at 1024^3: it wins from W = 25 down -- 2.49 -> 2.25 ms
+        // at T = 344 -- and loses above, where seeds are sparse and its larger halo and group minima only cost)
+        const bool coarse = ctx->ycoarse && W <= LTY3_MAX_W && (int)lt_y3_smem_bytes(Ly, W, T) <= ctx->max_smem_optin;
         const size_t smem = coarse ? lt_y3_smem_bytes(Ly, W, T) : lt_y2_smem_bytes(Ly, W, T);
         if ((int)smem > ctx->max_smem_optin)
             return fail(PSB200_ERR_UNSUPPORTED, "lt_y: tile needs %zu bytes of shared memory", smem);
@@ -1588,6 +1591,26 @@ extern "C" int psb200_expand_lut8(psb200_ctx *ctx, const void *idx, int idx_byte
         else
             expand_lut8_kernel<uint16_t><<<g, 256, 0, st>>>(reinterpret_cast<const uint16_t *>(idx), mask, lut,
                                                           reinterpret_cast<uint64_t *>(out), n, K);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_expand_lut1(psb200_ctx *ctx, const void *idx, int idx_bytes, const uint8_t *mask,
+                                  const uint8_t *lut, uint8_t *out, int64_t n, int K, psb200_stream stream)
+{
+    if (!ctx || !idx || !lut || !out || n < 0 || K < 1 || K > 65536 || (idx_bytes != 1 && idx_bytes != 2))
+        return fail(PSB200_ERR_INVALID, "expand_lut1: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid_for(n, 256, ctx->sm_count, 16);
+    {
+        ProfScope ps__(ctx, st, K_SIZEMAP);
+        if (idx_bytes == 1)
+            expand_lut1_kernel<uint8_t><<<g, 256, 0, st>>>(reinterpret_cast<const uint8_t *>(idx), mask, lut, out, n, K);
+        else
+            expand_lut1_kernel<uint16_t><<<g, 256, 0, st>>>(reinterpret_cast<const uint16_t *>(idx), mask, lut, out, n, K);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;

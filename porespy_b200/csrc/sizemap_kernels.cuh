@@ -53,6 +53,20 @@ expand_lut8_kernel(const I *__restrict__ idx, const uint8_t *__restrict__ mask, 
     }
 }
 
+// out[i] = lut[(mask && mask[i]) ? K + idx[i] : idx[i]]     one-byte payload (masks such as `seq >= i`)
+template <typename I>
+__global__ void __launch_bounds__(256)
+expand_lut1_kernel(const I *__restrict__ idx, const uint8_t *__restrict__ mask, const uint8_t *__restrict__ lut,
+                   uint8_t *__restrict__ out, int64_t n, int K)
+{
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        int b = (int)idx[i];
+        if (mask && mask[i]) b += K;
+        out[i] = __ldg(lut + b);
+    }
+}
+
 // ---- arbitrary 8-byte arrays -> index form
 // Distinct bit patterns of x[] into an open-addressing table (cap = power of two).  The empty marker is
 // 0x8000...0: as float64 it is -0.0, which the caller canonicalises to +0.0 beforehand (numpy's `unique` treats

@@ -299,13 +299,26 @@ def trim_nonpercolating_paths(im, inlets, outlets, strel=None):
     return _mask_to_host(hit)
 
 
+def _trapped_mask(ctx, shape, temp_of, bins, out_t):
+    """F:131-137 on the device: for every bin value i the voxels of `temp = seq >= i` whose component (cross
+    neighbourhood, scipy's default) holds no outlet voxel.  temp_of(i) -> flat uint8 device mask."""
+    torch = dev._torch()
+    conn = 6 if len(shape) == 3 else 4
+    trapped = torch.zeros(int(np.prod(shape)), dtype=torch.bool, device=out_t.device)
+    out_flat = out_t.reshape(-1)
+    for i in bins:
+        temp = temp_of(i)
+        reached = dev.flood(ctx, temp, temp * out_flat, conn, host.shape3(shape))
+        trapped |= (temp != 0) & (reached == 0)
+    return trapped.view(*shape)
+
+
 def find_trapped_regions(seq, outlets=None, bins: int = 25, return_mask: bool = True):
     r"""Trapped regions of an invasion sequence (F:73-147): for every bin value i, descending, the
     voxels with `seq >= i` that are not connected (cross neighbourhood, scipy's default) to an outlet
     voxel of the same set.  One flood per bin on the device, as in the reference's loop; the bins
     (`None`: every sequence value, int: `np.linspace(seq.max(), 1, bins)`) are the reference's own
     numpy expressions.  `return_mask=False` relabels on the host like `make_contiguous('symmetric')`."""
-    torch = dev._torch()
     seq = np.copy(seq)
     if seq.ndim not in (2, 3):
         raise ValueError("find_trapped_regions supports 2-D and 3-D images")
@@ -319,16 +332,11 @@ def find_trapped_regions(seq, outlets=None, bins: int = 25, return_mask: bool = 
         bins = bins[bins > 0]
     elif isinstance(bins, int):
         bins = np.linspace(seq.max(), 1, bins)
-    conn = 6 if seq.ndim == 3 else 4
     ctx = _lib.context()
     out_t = _mask_to_device(outlets, ctx, seq.shape)
-    trapped = torch.zeros(seq.shape, dtype=torch.bool, device=out_t.device)
-    for i in bins:
-        # `seq >= i` is numpy's own comparison (F:133: any dtype numpy accepts, its promotion rules); only
-        # the resulting mask goes to the device
-        temp = _mask_to_device(seq >= i, ctx, seq.shape)
-        reached = _reached_from(ctx, temp, temp * out_t, conn)
-        trapped |= (temp != 0) & (reached == 0)
+    # `seq >= i` is numpy's own comparison (F:133: any dtype numpy accepts, its promotion rules); only
+    # the resulting mask goes to the device
+    trapped = _trapped_mask(ctx, seq.shape, lambda i: _mask_to_device(seq >= i, ctx, seq.shape).reshape(-1), bins, out_t)
     trapped = _mask_to_host(trapped)
     if return_mask:
         return trapped

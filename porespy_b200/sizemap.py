@@ -143,6 +143,18 @@ class IndexMap:
             return (out.view(torch.float64) if lut.dtype.kind == "f" else out).view(*self.shape)
         return dev.to_host(out).view(lut.dtype).reshape(self.shape)
 
+    def expand_mask(self, lut_bool, mask=None):
+        """Device uint8 mask: out[v] = lut_bool[(mask[v] ? K : 0) + idx[v]] (flat tensor)."""
+        torch = dev._torch()
+        K = len(self.values)
+        lut = np.ascontiguousarray(lut_bool, dtype=np.uint8)
+        assert len(lut) == K * (2 if mask is not None else 1)
+        lut_d = torch.from_numpy(lut).to(self.idx.device)
+        out = torch.empty(self.idx.numel(), dtype=torch.uint8, device=self.idx.device)
+        _lib.check(self.ctx.lib.psb200_expand_lut1(self.ctx.handle, dev.ptr(self.idx), self.idx_bytes, dev.ptr(mask),
+                                                   dev.ptr(lut_d), dev.ptr(out), out.numel(), K, dev.stream_ptr()))
+        return out
+
     def to_numpy(self):
         """The map itself (float64 for radius maps), e.g. to hand it to code that wants the reference's array."""
         vals = self.values
@@ -237,12 +249,9 @@ def size_to_seq(size, im=None, bins=None, mode="drainage"):
     return sm.scatter(np.asarray(vals, dtype=np.int64), present, mask)
 
 
-def seq_to_satn(seq, im=None, mode="drainage"):
-    r"""Invasion sequence -> saturation (filters/_size_seq_satn.py:152-221).  `rankdata(seq, 'dense') - 1` is
-    evaluated as the dense rank `np.unique(..., return_inverse=True)` (integer, as the reference's bincount needs;
-    SciPy >= 1.18 returns floats there and breaks the reference itself)."""
-    sm = IndexMap.from_array(seq)
-    s, m, w, present, mask = sm.representatives(im)
+def _seq_to_satn_rep(s, m, w, size, mode="drainage"):
+    """Body of seq_to_satn (filters/_size_seq_satn.py:196-221) on representative voxels: s = sequence value,
+    m = pore flag (None: not given), w = voxel count of the combination, size = voxels of the image."""
     q = np.copy(s).astype(int)
     solid_mask = (q == 0) if m is None else (m == 0)
     uninvaded_mask = q == -1
@@ -257,10 +266,60 @@ def seq_to_satn(seq, im=None, mode="drainage"):
     if (w[solid_mask].sum() > 0) or (w[uninvaded_mask].sum() > 0):
         b[0] = 0
     c = np.cumsum(b)
-    satn = c[q] / (sm.size - w[solid_mask].sum())
+    with np.errstate(divide="ignore", invalid="ignore"):
+        satn = c[q] / (size - w[solid_mask].sum())
     satn[solid_mask] = 0
     satn[uninvaded_mask] = -1
-    return sm.scatter(satn, present, mask)
+    return satn
+
+
+def seq_to_satn(seq, im=None, mode="drainage"):
+    r"""Invasion sequence -> saturation (filters/_size_seq_satn.py:152-221).  `rankdata(seq, 'dense') - 1` is
+    evaluated as the dense rank `np.unique(..., return_inverse=True)` (integer, as the reference's bincount needs;
+    SciPy >= 1.18 returns floats there and breaks the reference itself)."""
+    sm = IndexMap.from_array(seq)
+    s, m, w, present, mask = sm.representatives(im)
+    return sm.scatter(_seq_to_satn_rep(s, m, w, sm.size, mode), present, mask)
+
+
+def _pc_to_satn_rep(s, m, w, size, mode="drainage"):
+    """pc_to_satn (filters/_size_seq_satn.py:338-342) on representative voxels (m: pore flag, mandatory)."""
+    a = np.digitize(s, bins=np.unique(s))
+    a[~m] = 0
+    a[np.where(s == np.inf)] = -1
+    return _seq_to_satn_rep(a, m, w, size, mode)
+
+
+def _satn_to_seq_rep(satn, m, mode="drainage"):
+    """satn_to_seq (filters/_size_seq_satn.py:384-399) on representative voxels (m: pore flag)."""
+    uninvaded = satn == -1
+    values = np.unique(satn)
+    seq = np.digitize(satn, bins=values)
+    seq[satn == -1] = -1
+    seq[~m] = 0
+    seq = host.make_contiguous_symmetric(seq)
+    if mode.startswith("im"):
+        seq = (seq.max() + 1) - seq
+        seq[~m] = 0
+    seq[uninvaded] = -1
+    return seq
+
+
+def _pc_curve_pc_rep(s, m, w):
+    """pc_curve's `pc` branch (metrics/_funcs.py:1091-1108) on representative voxels -> (Ps, snwp)."""
+    Ps = np.unique(s[m])
+    if Ps[-1] == np.inf:
+        Ps[-1] = Ps[-2] * 2
+    if Ps[0] == -np.inf:
+        Ps[0] = Ps[1] - np.abs(Ps[1] / 2)
+    else:
+        Ps = np.hstack((Ps[0] - np.abs(Ps[0] / 2), Ps))
+    y = []
+    Vp = w[m].sum(dtype=np.int64)
+    temp, tw = s[m], w[m]
+    for p in Ps:
+        y.append(tw[temp <= p].sum(dtype=np.int64) / Vp)
+    return Ps, y
 
 
 def _parse_histogram(h, voxel_size=1, density=True):

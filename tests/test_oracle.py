@@ -254,3 +254,28 @@ def test_sizemap_restatements_match_reference_goldens(golden):
     assert np.array_equal(oc.size_to_seq(small), g.raw("small_seq"))
     assert np.array_equal(oc.size_to_seq(small, mode="imbibition"), g.raw("small_seq_im"))
     assert np.array_equal(oc.seq_to_satn(g.raw("small_seq")), g.raw("small_seq_satn"))
+
+
+def _drainage_same(got, g, name):
+    assert np.array_equal(got["im_pc"], g.rmap(name + "_im_pc")), name + " im_pc"
+    assert np.array_equal(got["im_satn"], g.rmap(name + "_im_satn")), name + " im_satn"
+    if got["im_trapped"] is not None:
+        assert np.array_equal(got["im_trapped"], g.mask(name + "_im_trapped")), name + " trapped"
+    assert np.array_equal(np.asarray(got["pc"]), g.raw(name + "_pc")), name + " pc"
+    assert np.array_equal(np.asarray(got["snwp"]), g.raw(name + "_snwp")), name + " snwp"
+
+
+def test_drainage_restatement_matches_reference_goldens(golden):
+    """oracle.cpu.drainage against the reference's own simulations.drainage (tests/golden/make_golden_drainage.py)."""
+    g = golden.drainage
+    im, inl, out, res = g.mask("a_im"), g.mask("a_inlets"), g.mask("a_outlets"), g.mask("a_residual")
+    vs = 1e-4
+    _drainage_same(oc.drainage(im, vs, inlets=inl, g=0), g, "a1")
+    _drainage_same(oc.drainage(im, vs, inlets=inl, outlets=out, residual=res, g=0), g, "a4")
+    _drainage_same(oc.drainage(im, vs, inlets=inl, outlets=out), g, "a5")
+    _drainage_same(oc.drainage(im, vs, inlets=inl, bins=[300.0, 900.0, 2000.0, 1500.0, 8000.0], delta_rho=-997, g=9.81,
+                               sigma=0.05, theta=140), g, "a6")
+    _drainage_same(oc.drainage(im, np.float64(vs), inlets=inl, bins=12), g, "a7")
+    im3, out3 = g.mask("b_im"), g.mask("b_outlets")
+    _drainage_same(oc.drainage(im3, 1e-5), g, "b1")
+    _drainage_same(oc.drainage(im3, 1e-5, pc=g.raw("b_pc_user"), bins=10), g, "b3")
