@@ -174,6 +174,10 @@ int psb200_lt_z(psb200_ctx *ctx, uint8_t *reach, const uint8_t *m_lo, int nlo,
  * puts the W = ceil(sqrt(T))-1 halo planes of its neighbours in front of / behind its own. */
 int psb200_lt_pack(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t *bits,
                    int64_t nz, int64_t ny, int64_t nx, psb200_stream stream);
+/* seed bits of nk <= 16 consecutive radii k0 .. k0 + nk - 1 from ONE read of the class map (bit-sliced
+ * comparator): bits + i * vol_words receives radius k0 + i (vol_words >= nz*ny*nx/32, multiple of 4). */
+int psb200_lt_packn(psb200_ctx *ctx, const uint8_t *cls, int k0, int nk, uint32_t *bits, int64_t vol_words,
+                    int64_t nz, int64_t ny, int64_t nx, psb200_stream stream);
 int psb200_lt_wmask(psb200_ctx *ctx, const uint8_t *idx, uint32_t *written,
                     int64_t nz, int64_t ny, int64_t nx, psb200_stream stream);
 int psb200_lt_bitball(psb200_ctx *ctx, const uint32_t *seedbits, int64_t nz_src, int64_t z_off,

@@ -74,6 +74,7 @@ SIGNATURES = {
     "psb200_lt_xy": (_i32, [_vp, _vp, _i32, _u32, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_lt_z": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _u32, _i64, _i64, _i64, _vp]),
     "psb200_lt_pack": (_i32, [_vp, _vp, _i32, _vp, _i64, _i64, _i64, _vp]),
+    "psb200_lt_packn": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _i64, _i64, _i64, _vp]),
     "psb200_lt_wmask": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "psb200_lt_bitball": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _u32, _i64, _i64, _i64, _vp]),
     "psb200_expand_idx_f64": (_i32, [_vp, _vp, _c.POINTER(_c.c_double), _i32, _vp, _i64, _i32, _vp]),

@@ -991,6 +991,28 @@ extern "C" int psb200_lt_pack(psb200_ctx *ctx, const uint8_t *cls, int k, uint32
     return lt_pack_impl(ctx, cls, k, bits, nz * ny * nx / 32, nullptr, (cudaStream_t)stream);
 }
 
+extern "C" int psb200_lt_packn(psb200_ctx *ctx, const uint8_t *cls, int k0, int nk, uint32_t *bits, int64_t vol_words,
+                               int64_t nz, int64_t ny, int64_t nx, psb200_stream stream)
+{
+    if (!ctx || !cls || !bits || k0 < 0 || nk < 1 || nk > PACKN_MAX || k0 + nk > PSB200_MAX_THRESHOLDS)
+        return fail(PSB200_ERR_INVALID, "lt_packn: bad argument (1 <= nk <= %d)", PACKN_MAX);
+    int rc = check_dims("lt_packn", nz, ny, nx);
+    if (!rc) rc = bit_shape_ok("lt_packn", nx, cls, bits);
+    if (rc) return rc;
+    const int64_t nwords = nz * ny * nx / 32;
+    if (vol_words < nwords || (vol_words & 3)) return fail(PSB200_ERR_INVALID, "lt_packn: vol_words must be >= the words of one volume and a multiple of 4");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int nb = 1;
+    while (nb < 8 && (k0 + nk - 1) >> nb) ++nb;
+    {
+        ProfScope ps__(ctx, st, K_LT_PACK);
+        lt_packn_kernel<<<grid_for(nwords, 256, ctx->sm_count, 8), 256, 0, st>>>(cls, bits, nwords, vol_words, k0, nk, nb);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
 extern "C" int psb200_lt_wmask(psb200_ctx *ctx, const uint8_t *idx, uint32_t *written, int64_t nz, int64_t ny,
                                int64_t nx, psb200_stream stream)
 {

@@ -86,6 +86,14 @@ class CudaBackend:
                                                  nz, ny, nx, dev.stream_ptr()))
         return out, int(mx.cpu().numpy().view(np.uint32)[0])
 
+    def edt_ext(self, ext_u8, shape_ext, lo, nzl):
+        """Exact EDT of the extended slab (own planes plus input halo planes), one-GPU kernels; returns the own
+        planes [lo, lo + nzl) as a flat int32 tensor and their maximum."""
+        nze, ny, nx = shape_ext
+        d2e, _ = dev.edt_run(self.ctx, ext_u8, shape_ext)
+        own = d2e[lo * ny * nx:(lo + nzl) * ny * nx]
+        return own, dev.max_u32(self.ctx, own)
+
     # -- per-radius steps
     def classify(self, d2, T):
         cls = self.empty(d2.numel(), self.torch.uint8)
@@ -114,6 +122,14 @@ class CudaBackend:
         nz, ny, nx = shape
         _lib.check(self.ctx.lib.psb200_lt_pack(self.ctx.handle, dev.ptr(cls), int(k), dev.ptr(out_bits),
                                                nz, ny, nx, dev.stream_ptr()))
+
+    PACKN = 16
+
+    def packn(self, cls, k0, nk, out_bits, vol_words, shape):
+        """Seed bits of the radii k0 .. k0 + nk - 1 from one read of the class map (psb200_lt_packn)."""
+        nz, ny, nx = shape
+        _lib.check(self.ctx.lib.psb200_lt_packn(self.ctx.handle, dev.ptr(cls), int(k0), int(nk), dev.ptr(out_bits),
+                                                int(vol_words), nz, ny, nx, dev.stream_ptr()))
 
     def wmask(self, idx, written, shape):
         nz, ny, nx = shape
@@ -331,12 +347,49 @@ class ShardedVolume:
         return float(t.item())
 
     # ------------------------------------------------------------------------------ EDT
+    # Fast path of the sharded EDT: every rank receives EDT_HALO input planes from each z-neighbour (1 byte per
+    # voxel, 1/4 of one plane of distances) and runs the one-GPU EDT on its extended slab.  A voxel of the own
+    # slab is at least EDT_HALO + 1 planes away from anything outside the extended slab, so every squared
+    # distance below (EDT_HALO + 1)^2 is exact; if the global maximum stays below that bound -- porous media: the
+    # largest pore radius is a few tens of voxels -- the result is the exact EDT and neither all-to-all
+    # transpose is needed.  Otherwise (or with `edt_halo = 0`) the slab -> pencil all-to-all path runs, which is
+    # exact for any input.
+    EDT_HALO = 64
+
+    def _edt_halo(self, local_u8):
+        """(own-slab squared distances as flat int32, global max d2) through the input-halo path, or None when
+        the bound does not hold (or the slabs are thinner than the halo)."""
+        torch, be = self.torch, self.backend
+        nz, ny, nx = self.shape
+        nzl, P, H = self.nzl, self.world, int(getattr(self, "edt_halo", self.EDT_HALO))
+        if P == 1 or H <= 0 or H > min(self.zcounts) or not hasattr(be, "edt_ext"):
+            return None
+        plane = ny * nx
+        lo = H if self.rank > 0 else 0
+        hi = H if self.rank < P - 1 else 0
+        flat = local_u8.reshape(-1)
+        ext = be.empty((lo + nzl + hi) * plane, torch.uint8)
+        ext[lo * plane:(lo + nzl) * plane] = flat
+        self.exchange_halo(flat[:H * plane] if self.rank > 0 else None,
+                           flat[(nzl - H) * plane:] if self.rank < P - 1 else None,
+                           ext[:lo * plane] if lo else None, ext[(lo + nzl) * plane:] if hi else None)
+        own, lmax = be.edt_ext(ext, (lo + nzl + hi, ny, nx), lo, nzl)
+        del ext
+        gmax = self._allreduce_max(lmax)
+        if gmax >= (H + 1) * (H + 1):          # includes INF (a slab without background): not provably exact
+            return None
+        return own, gmax
+
     def edt_sq(self, local_u8):
         """Local slab (uint8, flat or [nzl][ny][nx]) -> (uint32 squared distances of the slab as a
         flat int32 tensor, global max d2)."""
         torch, be = self.torch, self.backend
         nz, ny, nx = self.shape
         nzl, nyl, P = self.nzl, self.nyl, self.world
+        fast = self._edt_halo(local_u8)
+        self.edt_path = "halo" if fast is not None else "all-to-all"
+        if fast is not None:
+            return fast
         d2p, lmax = self._edt_pencils(local_u8)
         if P == 1:
             return d2p, lmax
@@ -427,8 +480,15 @@ class ShardedVolume:
         lshape = (nzl, ny, nx)
         # the radius loop only needs the class of every voxel, so the distances are classified on the
         # pencils and ONE byte per voxel travels back to the slabs instead of four
-        d2p, lmax = self._edt_pencils(be.to_u8(local_im, positive=True))       # F:1126 edt(im > 0)
-        max_d2 = self._allreduce_max(lmax)
+        local_u8 = be.to_u8(local_im, positive=True)                           # F:1126 edt(im > 0)
+        fast = self._edt_halo(local_u8)
+        self.edt_path = "halo" if fast is not None else "all-to-all"
+        if fast is not None:
+            d2p, max_d2 = fast               # already in slab layout
+        else:
+            d2p, lmax = self._edt_pencils(local_u8)
+            max_d2 = self._allreduce_max(lmax)
+        del local_u8
         self.last_max_d2 = max_d2
         radii = host.reference_sizes(sizes, max_d2)
         if max_d2 == host.INF_U32:
@@ -446,7 +506,7 @@ class ShardedVolume:
             return be.expand(idx, np.array([0.0])).view(*lshape)
         cls = be.classify(d2p, T)
         del d2p
-        if self.world > 1:
+        if self.world > 1 and fast is None:
             cls = self._pencils_to_slab(cls, torch.uint8)
         st = None
         if access_limited:
@@ -458,6 +518,7 @@ class ShardedVolume:
             st = be.uf_begin(cls, inl, lshape, self.zstarts[self.rank], nz)
             self.flood_sweeps = []
         written = None
+        packed, packed_bits = None, None
         # Not access-limited: the seed bits of every bit-path radius are a function of the class map
         # alone, so the class bytes of the deepest bit-path halo travel ONCE and each rank packs its
         # extended slab itself -- one halo exchange instead of one per bit-path radius.
@@ -493,10 +554,19 @@ class ShardedVolume:
                         be.wmask(idx, written, lshape)
                 if cls_ext is not None:
                     nze = ext_lo + nzl + ext_hi
-                    ext = be.empty(nze * plane, torch.int32)
-                    be.pack(cls_ext, k, ext, (nze, ny, nx))
-                    be.bitball(ext, nze, ext_lo, written, idx, k, Tk, lshape)
-                    del ext
+                    if packed is None or not (packed[0] <= k < packed[1]):
+                        # every later radius is a bit radius too (thresholds descend): pack up to PACKN of them
+                        # from one read of the extended class map
+                        nk = min(getattr(be, "PACKN", 1), len(T) - k)
+                        vol_words = (nze * plane + 63) & ~63
+                        packed_bits = be.empty(nk * vol_words, torch.int32)
+                        if nk > 1:
+                            be.packn(cls_ext, k, nk, packed_bits, vol_words, (nze, ny, nx))
+                        else:
+                            be.pack(cls_ext, k, packed_bits[:nze * plane], (nze, ny, nx))
+                        packed = (k, k + nk, vol_words)
+                    off = (k - packed[0]) * packed[2]
+                    be.bitball(packed_bits[off:off + nze * plane], nze, ext_lo, written, idx, k, Tk, lshape)
                     continue
                 ext = be.empty((nlo + nzl + nhi) * plane, torch.int32)
                 mine = ext[nlo * plane:(nlo + nzl) * plane]

@@ -74,7 +74,7 @@ def drainage(im, voxel_size, pc=None, inlets=None, outlets=None, residual=None, 
     conn = 26 if im.ndim == 3 else 8                         # trim_disconnected_blobs' default strel (F:1260-1264)
 
     if isinstance(bins, int):                                                       # F:121-124
-        nb = ctx.sm_count * 8
+        nb = 148 * 8
         part = torch.empty(2 * nb, dtype=torch.float64, device=device)
         _lib.check(lib.psb200_drain_stats(h_, dev.ptr(dt), dev.ptr(im_u8), dev.ptr(pc_d), *fnargs, dev.ptr(part), nb,
                                           dev.stream_ptr()))

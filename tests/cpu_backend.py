@@ -49,6 +49,11 @@ class CpuBackend:
             h = np.concatenate(blocks)
         return torch.from_numpy(h.reshape(-1).view(np.int32).copy())
 
+    def edt_ext(self, ext_u8, shape_ext, lo, nzl):
+        nze, ny, nx = shape_ext
+        d2 = oc.edt_sq(ext_u8.numpy().reshape(shape_ext))[lo:lo + nzl]
+        return torch.from_numpy(d2.reshape(-1).view(np.int32).copy()), int(d2.max()) if d2.size else 0
+
     # psb200_edt_z_u32: out[z] = min_z' h[z'] + (z - z')^2
     def edt_z(self, h, shape):
         nz, ny, nx = shape
@@ -86,6 +91,13 @@ class CpuBackend:
     def pack(self, cls, k, out_bits, shape):
         bits = np.packbits(cls.numpy() <= k, bitorder="little")
         out_bits.numpy().view(np.uint8)[:] = bits
+
+    PACKN = 3
+
+    def packn(self, cls, k0, nk, out_bits, vol_words, shape):
+        n = cls.numel() // 32
+        for i in range(nk):
+            self.pack(cls, k0 + i, out_bits[i * vol_words:i * vol_words + n], shape)
 
     def wmask(self, idx, written, shape):
         written.numpy().view(np.uint8)[:] = np.packbits(idx.numpy() != 0, bitorder="little")

@@ -25,11 +25,17 @@ def run_cases(ctx, rank, world, cases, verbose=True):
         job = ShardedVolume(shape, ctx)
         job.backend.bit_tmax = bit_tmax
         sl = job.local_slice()
-        d2, mx = job.edt_sq(job.backend.to_u8(im[sl]))
         want = oc.edt_sq(im)
-        assert mx == int(want.max()), (mx, int(want.max()))
-        got = d2.cpu().numpy().view(np.uint32).reshape(want[sl].shape)
-        assert np.array_equal(got, want[sl]), f"rank {rank}: sharded edt differs {shape}"
+        # all-to-all transposes (halo 0), the input-halo fast path (16 planes: deeper than every distance here)
+        # and its fallback (2 planes: the exactness bound fails)
+        for halo in (0, 2, 16):
+            job.edt_halo = halo
+            d2, mx = job.edt_sq(job.backend.to_u8(im[sl]))
+            path = "halo" if world > 1 and 0 < halo <= min(job.zcounts) and int(want.max()) < (halo + 1) ** 2 else "all-to-all"
+            assert job.edt_path == path, (halo, job.edt_path, path)
+            assert mx == int(want.max()), (mx, int(want.max()))
+            got = d2.cpu().numpy().view(np.uint32).reshape(want[sl].shape)
+            assert np.array_equal(got, want[sl]), f"rank {rank}: sharded edt differs {shape} halo={halo}"
         assert np.array_equal(job.edt(im[sl]).cpu().numpy(), oc.edt(im)[sl]), "edt float"
         lt = job.local_thickness(im[sl], sizes=sizes).cpu().numpy()
         ref = oc.local_thickness(im, sizes=sizes, mode="dt")

@@ -31,11 +31,17 @@ def _worker(rank, world, port, shape, sizes, bit_tmax, errq):
         im = oc.blobs(list(shape), porosity=0.6, blobiness=1.5, seed=3)
         job = ShardedVolume(shape, backend=CpuBackend(bit_tmax=bit_tmax))
         sl = job.local_slice()
-        # EDT through both all-to-all transposes
-        d2, mx = job.edt_sq(job.backend.to_u8(im[sl]))
+        # EDT through both all-to-all transposes (edt_halo = 0), through the input-halo fast path (halo deeper than
+        # the largest distance) and through its fallback (halo too shallow: the bound fails, all-to-all runs)
         want = oc.edt_sq(im)
-        assert mx == int(want.max()), (mx, int(want.max()))
-        assert np.array_equal(d2.numpy().view(np.uint32).reshape(want[sl].shape), want[sl]), "edt slab"
+        deep = min(job.zcounts)
+        for halo in (0, 1, deep):
+            path = "halo" if halo > 0 and int(want.max()) < (halo + 1) ** 2 else "all-to-all"
+            job.edt_halo = halo
+            d2, mx = job.edt_sq(job.backend.to_u8(im[sl]))
+            assert job.edt_path == path, (halo, job.edt_path, path)
+            assert mx == int(want.max()), (mx, int(want.max()))
+            assert np.array_equal(d2.numpy().view(np.uint32).reshape(want[sl].shape), want[sl]), f"edt slab halo={halo}"
         assert np.array_equal(job.edt(im[sl]).numpy(), oc.edt(im)[sl]), "edt float"
         # radius loop with halo exchange (byte and bit pipelines)
         lt = job.local_thickness(im[sl], sizes=sizes).numpy()
