@@ -440,16 +440,18 @@ class ShardedVolume:
         return out.view(self.nzl, self.shape[1], self.shape[2])
 
     # --------------------------------------------------------------------- radius loop
-    def local_thickness(self, local_im, sizes=25, to_host=False):
+    def local_thickness(self, local_im, sizes=25, to_host=False, as_index=False):
         """ps.filters.local_thickness of the GLOBAL volume; returns this rank's slab (float64):
-        a device tensor, or with `to_host` a numpy array (the reference's return type)."""
-        return self._porosimetry(local_im, sizes, access_limited=False, to_host=to_host)
+        a device tensor, or with `to_host` a numpy array (the reference's return type).  `as_index`: the slab in
+        index form instead, (uint8 device tensor, float64 table): map = table[index] (sizemap.IndexMap layout)."""
+        return self._porosimetry(local_im, sizes, access_limited=False, to_host=to_host, as_index=as_index)
 
-    def porosimetry(self, local_im, sizes=25, inlets=None, access_limited=True, to_host=False):
+    def porosimetry(self, local_im, sizes=25, inlets=None, access_limited=True, to_host=False, as_index=False):
         """ps.filters.porosimetry of the GLOBAL volume (F:1032-1212); returns this rank's slab.
         `inlets`: None = all faces of the global volume (F:1128-1129), else this rank's slab
         [nzl][ny][nx] of the global inlet mask."""
-        return self._porosimetry(local_im, sizes, access_limited=access_limited, inlets=inlets, to_host=to_host)
+        return self._porosimetry(local_im, sizes, access_limited=access_limited, inlets=inlets, to_host=to_host,
+                                 as_index=as_index)
 
     def _flood_exchange(self, st, k):
         """Propagate inlet connectivity through the slab faces until no rank learns anything new
@@ -473,7 +475,7 @@ class ShardedVolume:
             if not self._allreduce_max(be.uf_changed(st)):
                 return sweeps
 
-    def _porosimetry(self, local_im, sizes, access_limited, inlets=None, to_host=False):
+    def _porosimetry(self, local_im, sizes, access_limited, inlets=None, to_host=False, as_index=False):
         torch, be = self.torch, self.backend
         nz, ny, nx = self.shape
         nzl = self.nzl
@@ -587,6 +589,8 @@ class ShardedVolume:
                 be.lt_z(reach, m_lo, m_hi, idx, k, Tk, lshape)
                 del reach
         lut = np.concatenate([[0.0], R])
+        if as_index:
+            return idx, lut
         if to_host and hasattr(be, "expand_to_host"):
             return be.expand_to_host(idx, lut, lshape, self.world)
         return be.expand(idx, lut).view(*lshape)
