@@ -100,6 +100,11 @@ int psb200_edt_sq_u8(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2_out,
 int psb200_edt_u8(psb200_ctx *ctx, const uint8_t *in, void *out, int out_kind,
                   uint32_t *max_out, int64_t nz, int64_t ny, int64_t nx,
                   void *ws, size_t ws_bytes, psb200_stream stream);
+/* The same, with *max_out taken over the planes [zmax0, zmax1) only: a z-slab shard runs the transform on its slab
+ * plus input halo planes, but the maximum that defines the radii (F:1132) is the one of its own planes. */
+int psb200_edt_u8_zmax(psb200_ctx *ctx, const uint8_t *in, void *out, int out_kind, uint32_t *max_out, int64_t nz,
+                       int64_t ny, int64_t nx, int64_t zmax0, int64_t zmax1, void *ws, size_t ws_bytes,
+                       psb200_stream stream);
 
 /* Single passes of the separable transform, exposed for z-slab sharded volumes
  * (SURVEY 8(e)): x and y passes run on the local slab, the z pass on the pencil

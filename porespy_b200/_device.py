@@ -140,17 +140,22 @@ def upload_mask(ctx, a):
     return out
 
 
-def edt_run(ctx, im_u8, shape, as_f32=False, want_max=False):
+def edt_run(ctx, im_u8, shape, as_f32=False, want_max=False, zmax=None):
     """uint8 device volume -> (uint32 squared distances | float32 distances, max d2 or None).
-    One call of psb200_edt_u8: sqrt and max are fused into the last pass."""
+    One call of psb200_edt_u8: sqrt and max are fused into the last pass.  `zmax = (z0, z1)`: the maximum
+    over those planes only (psb200_edt_u8_zmax)."""
     torch = _torch()
     nz, ny, nx = shape3(shape)
     out = torch.empty(nz * ny * nx, dtype=torch.float32 if as_f32 else torch.int32, device=im_u8.device)
     mx = torch.empty(1, dtype=torch.int32, device=im_u8.device) if want_max else None
     nbytes = ctx.lib.psb200_edt_workspace_bytes(ctx.handle, nz, ny, nx)
     ws = ctx.workspace(nbytes)
-    _lib.check(ctx.lib.psb200_edt_u8(ctx.handle, ptr(im_u8), ptr(out), 1 if as_f32 else 0, ptr(mx),
-                                     nz, ny, nx, ptr(ws), ws.numel(), stream_ptr()))
+    if zmax is None:
+        _lib.check(ctx.lib.psb200_edt_u8(ctx.handle, ptr(im_u8), ptr(out), 1 if as_f32 else 0, ptr(mx),
+                                         nz, ny, nx, ptr(ws), ws.numel(), stream_ptr()))
+    else:
+        _lib.check(ctx.lib.psb200_edt_u8_zmax(ctx.handle, ptr(im_u8), ptr(out), 1 if as_f32 else 0, ptr(mx),
+                                              nz, ny, nx, int(zmax[0]), int(zmax[1]), ptr(ws), ws.numel(), stream_ptr()))
     if want_max:
         return out, int(mx.cpu().numpy().view(np.uint32)[0])
     return out, None

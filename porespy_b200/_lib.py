@@ -62,6 +62,7 @@ SIGNATURES = {
     "psb200_edt_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
     "psb200_edt_sq_u8": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_edt_u8": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "psb200_edt_u8_zmax": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_edt_xy_u8": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_edt_z_u32": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i64, _vp]),
     "psb200_edt_pass": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),

@@ -68,6 +68,8 @@ __device__ __forceinline__ uint4 mp_load_row(const typename Src::T *row, int x, 
 // slab -> pencil all-to-all, so no separate pack pass is needed.
 // grid.x = ceil(nxc/128) * ceil(n/L)  (row tiles fastest: neighbours share halo rows in L2).
 // OUT 0: uint32 squared distance (PSB_INF when infinite); OUT 1: float32 sqrt (edt.edt's result).
+// gmax (optional) receives the maximum over the rows [mrow0, mrow1) of the pass axis only (a z-slab shard
+// computes on its slab plus halo planes, but the maximum that sets the radii is the one of its own planes).
 #define MP_R 4                 // rows per lane: a lane owns a 4 (rows) x 4 (columns) block of outputs
 
 __device__ __forceinline__ void mp_relax(uint4 &b, const uint4 &u, uint32_t d2)
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(MP_WARPS * 32)
 edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ dst, int n,
                    int64_t rstride, int64_t nxc, int64_t ostride, int L, int H, int vec,
                    uint32_t *__restrict__ gmax, int split, const int *__restrict__ gate,
-                   int64_t tiles_x, int nouter)
+                   int64_t tiles_x, int nouter, int mrow0, int mrow1)
 {
     if (gate && *gate == 0) return;        // the 16-bit form of the pass (below) resolved every voxel
     extern __shared__ uint4 mp_tile[];                     // [roundup4(L) + 2H][32]
@@ -202,7 +204,7 @@ edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ d
             const uint32_t o[4] = {B[i].x, B[i].y, B[i].z, B[i].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (xl + j < valid) lmax = max(lmax, o[j]);
+                if (xl + j < valid && g >= mrow0 && g < mrow1) lmax = max(lmax, o[j]);
             if (OUT == 0) {
                 // infinite values stay >= MP_INF here; edt_fix_inf_kernel maps them to PSB_INF
                 // afterwards, and only when the running max says there are any
@@ -260,7 +262,7 @@ template <typename Src, int OUT, int FOOT>
 __global__ void __launch_bounds__(MP16_WARPS * 32, 4)
 edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__ dst, int n,
                      int64_t rstride, int64_t nxc, int64_t ostride, int L, int H, int vec,
-                     uint32_t *__restrict__ gmax, int split, int *__restrict__ overflow)
+                     uint32_t *__restrict__ gmax, int split, int *__restrict__ overflow, int mrow0, int mrow1)
 {
     extern __shared__ uint4 mp16_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
@@ -398,7 +400,7 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (xl + j < valid) {
-                    lmax = max(lmax, o[j]);
+                    if (g >= mrow0 && g < mrow1) lmax = max(lmax, o[j]);
                     ovf |= o[j] >= MP16_CAP;
                 }
             if (OUT == 0) {

@@ -343,7 +343,8 @@ static bool ntiles_check(int64_t gx, int64_t nouter) { return gx > 0 && nouter >
 // bounded min-plus pass along y (axis 1) or z (axis 0); out_kind 0: u32 squared, 1: f32 sqrt
 template <typename Src>
 static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src, void *dst, int out_kind,
-                          uint32_t *gmax, int64_t nz, int64_t ny, int64_t nx, cudaStream_t st, int split = 0)
+                          uint32_t *gmax, int64_t nz, int64_t ny, int64_t nx, cudaStream_t st, int split = 0,
+                          int mrow0 = 0, int mrow1 = 0x7FFFFFFF)
 {
     const int64_t plane = ny * nx;
     int n;
@@ -379,13 +380,13 @@ static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src,
         {
             ProfScope ps__(ctx, st, axis == 1 ? K_EDT_Y : K_EDT_Z);
             if (out_kind == 0 && !ctx->foot)
-                edt_minplus16_kernel<Src, 0, 0><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
+                edt_minplus16_kernel<Src, 0, 0><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf, mrow0, mrow1);
             else if (out_kind == 0)
-                edt_minplus16_kernel<Src, 0, 1><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
+                edt_minplus16_kernel<Src, 0, 1><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf, mrow0, mrow1);
             else if (!ctx->foot)
-                edt_minplus16_kernel<Src, 1, 0><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
+                edt_minplus16_kernel<Src, 1, 0><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf, mrow0, mrow1);
             else
-                edt_minplus16_kernel<Src, 1, 1><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf);
+                edt_minplus16_kernel<Src, 1, 1><<<grid16, MP16_WARPS * 32, smem16, st>>>(src, dst, n, rstride, nxc, ostride, L16, H16, vec, gmax, split, ovf, mrow0, mrow1);
         }
         LAUNCH_CHECK(ctx);
         gate = ovf;
@@ -393,9 +394,9 @@ static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src,
     {
         ProfScope ps__(ctx, st, axis == 1 ? K_EDT_Y : K_EDT_Z);
         if (out_kind == 0)
-            edt_minplus_kernel<Src, 0><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax, split, gate, gx, (int)nouter);
+            edt_minplus_kernel<Src, 0><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax, split, gate, gx, (int)nouter, mrow0, mrow1);
         else
-            edt_minplus_kernel<Src, 1><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax, split, gate, gx, (int)nouter);
+            edt_minplus_kernel<Src, 1><<<grid, MP_WARPS * 32, smem, st>>>(src, dst, n, rstride, nxc, ostride, L, H, vec, gmax, split, gate, gx, (int)nouter, mrow0, mrow1);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
@@ -414,7 +415,8 @@ static int launch_fix_inf(psb200_ctx *ctx, void *out, int out_kind, uint32_t *gm
 }
 
 static int edt_fast(psb200_ctx *ctx, const uint8_t *in, void *out, int out_kind, uint32_t *gmax,
-                    int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes, cudaStream_t st)
+                    int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes, cudaStream_t st,
+                    int zmax0 = 0, int zmax1 = 0x7FFFFFFF)
 {
     const size_t n = (size_t)nz * ny * nx;
     char *base = ws ? (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
@@ -431,7 +433,7 @@ static int edt_fast(psb200_ctx *ctx, const uint8_t *in, void *out, int out_kind,
     else {
         rc = launch_minplus<MpSrcU16>(ctx, 1, dx, mid, 0, nullptr, nz, ny, nx, st);
         if (rc) return rc;
-        rc = launch_minplus<MpSrcU32>(ctx, 0, mid, out, out_kind, gmax, nz, ny, nx, st);
+        rc = launch_minplus<MpSrcU32>(ctx, 0, mid, out, out_kind, gmax, nz, ny, nx, st, 0, zmax0, zmax1);
     }
     if (rc) return rc;
     return launch_fix_inf(ctx, out, out_kind, gmax, (int64_t)n, st);
@@ -467,7 +469,18 @@ extern "C" int psb200_edt_u8(psb200_ctx *ctx, const uint8_t *in, void *out, int 
                              uint32_t *max_out, int64_t nz, int64_t ny, int64_t nx, void *ws,
                              size_t ws_bytes, psb200_stream stream)
 {
+    return psb200_edt_u8_zmax(ctx, in, out, out_kind, max_out, nz, ny, nx, 0, nz, ws, ws_bytes, stream);
+}
+
+extern "C" int psb200_edt_u8_zmax(psb200_ctx *ctx, const uint8_t *in, void *out, int out_kind,
+                                  uint32_t *max_out, int64_t nz, int64_t ny, int64_t nx, int64_t zmax0, int64_t zmax1,
+                                  void *ws, size_t ws_bytes, psb200_stream stream)
+{
     if (!ctx || !in || !out) return fail(PSB200_ERR_INVALID, "edt_u8: NULL argument");
+    if (zmax0 < 0 || zmax1 > nz || zmax0 > zmax1) return fail(PSB200_ERR_INVALID, "edt_u8_zmax: plane range outside [0, nz]");
+    const bool ranged = !(zmax0 == 0 && zmax1 == nz);
+    if (ranged && (nz == 1 || ctx->algo == PSB200_ALGO_GENERIC))
+        return fail(PSB200_ERR_UNSUPPORTED, "edt_u8_zmax: a plane range needs a 3-D volume and the fast algorithm");
     if (out_kind != 0 && out_kind != 1) return fail(PSB200_ERR_INVALID, "edt_u8: out_kind must be 0 (u32 d2) or 1 (f32)");
     int rc = check_dims("edt_u8", nz, ny, nx);
     if (rc) return rc;
@@ -488,7 +501,7 @@ extern "C" int psb200_edt_u8(psb200_ctx *ctx, const uint8_t *in, void *out, int 
         if (out_kind == 1) return psb200_sqrt_f32(ctx, d2, reinterpret_cast<float *>(out), n, stream);
         return PSB200_OK;
     }
-    return edt_fast(ctx, in, out, out_kind, max_out, nz, ny, nx, ws, ws_bytes, st);
+    return edt_fast(ctx, in, out, out_kind, max_out, nz, ny, nx, ws, ws_bytes, st, (int)zmax0, (int)zmax1);
 }
 
 extern "C" int psb200_edt_sq_u8(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2, int64_t nz,

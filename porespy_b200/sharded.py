@@ -90,9 +90,11 @@ class CudaBackend:
         """Exact EDT of the extended slab (own planes plus input halo planes), one-GPU kernels; returns the own
         planes [lo, lo + nzl) as a flat int32 tensor and their maximum."""
         nze, ny, nx = shape_ext
-        d2e, _ = dev.edt_run(self.ctx, ext_u8, shape_ext)
-        own = d2e[lo * ny * nx:(lo + nzl) * ny * nx]
-        return own, dev.max_u32(self.ctx, own)
+        if nze == 1:
+            d2e, mx = dev.edt_run(self.ctx, ext_u8, shape_ext, want_max=True)
+        else:
+            d2e, mx = dev.edt_run(self.ctx, ext_u8, shape_ext, want_max=True, zmax=(lo, lo + nzl))
+        return d2e[lo * ny * nx:(lo + nzl) * ny * nx], mx
 
     # -- per-radius steps
     def classify(self, d2, T):

@@ -115,7 +115,6 @@ def main():
             @staticmethod
             def local_thickness(im_, sizes=25, as_index=True):
                 m = psb.local_thickness_index(im_, sizes=sizes)
-                One.last_max_d2 = int(round(float(m.values.max()) ** 2)) if One.last_max_d2 is None else One.last_max_d2
                 return m.idx, m.values
 
             @staticmethod
@@ -142,14 +141,18 @@ def main():
                  voxels_per_s=nvox / (min(times[1:] or times) * 1e-3), flood_sweeps_per_radius=getattr(job, "flood_sweeps", None)))
         del idx
     if "cfg3" in what:
-        # max dt of the global image: the largest radius of a sizes=2 run is 10**log10(max dt)
-        _, lut2 = run.local_thickness(im, sizes=2, as_index=True)
-        dmax = float(np.max(lut2))
+        if world > 1:
+            job.local_thickness(im, sizes=2, as_index=True)
+            max_d2 = job.last_max_d2
+        else:
+            from porespy_b200 import _device as pdev
+            _, max_d2 = pdev.edt_run(ctx, im.reshape(-1), shape, want_max=True)
+        dmax = float(np.sqrt(np.float32(max_d2)))
         sizes = np.linspace(1, dmax, 100)
         times, (idx, lut) = timed(lambda: run.local_thickness(im, sizes=sizes, as_index=True), max(2, args.reps - 1))
         shas["cfg3"] = gather_sha(idx)
         say(dict(base, workload="local_thickness(sizes=linspace(1, max dt, 100)), index form", ms=[round(t, 2) for t in times],
-                 voxels_per_s=nvox / (min(times[1:] or times) * 1e-3), effective_radii=len(lut) - 1))
+                 voxels_per_s=nvox / (min(times[1:] or times) * 1e-3), effective_radii=len(lut) - 1, max_d2=int(max_d2)))
         del idx
     if args.sha_out and rank == 0:
         with open(args.sha_out, "w") as f:
