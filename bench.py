@@ -477,6 +477,23 @@ def run_ours(args):
     im_page = np.array(im_host, copy=True)                 # ordinary (pageable) numpy memory
     tp, per_call_p, _ = time_e2e(im_page)
     del im_page
+    # the same call for consumers of the INDEX form (pore_size_distribution, size_to_satn, ... on the device:
+    # porespy_b200.sizemap): numpy in, pore-size distribution out, no float64 map anywhere
+    idx_form = None
+    if world == 1:
+        def step_psd():
+            m = psb.local_thickness_index(im_host, sizes=SIZES)
+            return psb.metrics.pore_size_distribution(m, bins=10)
+        step_psd()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            step_psd()
+        torch.cuda.synchronize()
+        ti = (time.perf_counter() - t0) / n_e2e
+        idx_form = {"value": nvox / ti, "ms_per_step": ti * 1e3,
+                    "api": "porespy_b200.local_thickness_index(numpy bool) -> IndexMap -> metrics.pore_size_distribution",
+                    "note": "numpy volume in, pore-size distribution out; the radius map stays on the device as 1 B/voxel"}
     api = ("porespy_b200.filters.local_thickness(numpy bool, page-locked) -> numpy float64" if world == 1 else
            "ShardedVolume.local_thickness(numpy bool slab, page-locked, to_host=True) -> numpy float64 slab, every rank")
     e2e = {"value": nvox / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -485,6 +502,7 @@ def run_ours(args):
            "pageable_input": {"value": nvox / tp, "ms_per_step": tp * 1e3,
                               "ms_per_call": [round(t * 1e3, 1) for t in per_call_p],
                               "note": "the same call with the volume in ordinary (pageable) numpy memory"},
+           "index_form": idx_form,
            "input": (f"numpy bool volume of {im_host.nbytes * world} bytes in host memory, packed to bits by the library's host "
                      f"threads before the upload (psb200_upload_mask_u8)" if packed else "numpy bool volume, uploaded as bytes"),
            "result": f"float64 map of {im_host.size * 8 * world} bytes in host memory; {pdev.HOST_WIDEN_PERMILLE / 10:.0f} % of "

@@ -60,34 +60,46 @@ lt_pack_kernel(const uint8_t *__restrict__ cls, uint32_t *__restrict__ bits, int
 // handful of bitwise operations per radius on whole words (a most-significant-bit-first comparator) instead
 // of a byte-SWAR compare per radius and per 4 voxels.  bits of radius k0 + i go to bits + i * vol_words.
 #define PACKN_MAX 16
+// NB = number of low bit planes the comparator looks at (the largest radius index of the call is < 2^NB);
+// a compile-time constant so that the planes stay in registers and the loops unroll without predicates.
+template <int NB>
 __global__ void __launch_bounds__(256)
 lt_packn_kernel(const uint8_t *__restrict__ cls, uint32_t *__restrict__ bits, int64_t nwords, int64_t vol_words,
-                int k0, int nk, int nb)
+                int k0, int nk)
 {
-    const uint32_t hn = nb < 8 ? (1u << nb) : 0u;                       // "high" bytes are >= 2^nb
-    const uint32_t hl4 = (hn & 0x7Fu) * 0x01010101u, hsel = hn < 128u ? 0xFFFFFFFFu : 0u;
+    constexpr uint32_t hn = NB < 8 ? (1u << NB) : 0u;                   // "high" bytes are >= 2^NB
+    constexpr uint32_t hl4 = (hn & 0x7Fu) * 0x01010101u, hsel = hn < 128u ? 0xFFFFFFFFu : 0u;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += step) {
         const uint4 a = __ldg(reinterpret_cast<const uint4 *>(cls) + 2 * w);
         const uint4 b = __ldg(reinterpret_cast<const uint4 *>(cls) + 2 * w + 1);
         const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t p[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, hi = 0u;
+        uint32_t p[NB], hi = 0u;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int j = 0; j < NB; ++j) {
+            uint32_t pj = 0u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < nb) p[j] |= (((((v[q] >> j) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * q);
-            if (nb < 8) hi |= gather_bit7(swar_ge(v[q], hl4, hsel)) << (4 * q);
+            for (int q = 0; q < 8; q += 2) {
+                // bit j of the 8 bytes of (v[q], v[q+1]) -> one byte: the multiply moves the bits at positions
+                // 0,8,16,24 (v[q]) and 4,12,20,28 (v[q+1], pre-shifted by 4) to 24..31 without carries
+                const uint32_t t = ((v[q] >> j) & 0x01010101u) | (((v[q + 1] >> j) & 0x01010101u) << 4);
+                pj |= ((t * 0x01020408u) >> 24) << (4 * q);
+            }
+            p[j] = pj;
+        }
+        if (NB < 8) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) hi |= gather_bit7(swar_ge(v[q], hl4, hsel)) << (4 * q);
         }
         for (int i = 0; i < nk; ++i) {
             const uint32_t k = (uint32_t)(k0 + i);
             uint32_t lt = 0u, eq = 0xFFFFFFFFu;
 #pragma unroll
-            for (int j = 7; j >= 0; --j)
-                if (j < nb) {
-                    if ((k >> j) & 1u) { lt |= eq & ~p[j]; eq &= p[j]; }
-                    else eq &= ~p[j];
-                }
+            for (int j = NB - 1; j >= 0; --j) {
+                const uint32_t m = 0u - ((k >> j) & 1u);                 // all ones where bit j of k is set (uniform)
+                lt |= eq & ~p[j] & m;
+                eq &= ~(p[j] ^ m);
+            }
             bits[(int64_t)i * vol_words + w] = (lt | eq) & ~hi;
         }
     }

@@ -959,6 +959,16 @@ static int lt_wmask_impl(psb200_ctx *ctx, const uint8_t *idx, uint32_t *written,
     return PSB200_OK;
 }
 
+static void launch_packn(const uint8_t *cmap, uint32_t *bits, int64_t nwords, int64_t vol_words, int k0, int nk, int grid,
+                         cudaStream_t st)
+{
+    const int kmax = k0 + nk - 1;
+    if (kmax < 32) lt_packn_kernel<5><<<grid, 256, 0, st>>>(cmap, bits, nwords, vol_words, k0, nk);
+    else if (kmax < 64) lt_packn_kernel<6><<<grid, 256, 0, st>>>(cmap, bits, nwords, vol_words, k0, nk);
+    else if (kmax < 128) lt_packn_kernel<7><<<grid, 256, 0, st>>>(cmap, bits, nwords, vol_words, k0, nk);
+    else lt_packn_kernel<8><<<grid, 256, 0, st>>>(cmap, bits, nwords, vol_words, k0, nk);
+}
+
 // One radius of the bit path.  Thresholds descend, so every radius after the first bit radius takes the
 // bit path too: the seed bits of radii k .. k + PACKN_MAX - 1 are packed together from one read of the class
 // map (lt_packn_kernel).  `packed_lo/hi`: the radii whose seed bits sit in w.seedbits.
@@ -969,13 +979,10 @@ static int lt_bit_step(psb200_ctx *ctx, LtWorkspace &w, const uint8_t *cmap, uin
     const int64_t nwords = nz * ny * nx / 32;
     if (k < packed_lo || k >= packed_hi) {
         const int nk = nT - k < PACKN_MAX ? nT - k : PACKN_MAX;
-        int nb = 1;
-        while (nb < 8 && (k + nk - 1) >> nb) ++nb;
         {
             ProfScope ps__(ctx, st, K_LT_PACK);
             // not gated: the buffers must be valid at the later radii even if radius k is still before the breakthrough
-            lt_packn_kernel<<<grid_for(nwords, 256, ctx->sm_count, 8), 256, 0, st>>>(cmap, w.seedbits, nwords,
-                                                                                  (int64_t)w.seed_words, k, nk, nb);
+            launch_packn(cmap, w.seedbits, nwords, (int64_t)w.seed_words, k, nk, grid_for(nwords, 256, ctx->sm_count, 8), st);
         }
         LAUNCH_CHECK(ctx);
         packed_lo = k;
@@ -1016,11 +1023,9 @@ extern "C" int psb200_lt_packn(psb200_ctx *ctx, const uint8_t *cls, int k0, int 
     if (vol_words < nwords || (vol_words & 3)) return fail(PSB200_ERR_INVALID, "lt_packn: vol_words must be >= the words of one volume and a multiple of 4");
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    int nb = 1;
-    while (nb < 8 && (k0 + nk - 1) >> nb) ++nb;
     {
         ProfScope ps__(ctx, st, K_LT_PACK);
-        lt_packn_kernel<<<grid_for(nwords, 256, ctx->sm_count, 8), 256, 0, st>>>(cls, bits, nwords, vol_words, k0, nk, nb);
+        launch_packn(cls, bits, nwords, vol_words, k0, nk, grid_for(nwords, 256, ctx->sm_count, 8), st);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;

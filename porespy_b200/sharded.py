@@ -317,6 +317,7 @@ class ShardedVolume:
             gen.gauss_axis(ctx, a, b, 0, sigma[0], (nzl, ny, nx), z_out0=z0, z_in0=lo, nz_in=hi - lo, nz_glob=nz)
         else:
             b.copy_(a[(z0 - lo) * plane:(z0 - lo + nzl) * plane])
+        del a                                   # (the noise planes: at 2048^3 on one GPU they are 64 GiB)
         a = torch.empty_like(b)
         for axis in (1, 2):
             if float(sigma[axis]) > 1e-15:
