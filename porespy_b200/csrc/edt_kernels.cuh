@@ -120,8 +120,9 @@ struct EdtStoreFill {
 template <typename Store>
 __global__ void __launch_bounds__(128)
 edt_col_kernel(const uint32_t *in, Store store, int64_t ncols, int64_t inner,
-               int64_t outer, int64_t stride, int n, uint2 *stk)   // in may alias store.out (in place)
+               int64_t outer, int64_t stride, int n, uint2 *stk, const int *gate = nullptr)   // in may alias store.out (in place)
 {
+    if (gate && *gate == 0) return;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint2 *mystk = stk + tid;
@@ -186,8 +187,9 @@ edt_col_kernel(const uint32_t *in, Store store, int64_t ncols, int64_t inner,
 }
 
 // ---------------------------------------------------------------------------- pointwise
-__global__ void sqrt_f32_kernel(const uint32_t *__restrict__ d2, float *__restrict__ out, int64_t n)
+__global__ void sqrt_f32_kernel(const uint32_t *d2, float *out, int64_t n, const int *gate = nullptr)   // may run in place
 {
+    if (gate && *gate == 0) return;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
         uint32_t v = d2[i];
@@ -195,8 +197,10 @@ __global__ void sqrt_f32_kernel(const uint32_t *__restrict__ d2, float *__restri
     }
 }
 
-__global__ void max_u32_kernel(const uint32_t *__restrict__ d2, int64_t n, uint32_t *__restrict__ out)
+__global__ void max_u32_kernel(const uint32_t *__restrict__ d2, int64_t n, uint32_t *__restrict__ out,
+                               const int *gate = nullptr)
 {
+    if (gate && *gate == 0) return;
     uint32_t m = 0;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
@@ -212,4 +216,26 @@ fill_from_d2_kernel(const uint32_t *__restrict__ d2, EdtStoreFill store, int64_t
 {
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) store(i, d2[i]);
+}
+
+
+// ---- pieces of the gated envelope fallback of the fast EDT (psb200.cu edt_fast): uint16 x-distances ->
+// uint32 squared distances (PSB_INF: no site in the line), and a gated copy
+__global__ void __launch_bounds__(256)
+sq16_to_u32_kernel(const uint16_t *__restrict__ dx, uint32_t *__restrict__ out, int64_t n, const int *__restrict__ gate)
+{
+    if (gate && *gate == 0) return;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const uint32_t d = dx[i];
+        out[i] = d >= 0x8000u ? PSB_INF : d * d;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+copy_u32_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int64_t n, const int *__restrict__ gate)
+{
+    if (gate && *gate == 0) return;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) dst[i] = src[i];
 }

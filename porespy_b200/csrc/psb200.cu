@@ -272,9 +272,8 @@ extern "C" size_t psb200_edt_workspace_bytes(const psb200_ctx *ctx, int64_t nz, 
 {
     if (!ctx) return 0;
     const size_t n = (size_t)nz * ny * nx;
-    size_t fast = align256(n * 2) + align256(n * 4) + 512;
-    size_t fh = stack_bytes(ctx, nz, ny) + 512;
-    return fast > fh ? fast : fh;
+    // fast path: uint16 x-distances, uint32 y-pass result, the scalar, and the stacks of its envelope fallback
+    return align256(n * 2) + align256(n * 4) + 256 + align256(stack_bytes(ctx, nz, ny)) + 1024;
 }
 
 template <int SITE_MODE>
@@ -298,7 +297,7 @@ static int launch_x(psb200_ctx *ctx, const uint8_t *in, uint32_t *d2, int64_t nl
 template <typename Store>
 static int launch_col(psb200_ctx *ctx, int axis, const uint32_t *src, Store store, int64_t nz,
                       int64_t ny, int64_t nx, void *ws, size_t ws_bytes, cudaStream_t st,
-                      int prof_kid = -1)
+                      int prof_kid = -1, const int *gate = nullptr)
 {
     if (prof_kid < 0) prof_kid = axis == 1 ? K_FH_Y : K_FH_Z;
     const int64_t plane = ny * nx;
@@ -314,7 +313,7 @@ static int launch_col(psb200_ctx *ctx, int axis, const uint32_t *src, Store stor
     {
         ProfScope ps__(ctx, st, prof_kid);
         edt_col_kernel<Store><<<grid, COL_BLOCK, 0, st>>>(src, store, ncols, inner, outer, stride, n,
-                                                          reinterpret_cast<uint2 *>(ws));
+                                                          reinterpret_cast<uint2 *>(ws), gate);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
@@ -344,8 +343,10 @@ static bool ntiles_check(int64_t gx, int64_t nouter) { return gx > 0 && nouter >
 template <typename Src>
 static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src, void *dst, int out_kind,
                           uint32_t *gmax, int64_t nz, int64_t ny, int64_t nx, cudaStream_t st, int split = 0,
-                          int mrow0 = 0, int mrow1 = 0x7FFFFFFF)
+                          int mrow0 = 0, int mrow1 = 0x7FFFFFFF, int **ovf_out = nullptr)
 {
+    // ovf_out != nullptr: the caller provides the fallback for overflowed 16-bit passes itself (edt_fast: the
+    // lower-envelope kernels, whose cost does not depend on the distances); *ovf_out = the device flag
     const int64_t plane = ny * nx;
     int n;
     int64_t rstride, nxc, ostride, nouter;
@@ -390,7 +391,9 @@ static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src,
         }
         LAUNCH_CHECK(ctx);
         gate = ovf;
+        if (ovf_out) { *ovf_out = ovf; return PSB200_OK; }
     }
+    if (ovf_out) *ovf_out = nullptr;
     {
         ProfScope ps__(ctx, st, axis == 1 ? K_EDT_Y : K_EDT_Z);
         if (out_kind == 0)
@@ -414,26 +417,83 @@ static int launch_fix_inf(psb200_ctx *ctx, void *out, int out_kind, uint32_t *gm
     return PSB200_OK;
 }
 
+// Gated fallback of one overflowed 16-bit pass: the lower-envelope kernel on uint32 data in place.  A pass overflows
+// when some squared distance along the axes done so far reaches 32767 (181 voxels) -- never on porous media, but a
+// volume with a single background voxel has distances of a thousand voxels, and a bounded min-plus scan (O(distance)
+// per voxel, from global memory beyond the staged halo) then takes seconds where the envelope (O(1) per voxel)
+// takes tens of milliseconds.  Every kernel below returns at once when *ovf == 0.
+static int edt_envelope_fallback(psb200_ctx *ctx, int axis, uint32_t *data, void *out, int out_kind, uint32_t *gmax,
+                                 int64_t nz, int64_t ny, int64_t nx, int zmax0, int zmax1, bool last, void *stk,
+                                 size_t stk_bytes, const int *ovf, cudaStream_t st)
+{
+    const int64_t n = nz * ny * nx, plane = ny * nx;
+    int rc = launch_col(ctx, axis, data, EdtStoreU32{data}, nz, ny, nx, stk, stk_bytes, st, axis == 1 ? K_EDT_Y : K_EDT_Z, ovf);
+    if (rc || !last) return rc;
+    const int g = grid_for(n, 256, ctx->sm_count, 16);
+    if (gmax) {
+        const int64_t z0 = nz > 1 ? zmax0 : 0, z1 = nz > 1 ? (zmax1 < nz ? zmax1 : nz) : 1;
+        {
+            ProfScope ps__(ctx, st, K_MAX);
+            max_u32_kernel<<<g, 256, 0, st>>>(data + z0 * plane, (z1 - z0) * plane, gmax, ovf);
+        }
+        LAUNCH_CHECK(ctx);
+    }
+    if (out_kind == 1) {
+        ProfScope ps__(ctx, st, K_SQRT);
+        sqrt_f32_kernel<<<g, 256, 0, st>>>(data, reinterpret_cast<float *>(out), n, ovf);
+        LAUNCH_CHECK(ctx);
+    }
+    return PSB200_OK;
+}
+
 static int edt_fast(psb200_ctx *ctx, const uint8_t *in, void *out, int out_kind, uint32_t *gmax,
                     int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes, cudaStream_t st,
                     int zmax0 = 0, int zmax1 = 0x7FFFFFFF)
 {
     const size_t n = (size_t)nz * ny * nx;
     char *base = ws ? (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
-    const size_t need = align256(n * 2) + ((nz > 1) ? align256(n * 4) : 0) + 256;
+    const size_t off_mid = align256(n * 2), off_max = off_mid + ((nz > 1) ? align256(n * 4) : 0), off_stk = off_max + 256;
+    // the envelope fallback serves passes of more than one row; a one-row pass keeps the (trivial) uint32 min-plus one
+    const bool env_y = ctx->edt16 && ny > 1, env_z = ctx->edt16 && nz > 1;
+    const size_t stk_bytes = (env_y || env_z) ? stack_bytes(ctx, nz, ny) : 0;
+    const size_t need = off_stk + stk_bytes + 256;
     if (!base || ws_bytes < need + (size_t)(base - (char *)ws))
         return fail(PSB200_ERR_WORKSPACE, "edt needs %zu workspace bytes, got %zu", need + 256, ws_bytes);
     uint16_t *dx = reinterpret_cast<uint16_t *>(base);
-    uint32_t *mid = reinterpret_cast<uint32_t *>(base + align256(n * 2));
-    if (!gmax) gmax = reinterpret_cast<uint32_t *>(base + align256(n * 2) + ((nz > 1) ? align256(n * 4) : 0));
+    uint32_t *mid = reinterpret_cast<uint32_t *>(base + off_mid);
+    void *stk = base + off_stk;
+    if (!gmax) gmax = reinterpret_cast<uint32_t *>(base + off_max);
     CUDA_TRY(cudaMemsetAsync(gmax, 0, sizeof(uint32_t), st));
+    const int g = grid_for((int64_t)n, 256, ctx->sm_count, 16);
     int rc = launch_xdist<XD_EDT>(ctx, in, dx, nz * ny, (int)nx, 0, 0, nullptr, st);
     if (rc) return rc;
-    if (nz == 1) rc = launch_minplus<MpSrcU16>(ctx, 1, dx, out, out_kind, gmax, nz, ny, nx, st);
-    else {
-        rc = launch_minplus<MpSrcU16>(ctx, 1, dx, mid, 0, nullptr, nz, ny, nx, st);
+    int *ovf = nullptr;
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(out);          // float32 and uint32 have the same size
+    if (nz == 1) {
+        rc = launch_minplus<MpSrcU16>(ctx, 1, dx, out, out_kind, gmax, nz, ny, nx, st, 0, 0, 0x7FFFFFFF, env_y ? &ovf : nullptr);
         if (rc) return rc;
-        rc = launch_minplus<MpSrcU32>(ctx, 0, mid, out, out_kind, gmax, nz, ny, nx, st, 0, zmax0, zmax1);
+        if (ovf) {
+            sq16_to_u32_kernel<<<g, 256, 0, st>>>(dx, out32, (int64_t)n, ovf);
+            LAUNCH_CHECK(ctx);
+            rc = edt_envelope_fallback(ctx, 1, out32, out, out_kind, gmax, nz, ny, nx, 0, 1, true, stk, stk_bytes, ovf, st);
+        }
+    } else {
+        rc = launch_minplus<MpSrcU16>(ctx, 1, dx, mid, 0, nullptr, nz, ny, nx, st, 0, 0, 0x7FFFFFFF, env_y ? &ovf : nullptr);
+        if (rc) return rc;
+        if (ovf) {
+            sq16_to_u32_kernel<<<g, 256, 0, st>>>(dx, mid, (int64_t)n, ovf);
+            LAUNCH_CHECK(ctx);
+            rc = edt_envelope_fallback(ctx, 1, mid, nullptr, 0, nullptr, nz, ny, nx, 0, 0, false, stk, stk_bytes, ovf, st);
+            if (rc) return rc;
+        }
+        ovf = nullptr;
+        rc = launch_minplus<MpSrcU32>(ctx, 0, mid, out, out_kind, gmax, nz, ny, nx, st, 0, zmax0, zmax1, env_z ? &ovf : nullptr);
+        if (rc) return rc;
+        if (ovf) {
+            copy_u32_kernel<<<g, 256, 0, st>>>(mid, out32, (int64_t)n, ovf);
+            LAUNCH_CHECK(ctx);
+            rc = edt_envelope_fallback(ctx, 0, out32, out, out_kind, gmax, nz, ny, nx, zmax0, zmax1, true, stk, stk_bytes, ovf, st);
+        }
     }
     if (rc) return rc;
     return launch_fix_inf(ctx, out, out_kind, gmax, (int64_t)n, st);
