@@ -202,9 +202,11 @@ edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ d
                 oi = ((int64_t)d * split * nouter + (int64_t)by * nyd + yy) * rstride + x0 + xl;
             }
             const uint32_t o[4] = {B[i].x, B[i].y, B[i].z, B[i].w};
+            if (g >= mrow0 && g < mrow1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (xl + j < valid && g >= mrow0 && g < mrow1) lmax = max(lmax, o[j]);
+                for (int j = 0; j < 4; ++j)
+                    if (xl + j < valid) lmax = max(lmax, o[j]);
+            }
             if (OUT == 0) {
                 // infinite values stay >= MP_INF here; edt_fix_inf_kernel maps them to PSB_INF
                 // afterwards, and only when the running max says there are any
@@ -307,8 +309,7 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
 
     // A lane owns 4 rows x 4 columns; warp footprint 64 columns x 8 rows (16 column groups x 2 row
     // blocks: every half-warp reads 128 contiguous bytes of one tile row).  Block: 2 warps across x, 4 down.
-    uint32_t lmax = 0;
-    bool ovf = false;
+    uint32_t lmax = 0, amax = 0;
     const int cq = FOOT ? (warp & 3) * 8 + (lane & 7) : (warp & 1) * 16 + (lane & 15);
     const int xl = 4 * cq;
     for (int ry = FOOT ? ((warp >> 2) * 4 + (lane >> 3)) * 4 : ((warp >> 1) * 2 + (lane >> 4)) * 4; ry < L; ry += 32) {
@@ -397,12 +398,19 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
                 oi = ((int64_t)d * split * gridDim.y + (int64_t)blockIdx.y * nyd + yy) * rstride + x0 + xl;
             }
             const uint32_t o[4] = {B0[i] & 0xFFFFu, B0[i] >> 16, B1[i] & 0xFFFFu, B1[i] >> 16};
+            {   // row maximum: every row feeds the overflow test, the rows [mrow0, mrow1) feed gmax
+                uint32_t rmax = 0;
+                if (xl + 3 < valid) {
+                    const uint32_t m2 = __vmaxu2(B0[i], B1[i]);
+                    rmax = max(m2 & 0xFFFFu, m2 >> 16);
+                } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (xl + j < valid) {
-                    if (g >= mrow0 && g < mrow1) lmax = max(lmax, o[j]);
-                    ovf |= o[j] >= MP16_CAP;
+                    for (int j = 0; j < 4; ++j)
+                        if (xl + j < valid) rmax = max(rmax, o[j]);
                 }
+                amax = max(amax, rmax);
+                if (g >= mrow0 && g < mrow1) lmax = max(lmax, rmax);
+            }
             if (OUT == 0) {
                 uint32_t *orow = reinterpret_cast<uint32_t *>(dst) + oi;
                 if (vec && xl + 3 < valid) *reinterpret_cast<uint4 *>(orow) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -425,7 +433,7 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
             }
         }
     }
-    if (__any_sync(0xFFFFFFFFu, ovf) && lane == 0) *overflow = 1;
+    if (__any_sync(0xFFFFFFFFu, amax >= MP16_CAP) && lane == 0) *overflow = 1;
     if (gmax) {
         lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
         if (lane == 0 && lmax) atomicMax(gmax, lmax);
