@@ -177,6 +177,10 @@ class Context:
         8 rows, 1 = 32 x 16."""
         check(self.lib.psb200_set_option(self.handle, b"foot", int(foot)))
 
+    def set_xbits(self, on):
+        """Per-radius x pass from packed seed bits (default) / from the class bytes."""
+        check(self.lib.psb200_set_option(self.handle, b"xbits", 1 if on else 0))
+
     def set_ycoarse(self, on):
         """Per-radius y pass: hierarchical scan that skips row groups by their minima (default) / plain scan."""
         check(self.lib.psb200_set_option(self.handle, b"ycoarse", 1 if on else 0))

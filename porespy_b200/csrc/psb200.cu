@@ -98,6 +98,7 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->bit4 = 1;
     c->foot = 1;
     c->ycoarse = 1;
+    c->xbits = 1;
     c->flag_slot = 0;
     CUDA_TRY(cudaMalloc(&c->flags, 64 * sizeof(int)));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -152,6 +153,10 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
     }
     if (!strcmp(name, "bit4")) {
         ctx->bit4 = value ? 1 : 0;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "xbits")) {
+        ctx->xbits = value ? 1 : 0;
         return PSB200_OK;
     }
     if (!strcmp(name, "ycoarse")) {
@@ -808,10 +813,23 @@ static bool streaming_ok(int64_t ny, int64_t nx, uint32_t T, const void *a, cons
 
 static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t *gx,
                              uint8_t *reach, int64_t nz, int64_t ny, int64_t nx, const int *gate,
-                             cudaStream_t st)
+                             cudaStream_t st, const uint32_t *seedbits = nullptr)
 {
     const int W = (int)isqrt_u32(T - 1);
-    int rc = launch_xdist<XD_LT>(ctx, cls, gx, nz * ny, (int)nx, k, W + 1, gate, st);
+    int rc = PSB200_OK;
+    if (seedbits && nx % 32 == 0 && ctx->xbits) {
+        // the seed set of this radius is already packed: x pass from the bits (xdist_bits_kernel)
+        const int nw = (int)(nx / 32);
+        int warps = 8;
+        while (warps > 1 && (size_t)warps * 2 * nw * 4 > 48 * 1024) warps >>= 1;
+        {
+            ProfScope ps__(ctx, st, K_LT_X);
+            xdist_bits_kernel<<<grid_for(nz * ny, warps, ctx->sm_count, 32), warps * 32, (size_t)warps * 2 * nw * 4, st>>>(
+                seedbits, gx, nz * ny, nw, W + 1, gate);
+        }
+        LAUNCH_CHECK(ctx);
+    } else
+        rc = launch_xdist<XD_LT>(ctx, cls, gx, nz * ny, (int)nx, k, W + 1, gate, st);
     if (rc) return rc;
     {   // y pass
         int Ly = ny < 128 ? (int)ny : 128;
@@ -1029,14 +1047,12 @@ static void launch_packn(const uint8_t *cmap, uint32_t *bits, int64_t nwords, in
     else lt_packn_kernel<8><<<grid, 256, 0, st>>>(cmap, bits, nwords, vol_words, k0, nk);
 }
 
-// One radius of the bit path.  Thresholds descend, so every radius after the first bit radius takes the
-// bit path too: the seed bits of radii k .. k + PACKN_MAX - 1 are packed together from one read of the class
-// map (lt_packn_kernel).  `packed_lo/hi`: the radii whose seed bits sit in w.seedbits.
-static int lt_bit_step(psb200_ctx *ctx, LtWorkspace &w, const uint8_t *cmap, uint8_t *idx, int k, int nT, uint32_t T,
-                       int64_t nz, int64_t ny, int64_t nx, const int *gate, cudaStream_t st, int &packed_lo,
-                       int &packed_hi)
+// Seed bits of radius k: the seed bits of radii k .. k + PACKN_MAX - 1 are packed together from one read of the
+// class map (lt_packn_kernel) whenever k is not in the buffer.  `packed_lo/hi`: the radii whose bits sit in
+// w.seedbits.  Both pipelines use them: the bit path dilates them, the byte path takes its x pass from them.
+static int lt_seed_bits(psb200_ctx *ctx, LtWorkspace &w, const uint8_t *cmap, int k, int nT, int64_t nwords,
+                        cudaStream_t st, int &packed_lo, int &packed_hi, const uint32_t **bits)
 {
-    const int64_t nwords = nz * ny * nx / 32;
     if (k < packed_lo || k >= packed_hi) {
         const int nk = nT - k < PACKN_MAX ? nT - k : PACKN_MAX;
         {
@@ -1048,8 +1064,19 @@ static int lt_bit_step(psb200_ctx *ctx, LtWorkspace &w, const uint8_t *cmap, uin
         packed_lo = k;
         packed_hi = k + nk;
     }
-    return lt_bitball_impl(ctx, w.seedbits + (size_t)(k - packed_lo) * w.seed_words, nz, 0, w.written, idx, k, T, nz, ny, nx,
-                           gate, st);
+    *bits = w.seedbits + (size_t)(k - packed_lo) * w.seed_words;
+    return PSB200_OK;
+}
+
+// One radius of the bit path (thresholds descend, so every radius after the first bit radius takes it too).
+static int lt_bit_step(psb200_ctx *ctx, LtWorkspace &w, const uint8_t *cmap, uint8_t *idx, int k, int nT, uint32_t T,
+                       int64_t nz, int64_t ny, int64_t nx, const int *gate, cudaStream_t st, int &packed_lo,
+                       int &packed_hi)
+{
+    const uint32_t *bits = nullptr;
+    int rc = lt_seed_bits(ctx, w, cmap, k, nT, nz * ny * nx / 32, st, packed_lo, packed_hi, &bits);
+    if (rc) return rc;
+    return lt_bitball_impl(ctx, bits, nz, 0, w.written, idx, k, T, nz, ny, nx, gate, st);
 }
 
 // step-level entry points of the bit path (z-slab shards exchange seed-bit halo planes between them)
@@ -1260,7 +1287,12 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
             continue;
         }
         if (streaming_ok(ny, nx, T, cmap, w.reach, w.gx) && (((uintptr_t)idx & 15u) == 0)) {
-            rc = lt_xy_stream_impl(ctx, cmap, k, T, w.gx, w.reach, nz, ny, nx, gate, st);
+            const uint32_t *bits = nullptr;
+            if (bit_ok && ctx->xbits) {
+                rc = lt_seed_bits(ctx, w, cmap, k, nT, n / 32, st, packed_lo, packed_hi, &bits);
+                if (rc) return rc;
+            }
+            rc = lt_xy_stream_impl(ctx, cmap, k, T, w.gx, w.reach, nz, ny, nx, gate, st, bits);
             if (rc) return rc;
             rc = lt_z_stream_impl(ctx, w.reach, nullptr, 0, nullptr, 0, idx, k, T, nz, ny, nx, gate, st);
         } else {

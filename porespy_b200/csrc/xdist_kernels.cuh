@@ -194,3 +194,96 @@ xdist_kernel(const uint8_t *__restrict__ in, void *__restrict__ outp, int64_t nl
         __syncwarp();
     }
 }
+
+// ------------------------------------------------------------------ x pass from seed BITS
+// The per-radius x pass when the seed set of the radius is already packed (lt_packn_kernel packs up to 16 radii
+// from one read of the class map): a lane owns one 32-voxel word, so the site masks come for free and the
+// byte-SWAR compares -- most of xdist_kernel<XD_LT>'s instructions -- disappear; the distances are the same two
+// running-distance recurrences (VIADDMNMX.U16x2, voxel j and j + 16 in the halves of one register).
+//   gx[line][x] = min(distance along x to the nearest set bit of the line, cap)      cap = W + 1 <= 254
+// nx = 32 * nw.  dyn smem = warps * 2 * nw ints.
+__global__ void __launch_bounds__(256)
+xdist_bits_kernel(const uint32_t *__restrict__ bits, uint8_t *__restrict__ gx, int64_t nlines, int nw, int cap,
+                  const int *__restrict__ gate)
+{
+    if (gate && *gate == 0) return;
+    extern __shared__ int xb_smem[];
+    const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = lane_id();
+    int *lastp = xb_smem + (size_t)wid * 2 * nw;      // last site at or before the end of word w
+    int *firstp = lastp + nw;                         // first site at or after the start of word w
+    const int nx = 32 * nw;
+    const int NONE_L = -0x4000, NONE_R = 0x4000 + nx;
+    const uint32_t cap2 = (uint32_t)cap * 0x00010001u;
+    for (int64_t line = (int64_t)blockIdx.x * warps + wid; line < nlines; line += (int64_t)gridDim.x * warps) {
+        const uint32_t *row = bits + line * nw;
+        int carry = NONE_L;
+        for (int base = 0; base < nw; base += 32) {
+            const int w = base + lane;
+            const uint32_t m = w < nw ? __ldg(row + w) : 0u;
+            int vl = m ? 32 * w + 31 - __clz(m) : NONE_L;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, vl, off);
+                if (lane >= off) vl = max(vl, t);
+            }
+            vl = max(vl, carry);
+            carry = __shfl_sync(0xFFFFFFFFu, vl, 31);
+            if (w < nw) {
+                lastp[w] = vl;
+                firstp[w] = m ? 32 * w + __ffs(m) - 1 : NONE_R;
+            }
+        }
+        __syncwarp();
+        carry = NONE_R;
+        for (int base = ((nw - 1) / 32) * 32; base >= 0; base -= 32) {
+            const int w = base + lane;
+            int vr = w < nw ? firstp[w] : NONE_R;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_down_sync(0xFFFFFFFFu, vr, off);
+                if (lane + off < 32) vr = min(vr, t);
+            }
+            vr = min(vr, carry);
+            carry = __shfl_sync(0xFFFFFFFFu, vr, 0);
+            if (w < nw) firstp[w] = vr;
+        }
+        __syncwarp();
+        for (int w = lane; w < nw; w += 32) {
+            const uint32_t m = __ldg(row + w);
+            const int Lpos = w > 0 ? lastp[w - 1] : NONE_L;
+            const int Rpos = w + 1 < nw ? firstp[w + 1] : NONE_R;
+            const uint32_t carryL = (uint32_t)min(32 * w - 1 - Lpos, 0x4000);       // distance at x = 32w - 1
+            const uint32_t carryR = (uint32_t)min(Rpos - (32 * w + 32), 0x4000);    // distance at x = 32w + 32
+            const uint32_t mlo = m & 0xFFFFu, mhi = m >> 16;
+            const uint32_t fhi = mlo ? (uint32_t)(15 - (31 - __clz(mlo))) : carryL + 16u;   // forward value at voxel 15
+            const uint32_t blo = mhi ? (uint32_t)(__ffs(mhi) - 1) : carryR + 16u;           // backward value at voxel 16
+            uint32_t f[16];
+            uint32_t run = carryL | (fhi << 16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t s = (~(m >> j) & 0x00010001u) * 0xFFFFu;             // 0xFFFF per non-site half
+                run = __viaddmin_u16x2(run, 0x00010001u, s);
+                f[j] = run;
+            }
+            run = blo | (carryR << 16);
+            uint32_t d[16];
+#pragma unroll
+            for (int j = 15; j >= 0; --j) {
+                const uint32_t s = (~(m >> j) & 0x00010001u) * 0xFFFFu;
+                run = __viaddmin_u16x2(run, 0x00010001u, s);
+                d[j] = __vminu2(__vminu2(f[j], run), cap2);
+            }
+            uint32_t olo[4], ohi[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t t01 = __byte_perm(d[4 * q], d[4 * q + 1], 0x6240), t23 = __byte_perm(d[4 * q + 2], d[4 * q + 3], 0x6240);
+                olo[q] = __byte_perm(t01, t23, 0x5410);          // voxels 4q .. 4q + 3
+                ohi[q] = __byte_perm(t01, t23, 0x7632);          // voxels 16 + 4q .. 16 + 4q + 3
+            }
+            uint4 *o = reinterpret_cast<uint4 *>(gx + line * nx + 32 * w);
+            o[0] = make_uint4(olo[0], olo[1], olo[2], olo[3]);
+            o[1] = make_uint4(ohi[0], ohi[1], ohi[2], ohi[3]);
+        }
+        __syncwarp();
+    }
+}
