@@ -177,6 +177,10 @@ class Context:
         8 rows, 1 = 32 x 16."""
         check(self.lib.psb200_set_option(self.handle, b"foot", int(foot)))
 
+    def set_bitquad(self, on):
+        """Bit path: 2 x 2 output rows per lane (default) / one output row per lane."""
+        check(self.lib.psb200_set_option(self.handle, b"bitquad", 1 if on else 0))
+
     def set_xbits(self, on):
         """Per-radius x pass from packed seed bits (default) / from the class bytes."""
         check(self.lib.psb200_set_option(self.handle, b"xbits", 1 if on else 0))

@@ -350,9 +350,16 @@ lt_zsweep_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo, 
 #pragma unroll
         for (int i = 0; i < ZS_UNROLL; ++i) v[i] = col[(int64_t)(z + i) * ps];
 #pragma unroll
-        for (int i = 0; i < ZS_UNROLL; ++i) col[(int64_t)(z + i) * ps] = cone_step(v[i], c);
+        for (int i = 0; i < ZS_UNROLL; ++i) {
+            // the forward value differs from the reach byte only inside a cone: most stores are not needed
+            const uint32_t f = cone_step(v[i], c);
+            if (f != v[i]) col[(int64_t)(z + i) * ps] = f;
+        }
     }
-    for (; z < nz; ++z) col[(int64_t)z * ps] = cone_step(col[(int64_t)z * ps], c);
+    for (; z < nz; ++z) {
+        const uint32_t v = col[(int64_t)z * ps], f = cone_step(v, c);
+        if (f != v) col[(int64_t)z * ps] = f;
+    }
 
 #pragma unroll
     for (int j = 0; j < 4; ++j) c[j] = 0;

@@ -99,6 +99,7 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->foot = 1;
     c->ycoarse = 1;
     c->xbits = 1;
+    c->bitquad = 1;
     c->flag_slot = 0;
     CUDA_TRY(cudaMalloc(&c->flags, 64 * sizeof(int)));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -153,6 +154,10 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
     }
     if (!strcmp(name, "bit4")) {
         ctx->bit4 = value ? 1 : 0;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "bitquad")) {
+        ctx->bitquad = value ? 1 : 0;
         return PSB200_OK;
     }
     if (!strcmp(name, "xbits")) {
@@ -973,6 +978,36 @@ static bool build_ball_pairs(uint32_t T, int64_t ny, int64_t nw, BallPairs &bp)
     return true;
 }
 
+// load entries of the 2 x 2-output dilation kernel (bitball_kernels.cuh, lt_bitball4q_kernel): for every Horner
+// stage a the source rows (sy, sz) relative to output (0, 0) together with the mask of the outputs (oy + 2 oz) whose
+// allowance for that row is exactly a
+static bool build_ball_quads(uint32_t T, int64_t ny, int64_t nw, BallQuads &bq)
+{
+    const int W = (int)isqrt_u32(T - 1);
+    if (W > 31) return false;
+    bq.W = W;
+    int cnt = 0;
+    for (int a = W; a >= 0; --a) {
+        for (int sz = -W; sz <= W + 1; ++sz)
+            for (int sy = -W; sy <= W + 1; ++sy) {
+                int mask = 0;
+                for (int o = 0; o < 4; ++o) {
+                    const int dy = sy - (o & 1), dz = sz - (o >> 1);
+                    const int64_t rem = (int64_t)T - 1 - (int64_t)dy * dy - (int64_t)dz * dz;
+                    if (rem >= 0 && (int)isqrt_u32((uint32_t)rem) == a) mask |= 1 << o;
+                }
+                if (!mask) continue;
+                if (cnt >= BB2_MAX_ENTRIES) return false;
+                bq.e[cnt].x = (int)((sz * ny + sy) * nw);
+                bq.e[cnt].y = mask;
+                ++cnt;
+            }
+        bq.ring_end[a] = (unsigned short)cnt;
+    }
+    bq.ring_end[W + 1] = 0;
+    return true;
+}
+
 static int lt_pack_impl(psb200_ctx *ctx, const uint8_t *cmap, int k, uint32_t *bits, int64_t nwords,
                         const int *gate, cudaStream_t st)
 {
@@ -999,6 +1034,23 @@ static int lt_bitball_impl(psb200_ctx *ctx, const uint32_t *seedbits, int64_t nz
     // rows of 32 / 64 / 128 words: four words per lane (16-byte loads)
     const bool four = ctx->bit4 && (nw == 32 || nw == 64 || nw == 128) &&
                       ((((uintptr_t)seedbits | (uintptr_t)written) & 15u) == 0);
+    static thread_local BallQuads bq;
+    if (four && ctx->bitquad && nz >= 2 && ny >= 2 && build_ball_quads(T, ny, nx / 32, bq)) {
+        // 2 x 2 output rows per lane: 58 % of the loads per output
+        const int lpr = nw / 4, gz = (256 / lpr) / 8;
+        dim3 gq(1, (unsigned)((ny + 15) / 16), (unsigned)((nz + 2 * gz - 1) / (2 * gz)));
+        {
+            ProfScope ps__(ctx, st, K_LT_BITBALL);
+            if (lpr == 8)
+                lt_bitball4q_kernel<8><<<gq, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bq, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
+            else if (lpr == 16)
+                lt_bitball4q_kernel<16><<<gq, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bq, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
+            else
+                lt_bitball4q_kernel<32><<<gq, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bq, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
+        }
+        LAUNCH_CHECK(ctx);
+        return PSB200_OK;
+    }
     if (four) {
         const int lpr = nw / 4, tz = 32 / lpr;
         dim3 g4(1, (unsigned)((ny + 7) / 8), (unsigned)((nz + tz - 1) / tz));

@@ -15,6 +15,8 @@ if os.environ.get("BIT_TMAX"):
     ctx.set_bit_tmax(int(os.environ["BIT_TMAX"]))
 if os.environ.get("FOOT"):
     ctx.set_foot(int(os.environ["FOOT"]))
+if os.environ.get("BITQUAD"):
+    ctx.set_bitquad(int(os.environ["BITQUAD"]))
 if os.environ.get("XBITS"):
     ctx.set_xbits(int(os.environ["XBITS"]))
 if os.environ.get("YCOARSE"):
