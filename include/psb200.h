@@ -159,7 +159,9 @@ int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2,
 /* Step-level entry points of the same loop, for z-slab sharded volumes: the xy part of
  * one radius is slab-local; the z part needs up to W = ceil(sqrt(T))-1 halo planes of
  * the reach map from each z-neighbour (m_lo = the nlo planes just below local z=0 in
- * ascending z order, m_hi = the nhi planes just above local z=nz-1; NULL/0 at the ends). */
+ * ascending z order, m_hi = the nhi planes just above local z=nz-1; NULL/0 at the ends).
+ * psb200_lt_xy workspace: nz*ny*nx bytes (x-distances) select the streaming kernels; with another nz*ny*nx/8 + 512
+ * bytes behind them the x pass runs from packed seed bits (faster); without a workspace the fused any-shape kernel runs. */
 int psb200_lt_classify(psb200_ctx *ctx, const uint32_t *d2, const uint32_t *T_host, int nT,
                        uint8_t *cls, int64_t n, psb200_stream stream);
 int psb200_lt_xy(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t *reach,
