@@ -874,6 +874,9 @@ static int lt_z_stream_impl(psb200_ctx *ctx, uint8_t *reach, const uint8_t *m_lo
     return PSB200_OK;
 }
 
+static int lt_pack_impl(psb200_ctx *ctx, const uint8_t *cmap, int k, uint32_t *bits, int64_t nwords,
+                        const int *gate, cudaStream_t st);
+
 extern "C" int psb200_lt_xy(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t *reach,
                             int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
                             psb200_stream stream)
