@@ -178,7 +178,7 @@ class Context:
         check(self.lib.psb200_set_option(self.handle, b"foot", int(foot)))
 
     def set_bitquad(self, on):
-        """Bit path: 2 x 2 output rows per lane (default) / one output row per lane."""
+        """Bit path: two output rows per lane (default) / one output row per lane."""
         check(self.lib.psb200_set_option(self.handle, b"bitquad", 1 if on else 0))
 
     def set_xbits(self, on):

@@ -358,112 +358,123 @@ lt_bitball4_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ wr
     bb_commit(written, idx, wi + 3, A3, val);
 }
 
-// ------------------------------------------------- four words x (2 x 2) output rows per lane
+// ------------------------------------------------- four words x two output rows per lane
 // The dilation is bound by L1 wavefronts: one 16-byte load per (dy, dz) pair and output row.  A source row
-// (y + sy, z + sz) serves the four outputs (y + oy, z + oz), oy, oz in {0, 1}, with the allowances
-// allow(sy - oy, sz - oz); where two or more of those allowances coincide the row is loaded ONCE in that Horner
-// stage and ORed into all of them (masks below).  For the balls of this path that needs 58 % of the loads per
-// output (CPU count: T = 180: 1302 loads for 4 x 561 pairs).  Lanes whose 2 x 2 outputs touch the volume border
-// take the one-output loop for each of their rows.
+// (y + sy, z + sz) serves the outputs (y, z) and (y + 1, z) with the allowances allow(sy, sz) and allow(sy - 1, sz);
+// where the two coincide the row is loaded ONCE in that Horner stage and ORed into both accumulators.  For the
+// balls of this path that needs 79 % of the loads per output (CPU count; T = 180: 884 loads for 2 x 561 pairs).
+// Every stage has three lists -- rows for both outputs, for the upper one only, for the lower one only -- each
+// padded to a multiple of 4 so that the loops keep the 4-loads-per-iteration form of lt_bitball4_kernel.
+// Measured and NOT adopted (r2k): 2 x 2 outputs with a 4-bit output mask per load (58 % of the loads): the masked
+// ORs double the instruction count and the kernel turns issue-bound (3.26 -> 3.78 ms at T = 180).
+// Row groups whose two rows touch the volume border take the one-output loop with bounds checks.
 //   LPR lanes own one row group (4 * LPR words per row); a block of 256 threads owns 256 / LPR row groups:
-//   8 (y pairs) x (32 / LPR) (z pairs).  grid = (1, ceil(ny / 16), ceil(nz / (2 * 32 / LPR))).
-#define BB2_MAX_ENTRIES 1664        // balls up to T ~ 230; larger ones keep the one-output kernel
-struct BallQuads {                 // load entries sorted by x-allowance a, descending
+//   8 (y pairs) x (32 / LPR) (z).  grid = (1, ceil(ny / 16), ceil(nz / (32 / LPR))).
+#define BB3_MAX_ENTRIES 2432
+struct BallDuo {                   // word offsets sorted by stage (x-allowance a, descending) and list
     int W;
-    unsigned short ring_end[34];   // entries of stage a are [ring_end[a + 1], ring_end[a])
-    int2 e[BB2_MAX_ENTRIES];       // .x = (sz * ny + sy) * nw (word offset from output (0, 0)), .y = 4-bit output mask
+    unsigned short end[34][3];     // stage a: both = [prev, end[a][0]), upper only = [end[a][0], end[a][1]), lower only = [.., end[a][2])
+    int off[BB3_MAX_ENTRIES];      // (sz * ny + sy) * nw, relative to the upper output row
 };
 
 template <int LPR>
-__global__ void __launch_bounds__(256, 3)
-lt_bitball4q_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ written,
+__global__ void __launch_bounds__(256, 4)
+lt_bitball4d_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ written,
                     uint8_t *__restrict__ idx, int nz, int ny,
-                    const __grid_constant__ BallQuads bq, const __grid_constant__ BallPairs bp, uint32_t val,
+                    const __grid_constant__ BallDuo bd, const __grid_constant__ BallPairs bp, uint32_t val,
                     const int *__restrict__ gate, int nz_src, int z_off)
 {
     if (gate && *gate == 0) return;
     constexpr int GPB = 256 / LPR;         // row groups per block
     constexpr int GZ = GPB / 8;            // ... of which along z (8 along y)
     constexpr int NW = 4 * LPR;            // words per row
-    __shared__ __align__(16) int2 s_q[BB2_MAX_ENTRIES];
+    __shared__ __align__(16) int s_d[BB3_MAX_ENTRIES];
     __shared__ int s_off[BB_MAX_PAIRS];
     __shared__ int s_dyz[BB_MAX_PAIRS];
-    for (int i = threadIdx.x; i < (int)bq.ring_end[0]; i += blockDim.x) s_q[i] = bq.e[i];
+    for (int i = threadIdx.x; i < (int)bd.end[0][2]; i += blockDim.x) s_d[i] = bd.off[i];
     for (int i = threadIdx.x; i < (int)bp.ring_end[0]; i += blockDim.x) { s_off[i] = bp.e[i].x; s_dyz[i] = bp.e[i].y; }
     __syncthreads();
     const int grp = threadIdx.x / LPR, lr = threadIdx.x % LPR;
-    const int y0 = (blockIdx.y * 8 + (grp & 7)) * 2, z0 = (blockIdx.z * GZ + (grp >> 3)) * 2;
-    if (y0 >= ny || z0 >= nz) return;                      // (no warp-wide operation spans row groups of different rows: LPR | 32)
-    const int W = bq.W;
-    const int zs0 = z0 + z_off;
-    const bool interior = y0 - W >= 0 && y0 + 1 + W < ny && zs0 - W >= 0 && zs0 + 1 + W < nz_src && z0 + 1 < nz;
+    const int y0 = (blockIdx.y * 8 + (grp & 7)) * 2, z = blockIdx.z * GZ + (grp >> 3);
+    if (y0 >= ny || z >= nz) return;
+    const int W = bd.W;
+    const int zs = z + z_off;
+    const bool interior = y0 - W >= 0 && y0 + 1 + W < ny && zs - W >= 0 && zs + W < nz_src;
     // the lanes of one row group take the same branches; a warp may hold several groups, so every shuffle names
     // only the lanes of its own group
     const unsigned gmask = LPR == 32 ? 0xFFFFFFFFu : (((1u << LPR) - 1u) << ((lane_id() / LPR) * LPR));
+#define BB_DILATE4(P0, P1, P2, P3)                                                                        \
+    {                                                                                                     \
+        uint32_t l = __shfl_up_sync(gmask, P3, 1), rr = __shfl_down_sync(gmask, P0, 1);                   \
+        if (lr == 0) l = 0;                                                                               \
+        if (lr == LPR - 1) rr = 0;                                                                        \
+        const uint32_t n0 = P0 | (P0 << 1) | (l >> 31) | (P0 >> 1) | (P1 << 31);                          \
+        const uint32_t n1 = P1 | (P1 << 1) | (P0 >> 31) | (P1 >> 1) | (P2 << 31);                         \
+        const uint32_t n2 = P2 | (P2 << 1) | (P1 >> 31) | (P2 >> 1) | (P3 << 31);                         \
+        const uint32_t n3 = P3 | (P3 << 1) | (P2 >> 31) | (P3 >> 1) | (rr << 31);                         \
+        P0 = n0; P1 = n1; P2 = n2; P3 = n3;                                                               \
+    }
     if (interior) {
-        const uint32_t *base = seeds + ((int64_t)zs0 * ny + y0) * NW + 4 * lr;
+        const uint32_t *base = seeds + ((int64_t)zs * ny + y0) * NW + 4 * lr;
         asm volatile("" : "+l"(base));
-        uint32_t A[4][4];
-#pragma unroll
-        for (int o = 0; o < 4; ++o)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) A[o][j] = 0u;
+        uint32_t A0 = 0, A1 = 0, A2 = 0, A3 = 0, B0 = 0, B1 = 0, B2 = 0, B3 = 0;
         int p = 0;
         for (int a = W; a >= 0; --a) {
             if (a < W) {
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    uint32_t l = __shfl_up_sync(gmask, A[o][3], 1), rr = __shfl_down_sync(gmask, A[o][0], 1);
-                    if (lr == 0) l = 0;                    // row boundary (also a warp-internal one)
-                    if (lr == LPR - 1) rr = 0;
-                    const uint32_t n0 = A[o][0] | (A[o][0] << 1) | (l >> 31) | (A[o][0] >> 1) | (A[o][1] << 31);
-                    const uint32_t n1 = A[o][1] | (A[o][1] << 1) | (A[o][0] >> 31) | (A[o][1] >> 1) | (A[o][2] << 31);
-                    const uint32_t n2 = A[o][2] | (A[o][2] << 1) | (A[o][1] >> 31) | (A[o][2] >> 1) | (A[o][3] << 31);
-                    const uint32_t n3 = A[o][3] | (A[o][3] << 1) | (A[o][2] >> 31) | (A[o][3] >> 1) | (rr << 31);
-                    A[o][0] = n0; A[o][1] = n1; A[o][2] = n2; A[o][3] = n3;
-                }
+                BB_DILATE4(A0, A1, A2, A3)
+                BB_DILATE4(B0, B1, B2, B3)
             }
-            const int pend = bq.ring_end[a];
-            for (; p < pend; ++p) {
-                const int2 e = s_q[p];
-                const uint4 s = __ldg(reinterpret_cast<const uint4 *>(base + e.x));
-                // e.y is the same for every lane: uniform predicates, a 0 / ~0 mask per output keeps it branch-free
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    const uint32_t mk = 0u - (((uint32_t)e.y >> o) & 1u);
-                    A[o][0] |= s.x & mk; A[o][1] |= s.y & mk; A[o][2] |= s.z & mk; A[o][3] |= s.w & mk;
-                }
+            const int e0 = bd.end[a][0], e1 = bd.end[a][1], e2 = bd.end[a][2];
+            for (; p < e0; p += 4) {                        // rows that serve both outputs
+                const int4 o = *reinterpret_cast<const int4 *>(s_d + p);
+                const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(base + o.x));
+                const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(base + o.y));
+                const uint4 s2 = __ldg(reinterpret_cast<const uint4 *>(base + o.z));
+                const uint4 s3 = __ldg(reinterpret_cast<const uint4 *>(base + o.w));
+                const uint32_t c0 = (s0.x | s1.x) | (s2.x | s3.x), c1 = (s0.y | s1.y) | (s2.y | s3.y);
+                const uint32_t c2 = (s0.z | s1.z) | (s2.z | s3.z), c3 = (s0.w | s1.w) | (s2.w | s3.w);
+                A0 |= c0; A1 |= c1; A2 |= c2; A3 |= c3;
+                B0 |= c0; B1 |= c1; B2 |= c2; B3 |= c3;
+            }
+            for (; p < e1; p += 4) {                        // upper output only
+                const int4 o = *reinterpret_cast<const int4 *>(s_d + p);
+                const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(base + o.x));
+                const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(base + o.y));
+                const uint4 s2 = __ldg(reinterpret_cast<const uint4 *>(base + o.z));
+                const uint4 s3 = __ldg(reinterpret_cast<const uint4 *>(base + o.w));
+                A0 |= (s0.x | s1.x) | (s2.x | s3.x); A1 |= (s0.y | s1.y) | (s2.y | s3.y);
+                A2 |= (s0.z | s1.z) | (s2.z | s3.z); A3 |= (s0.w | s1.w) | (s2.w | s3.w);
+            }
+            for (; p < e2; p += 4) {                        // lower output only
+                const int4 o = *reinterpret_cast<const int4 *>(s_d + p);
+                const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(base + o.x));
+                const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(base + o.y));
+                const uint4 s2 = __ldg(reinterpret_cast<const uint4 *>(base + o.z));
+                const uint4 s3 = __ldg(reinterpret_cast<const uint4 *>(base + o.w));
+                B0 |= (s0.x | s1.x) | (s2.x | s3.x); B1 |= (s0.y | s1.y) | (s2.y | s3.y);
+                B2 |= (s0.z | s1.z) | (s2.z | s3.z); B3 |= (s0.w | s1.w) | (s2.w | s3.w);
             }
         }
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            const int64_t wi = ((int64_t)(z0 + (o >> 1)) * ny + y0 + (o & 1)) * NW + 4 * lr;
-            bb_commit(written, idx, wi, A[o][0], val);
-            bb_commit(written, idx, wi + 1, A[o][1], val);
-            bb_commit(written, idx, wi + 2, A[o][2], val);
-            bb_commit(written, idx, wi + 3, A[o][3], val);
-        }
+        const int64_t wi = ((int64_t)z * ny + y0) * NW + 4 * lr;
+        bb_commit(written, idx, wi, A0, val);
+        bb_commit(written, idx, wi + 1, A1, val);
+        bb_commit(written, idx, wi + 2, A2, val);
+        bb_commit(written, idx, wi + 3, A3, val);
+        bb_commit(written, idx, wi + NW, B0, val);
+        bb_commit(written, idx, wi + NW + 1, B1, val);
+        bb_commit(written, idx, wi + NW + 2, B2, val);
+        bb_commit(written, idx, wi + NW + 3, B3, val);
         return;
     }
-    // ---- border row groups: the one-output loop with bounds checks for each of the (up to) four rows
-    for (int o = 0; o < 4; ++o) {
-        const int y = y0 + (o & 1), z = z0 + (o >> 1);
-        if (y >= ny || z >= nz) continue;
-        const int zs = z + z_off;
+    // ---- border row groups: the one-output loop with bounds checks for each of the two rows
+    for (int o = 0; o < 2; ++o) {
+        const int y = y0 + o;
+        if (y >= ny) continue;
         const uint32_t *base = seeds + ((int64_t)zs * ny + y) * NW + 4 * lr;
         uint32_t A0 = 0, A1 = 0, A2 = 0, A3 = 0;
         int p = 0;
         for (int a = bp.W; a >= 0; --a) {
-            if (a < bp.W) {
-                uint32_t l = __shfl_up_sync(gmask, A3, 1), rr = __shfl_down_sync(gmask, A0, 1);
-                if (lr == 0) l = 0;
-                if (lr == LPR - 1) rr = 0;
-                const uint32_t n0 = A0 | (A0 << 1) | (l >> 31) | (A0 >> 1) | (A1 << 31);
-                const uint32_t n1 = A1 | (A1 << 1) | (A0 >> 31) | (A1 >> 1) | (A2 << 31);
-                const uint32_t n2 = A2 | (A2 << 1) | (A1 >> 31) | (A2 >> 1) | (A3 << 31);
-                const uint32_t n3 = A3 | (A3 << 1) | (A2 >> 31) | (A3 >> 1) | (rr << 31);
-                A0 = n0; A1 = n1; A2 = n2; A3 = n3;
-            }
+            if (a < bp.W) BB_DILATE4(A0, A1, A2, A3)
             const int pend = bp.ring_end[a];
             for (; p < pend; ++p) {
                 const int e = s_dyz[p];
@@ -480,4 +491,5 @@ lt_bitball4q_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ w
         bb_commit(written, idx, wi + 2, A2, val);
         bb_commit(written, idx, wi + 3, A3, val);
     }
+#undef BB_DILATE4
 }

@@ -27,7 +27,7 @@ struct psb200_ctx {
     int bit_tmax;      // thresholds T <= bit_tmax use the bit-parallel dilation (0: never)
     int bit4;          // bit path: four-words-per-lane kernel for rows of 32 / 64 / 128 words
     int foot;          // warp footprint of the 16-bit EDT min-plus scans: 0 = 64 x 8 voxels, 1 = 32 x 16 (default: 3 % faster, r2b)
-    int bitquad;       // bit path: 2 x 2 output rows per lane (lt_bitball4q_kernel, default) / one row per lane
+    int bitquad;       // bit path: two output rows per lane (lt_bitball4d_kernel, default) / one row per lane
     int xbits;         // per-radius x pass from packed seed bits (xdist_bits_kernel, default) or from the class map
     int ycoarse;       // per-radius y pass: hierarchical scan (lt_y3_kernel, default) or the plain one (lt_y2_kernel)
     int edt16;         // EDT y/z passes: 16-bit two-voxels-per-instruction kernel first, uint32 kernel gated behind it

@@ -992,33 +992,39 @@ static bool build_ball_pairs(uint32_t T, int64_t ny, int64_t nw, BallPairs &bp)
     return true;
 }
 
-// load entries of the 2 x 2-output dilation kernel (bitball_kernels.cuh, lt_bitball4q_kernel): for every Horner
-// stage a the source rows (sy, sz) relative to output (0, 0) together with the mask of the outputs (oy + 2 oz) whose
-// allowance for that row is exactly a
-static bool build_ball_quads(uint32_t T, int64_t ny, int64_t nw, BallQuads &bq)
+// load lists of the two-output dilation kernel (bitball_kernels.cuh, lt_bitball4d_kernel): for every Horner stage a
+// the source rows (sy, sz), relative to the upper output row, whose allowance is exactly a for both outputs
+// (allow(sy, sz) == allow(sy - 1, sz) == a), for the upper one only, for the lower one only; every list is padded
+// to a multiple of 4 with copies of its last entry (OR is idempotent)
+static bool build_ball_duo(uint32_t T, int64_t ny, int64_t nw, BallDuo &bd)
 {
     const int W = (int)isqrt_u32(T - 1);
     if (W > 31) return false;
-    bq.W = W;
+    bd.W = W;
     int cnt = 0;
+    auto allow = [&](int dy, int dz) -> int {
+        const int64_t rem = (int64_t)T - 1 - (int64_t)dy * dy - (int64_t)dz * dz;
+        return rem < 0 ? -1 : (int)isqrt_u32((uint32_t)rem);
+    };
     for (int a = W; a >= 0; --a) {
-        for (int sz = -W; sz <= W + 1; ++sz)
-            for (int sy = -W; sy <= W + 1; ++sy) {
-                int mask = 0;
-                for (int o = 0; o < 4; ++o) {
-                    const int dy = sy - (o & 1), dz = sz - (o >> 1);
-                    const int64_t rem = (int64_t)T - 1 - (int64_t)dy * dy - (int64_t)dz * dz;
-                    if (rem >= 0 && (int)isqrt_u32((uint32_t)rem) == a) mask |= 1 << o;
+        for (int list = 0; list < 3; ++list) {
+            const int first = cnt;
+            for (int sz = -W; sz <= W; ++sz)
+                for (int sy = -W; sy <= W + 1; ++sy) {
+                    const bool up = allow(sy, sz) == a, lo = allow(sy - 1, sz) == a;
+                    const bool take = list == 0 ? (up && lo) : (list == 1 ? (up && !lo) : (!up && lo));
+                    if (!take) continue;
+                    if (cnt >= BB3_MAX_ENTRIES) return false;
+                    bd.off[cnt++] = (int)((sz * ny + sy) * nw);
                 }
-                if (!mask) continue;
-                if (cnt >= BB2_MAX_ENTRIES) return false;
-                bq.e[cnt].x = (int)((sz * ny + sy) * nw);
-                bq.e[cnt].y = mask;
+            while (cnt > first && cnt % 4 != 0) {
+                if (cnt >= BB3_MAX_ENTRIES) return false;
+                bd.off[cnt] = bd.off[cnt - 1];
                 ++cnt;
             }
-        bq.ring_end[a] = (unsigned short)cnt;
+            bd.end[a][list] = (unsigned short)cnt;
+        }
     }
-    bq.ring_end[W + 1] = 0;
     return true;
 }
 
@@ -1048,19 +1054,19 @@ static int lt_bitball_impl(psb200_ctx *ctx, const uint32_t *seedbits, int64_t nz
     // rows of 32 / 64 / 128 words: four words per lane (16-byte loads)
     const bool four = ctx->bit4 && (nw == 32 || nw == 64 || nw == 128) &&
                       ((((uintptr_t)seedbits | (uintptr_t)written) & 15u) == 0);
-    static thread_local BallQuads bq;
-    if (four && ctx->bitquad && nz >= 2 && ny >= 2 && build_ball_quads(T, ny, nx / 32, bq)) {
-        // 2 x 2 output rows per lane: 58 % of the loads per output
+    static thread_local BallDuo bd;
+    if (four && ctx->bitquad && ny >= 2 && T >= 20 && build_ball_duo(T, ny, nx / 32, bd)) {
+        // two output rows per lane: 79 % of the loads per output (small balls: list padding eats the gain)
         const int lpr = nw / 4, gz = (256 / lpr) / 8;
-        dim3 gq(1, (unsigned)((ny + 15) / 16), (unsigned)((nz + 2 * gz - 1) / (2 * gz)));
+        dim3 gq(1, (unsigned)((ny + 15) / 16), (unsigned)((nz + gz - 1) / gz));
         {
             ProfScope ps__(ctx, st, K_LT_BITBALL);
             if (lpr == 8)
-                lt_bitball4q_kernel<8><<<gq, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bq, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
+                lt_bitball4d_kernel<8><<<gq, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bd, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
             else if (lpr == 16)
-                lt_bitball4q_kernel<16><<<gq, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bq, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
+                lt_bitball4d_kernel<16><<<gq, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bd, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
             else
-                lt_bitball4q_kernel<32><<<gq, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bq, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
+                lt_bitball4d_kernel<32><<<gq, 256, 0, st>>>(seedbits, written, idx, (int)nz, (int)ny, bd, bp, (uint32_t)(k + 1), gate, (int)nz_src, (int)z_off);
         }
         LAUNCH_CHECK(ctx);
         return PSB200_OK;
