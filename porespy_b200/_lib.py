@@ -177,6 +177,14 @@ class Context:
         8 rows, 1 = 32 x 16."""
         check(self.lib.psb200_set_option(self.handle, b"foot", int(foot)))
 
+    def set_edt_h(self, rows):
+        """Halo rows of the 16-bit EDT tiles (default 48)."""
+        check(self.lib.psb200_set_option(self.handle, b"edt_h", int(rows)))
+
+    def set_ydirect(self, on):
+        """Per-radius y pass: store reach bytes directly from registers (default) / through a shared-memory tile."""
+        check(self.lib.psb200_set_option(self.handle, b"ydirect", 1 if on else 0))
+
     def set_bitquad(self, on):
         """Bit path: two output rows per lane (default) / one output row per lane."""
         check(self.lib.psb200_set_option(self.handle, b"bitquad", 1 if on else 0))

@@ -473,16 +473,19 @@ __device__ __forceinline__ uint32_t sq_cap2(uint32_t a, uint32_t b, uint32_t W, 
 
 #define LTY_LUT_MAX 8192       // reach LUT in shared memory for T <= this, sqrtf above
 
-static inline size_t lt_y2_smem_bytes(int Ly, int W, uint32_t T)
+// direct: the reach bytes go from registers to global memory (4 bytes per lane and row, 64 contiguous bytes per
+// half-warp) instead of through a shared-memory copy of the tile: 16 KB less shared memory, i.e. 4 instead of 3
+// resident blocks per SM at W ~ 18
+static inline size_t lt_y2_smem_bytes(int Ly, int W, uint32_t T, int direct)
 {
     const int rows = ((Ly + 3) & ~3) + 2 * W;
-    return (size_t)rows * MP_TS * 8 + 16 + (size_t)(W + 2) * 16 + (size_t)Ly * 128 + (T <= LTY_LUT_MAX ? ((T + 16) & ~15u) : 0);
+    return (size_t)rows * MP_TS * 8 + 16 + (size_t)(W + 2) * 16 + (direct ? 0 : (size_t)Ly * 128) + (T <= LTY_LUT_MAX ? ((T + 16) & ~15u) : 0);
 }
 
 template <int FOOT>
 __global__ void __launch_bounds__(256)
 lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny, int nx, uint32_t T,
-             int W, int Ly, const int *__restrict__ gate)
+             int W, int Ly, const int *__restrict__ gate, int direct)
 {
     if (gate && *gate == 0) return;
     extern __shared__ uint4 lty2_smem[];
@@ -491,8 +494,8 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
     const int rows = ((Ly + 3) & ~3) + 2 * W;                     // Ly rounded up to whole 4-row blocks
     int *range = reinterpret_cast<int *>(tile + (size_t)rows * MP_TS);   // [0] = first useful row, [1] = last
     uint4 *offt = reinterpret_cast<uint4 *>(range + 4);               // [W + 2]: offt[d] = packed capped squares of d .. d+3
-    uint32_t *sout = reinterpret_cast<uint32_t *>(offt + (W + 2));    // [Ly][32] reach bytes of the tile
-    uint8_t *lut = reinterpret_cast<uint8_t *>(sout + (size_t)Ly * 32);   // lut[h] = ceil(sqrt(T - h)), lut[T] = 0
+    uint32_t *sout = reinterpret_cast<uint32_t *>(offt + (W + 2));    // [Ly][32] reach bytes of the tile (not with `direct`)
+    uint8_t *lut = reinterpret_cast<uint8_t *>(sout + (direct ? 0 : (size_t)Ly * 32));   // lut[h] = ceil(sqrt(T - h)), lut[T] = 0
     const bool use_lut = T <= LTY_LUT_MAX;
     const int x0 = blockIdx.x * MP_TX, y0 = blockIdx.y * Ly;
     const int64_t zoff = (int64_t)blockIdx.z * ny;
@@ -614,8 +617,14 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (ry + i < Ly) sout[(ry + i) * 32 + cq] = pack4(m[i][0], m[i][1], m[i][2], m[i][3]);
+            if (ry + i < Ly) {
+                const uint32_t pk = pack4(m[i][0], m[i][1], m[i][2], m[i][3]);
+                if (!direct) sout[(ry + i) * 32 + cq] = pk;
+                else if (y0 + ry + i < ny && x0 + 4 * cq < nx)
+                    *reinterpret_cast<uint32_t *>(reach + (zoff + y0 + ry + i) * nx + x0 + 4 * cq) = pk;
+            }
     }
+    if (direct) return;
     __syncthreads();
     // ---- coalesced write-out of the reach tile (16 bytes per thread)
     for (int i = tid; i < Ly * 8; i += 256) {
@@ -637,16 +646,16 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
 // instead of 8 row loads and 64 VIADDMNMX).  The decision is taken per warp (`__any_sync`), so there is no
 // divergence: a group is scanned by all lanes as soon as one lane needs it, which is harmless (a relaxation
 // with a valid candidate never hurts).  Halo = W rounded up to a multiple of 4 rows so that groups align.
-static inline size_t lt_y3_smem_bytes(int Ly, int W, uint32_t T)
+static inline size_t lt_y3_smem_bytes(int Ly, int W, uint32_t T, int direct)
 {
     const int Hh = (W + 3) & ~3, rows = ((Ly + 3) & ~3) + 2 * Hh;
-    return (size_t)rows * MP_TS * 8 + (size_t)rows * 16 + 16 + (size_t)(Hh + 6) * 16 + (size_t)Ly * 128 +
+    return (size_t)rows * MP_TS * 8 + (size_t)rows * 16 + 16 + (size_t)(Hh + 6) * 16 + (direct ? 0 : (size_t)Ly * 128) +
            (T <= LTY_LUT_MAX ? ((T + 16) & ~15u) : 0);
 }
 
 __global__ void __launch_bounds__(256)
 lt_y3_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny, int nx, uint32_t T,
-             int W, int Ly, const int *__restrict__ gate)
+             int W, int Ly, const int *__restrict__ gate, int direct)
 {
     if (gate && *gate == 0) return;
     extern __shared__ uint4 lty3_smem[];
@@ -657,8 +666,8 @@ lt_y3_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
     uint16_t *cm = reinterpret_cast<uint16_t *>(tile + (size_t)rows * MP_TS);   // [rows / 4][32] group minima
     int *range = reinterpret_cast<int *>(cm + (size_t)ngroups * 32);            // [0] first useful row, [1] last
     uint4 *offt = reinterpret_cast<uint4 *>(range + 4);          // [Hh + 6]: packed capped squares of d .. d+3
-    uint32_t *sout = reinterpret_cast<uint32_t *>(offt + (Hh + 6));             // [Ly][32] reach bytes of the tile
-    uint8_t *lut = reinterpret_cast<uint8_t *>(sout + (size_t)Ly * 32);
+    uint32_t *sout = reinterpret_cast<uint32_t *>(offt + (Hh + 6));             // [Ly][32] reach bytes of the tile (not with `direct`)
+    uint8_t *lut = reinterpret_cast<uint8_t *>(sout + (direct ? 0 : (size_t)Ly * 32));
     const bool use_lut = T <= LTY_LUT_MAX;
     const int x0 = blockIdx.x * MP_TX, y0 = blockIdx.y * Ly;
     const int64_t zoff = (int64_t)blockIdx.z * ny;
@@ -787,9 +796,15 @@ lt_y3_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 m[j] = !reachable ? 0u : (use_lut ? (uint32_t)lut[min(h[j], T)] : (h[j] >= T ? 0u : ceil_sqrt_small(T - h[j])));
-            if (ry + i < Ly) sout[(ry + i) * 32 + cq] = pack4(m[0], m[1], m[2], m[3]);
+            if (ry + i < Ly) {
+                const uint32_t pk = pack4(m[0], m[1], m[2], m[3]);
+                if (!direct) sout[(ry + i) * 32 + cq] = pk;
+                else if (y0 + ry + i < ny && x0 + 4 * cq < nx)
+                    *reinterpret_cast<uint32_t *>(reach + (zoff + y0 + ry + i) * nx + x0 + 4 * cq) = pk;
+            }
         }
     }
+    if (direct) return;
     __syncthreads();
     // ---- coalesced write-out of the reach tile (16 bytes per thread)
     for (int i = tid; i < Ly * 8; i += 256) {

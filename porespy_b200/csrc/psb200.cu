@@ -100,6 +100,8 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->ycoarse = 1;
     c->xbits = 1;
     c->bitquad = 1;
+    c->ydirect = 1;
+    c->edt_h = 48;
     c->flag_slot = 0;
     CUDA_TRY(cudaMalloc(&c->flags, 64 * sizeof(int)));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -154,6 +156,15 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
     }
     if (!strcmp(name, "bit4")) {
         ctx->bit4 = value ? 1 : 0;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "edt_h")) {
+        if (value < 8 || value > 48 || (value & 3)) return fail(PSB200_ERR_INVALID, "set_option: edt_h must be a multiple of 4 in [8,48]");
+        ctx->edt_h = (int)value;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "ydirect")) {
+        ctx->ydirect = value ? 1 : 0;
         return PSB200_OK;
     }
     if (!strcmp(name, "bitquad")) {
@@ -382,7 +393,7 @@ static int launch_minplus(psb200_ctx *ctx, int axis, const typename Src::T *src,
         int *ovf = ctx->flags + (ctx->flag_slot++ & 63u);
         int L16, H16;
         if (n <= 224) { L16 = n; H16 = 0; }
-        else { L16 = 128; H16 = 48; }
+        else { L16 = 128; H16 = ctx->edt_h; }
         const size_t smem16 = (size_t)(((L16 + 3) & ~3) + 2 * H16) * MP_TS * 8 + (size_t)(H16 + 2) * 16;
         const int64_t gx16 = ((nxc + MP_TX - 1) / MP_TX) * ((n + L16 - 1) / L16);
         if (gx16 > 0x7FFFFFFFLL) return fail(PSB200_ERR_UNSUPPORTED, "edt pass: volume too large for one launch");
@@ -840,16 +851,17 @@ static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_
         int Ly = ny < 128 ? (int)ny : 128;
         // hierarchical scan for the denser radii (measured r2c at 1024^3: it wins from W = 25 down -- 2.49 -> 2.25 ms
         // at T = 344 -- and loses above, where seeds are sparse and its larger halo and group minima only cost)
-        const bool coarse = ctx->ycoarse && W <= LTY3_MAX_W && (int)lt_y3_smem_bytes(Ly, W, T) <= ctx->max_smem_optin;
-        const size_t smem = coarse ? lt_y3_smem_bytes(Ly, W, T) : lt_y2_smem_bytes(Ly, W, T);
+        const int direct = ctx->ydirect;
+        const bool coarse = ctx->ycoarse && W <= LTY3_MAX_W && (int)lt_y3_smem_bytes(Ly, W, T, direct) <= ctx->max_smem_optin;
+        const size_t smem = coarse ? lt_y3_smem_bytes(Ly, W, T, direct) : lt_y2_smem_bytes(Ly, W, T, direct);
         if ((int)smem > ctx->max_smem_optin)
             return fail(PSB200_ERR_UNSUPPORTED, "lt_y: tile needs %zu bytes of shared memory", smem);
         dim3 grid((unsigned)((nx + MP_TX - 1) / MP_TX), (unsigned)((ny + Ly - 1) / Ly), (unsigned)nz);
         {
             ProfScope ps__(ctx, st, K_LT_Y);
             // (the 32 x 16 warp footprint that helps the EDT passes is 1 % slower here: r2b)
-            if (coarse) lt_y3_kernel<<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate);
-            else lt_y2_kernel<0><<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate);
+            if (coarse) lt_y3_kernel<<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate, direct);
+            else lt_y2_kernel<0><<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate, direct);
         }
         LAUNCH_CHECK(ctx);
     }

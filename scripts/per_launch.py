@@ -15,6 +15,10 @@ if os.environ.get("BIT_TMAX"):
     ctx.set_bit_tmax(int(os.environ["BIT_TMAX"]))
 if os.environ.get("FOOT"):
     ctx.set_foot(int(os.environ["FOOT"]))
+if os.environ.get("EDT_H"):
+    ctx.set_edt_h(int(os.environ["EDT_H"]))
+if os.environ.get("YDIRECT"):
+    ctx.set_ydirect(int(os.environ["YDIRECT"]))
 if os.environ.get("BITQUAD"):
     ctx.set_bitquad(int(os.environ["BITQUAD"]))
 if os.environ.get("XBITS"):
