@@ -178,7 +178,7 @@ class Context:
         check(self.lib.psb200_set_option(self.handle, b"foot", int(foot)))
 
     def set_edt_h(self, rows):
-        """Halo rows of the 16-bit EDT tiles (default 48)."""
+        """Halo rows of the 16-bit EDT tiles (default 32)."""
         check(self.lib.psb200_set_option(self.handle, b"edt_h", int(rows)))
 
     def set_ydirect(self, on):

@@ -27,7 +27,8 @@ struct psb200_ctx {
     int bit_tmax;      // thresholds T <= bit_tmax use the bit-parallel dilation (0: never)
     int bit4;          // bit path: four-words-per-lane kernel for rows of 32 / 64 / 128 words
     int foot;          // warp footprint of the 16-bit EDT min-plus scans: 0 = 64 x 8 voxels, 1 = 32 x 16 (default: 3 % faster, r2b)
-    int edt_h;         // halo rows staged on each side of a 128-row tile of the 16-bit EDT passes (scans beyond it read global memory)
+    int edt_h;         // halo rows staged on each side of a 128-row tile of the 16-bit EDT passes (scans beyond it read global
+                       // memory); 32: 52 KB of shared memory, 4 resident blocks per SM -- y 3.48 -> 3.20, z 3.18 -> 2.71 ms vs 48 (r2m)
     int ydirect;       // per-radius y pass: reach bytes straight from registers to global memory (default) / via a tile copy
     int bitquad;       // bit path: two output rows per lane (lt_bitball4d_kernel, default) / one row per lane
     int xbits;         // per-radius x pass from packed seed bits (xdist_bits_kernel, default) or from the class map

@@ -250,6 +250,8 @@ edt_minplus_kernel(const typename Src::T *__restrict__ src, void *__restrict__ d
 // recomputes the pass.
 #define MP16_CAP 0x7FFFu
 #define MP16_WARPS 8
+struct MpTrue { static constexpr bool value = true; };
+struct MpFalse { static constexpr bool value = false; };
 
 __device__ __forceinline__ uint2 mp16_pack(const uint4 &v)
 {
@@ -308,131 +310,160 @@ edt_minplus16_kernel(const typename Src::T *__restrict__ src, void *__restrict__
     __syncthreads();
 
     // A lane owns 4 rows x 4 columns; warp footprint 64 columns x 8 rows (16 column groups x 2 row
-    // blocks: every half-warp reads 128 contiguous bytes of one tile row).  Block: 2 warps across x, 4 down.
+    // blocks: every half-warp reads 128 contiguous bytes of one tile row) or 32 x 16 (FOOT 1).
+    // FULL (decided per block): the tile lies inside the volume, rows and columns, and stores go to the plain layout,
+    // so the per-row / per-column bounds tests and the 64-bit index arithmetic of the general form drop out (they were
+    // 45 % of the executed instructions: profiles/r2g_sass_hotspots.txt)
     uint32_t lmax = 0, amax = 0;
     const int cq = FOOT ? (warp & 3) * 8 + (lane & 7) : (warp & 1) * 16 + (lane & 15);
     const int xl = 4 * cq;
-    for (int ry = FOOT ? ((warp >> 2) * 4 + (lane >> 3)) * 4 : ((warp >> 1) * 2 + (lane >> 4)) * 4; ry < L; ry += 32) {
-        const int gr = row0 + ry;
-        if (gr >= n) break;
-        const int rr = ry + H;
-        uint2 O[4];
-        uint32_t B0[4], B1[4];
+    const int ry0 = FOOT ? ((warp >> 2) * 4 + (lane >> 3)) * 4 : ((warp >> 1) * 2 + (lane >> 4)) * 4;
+    auto body = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        for (int ry = ry0; ry < L; ry += 32) {
+            const int gr = row0 + ry;
+            if (!FULL && gr >= n) break;
+            const int rr = ry + H;
+            uint2 O[4];
+            uint32_t B0[4], B1[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) O[i] = tile[(rr + i) * MP_TS + cq];
+            for (int i = 0; i < 4; ++i) O[i] = tile[(rr + i) * MP_TS + cq];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            B0[i] = O[i].x;
-            B1[i] = O[i].y;
+            for (int i = 0; i < 4; ++i) {
+                B0[i] = O[i].x;
+                B1[i] = O[i].y;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j != i) {
-                    const uint32_t d = (uint32_t)((i - j) * (i - j)) * 0x00010001u;
-                    B0[i] = __viaddmin_u16x2(O[j].x, d, B0[i]);
-                    B1[i] = __viaddmin_u16x2(O[j].y, d, B1[i]);
+                for (int j = 0; j < 4; ++j)
+                    if (j != i) {
+                        const uint32_t d = (uint32_t)((i - j) * (i - j)) * 0x00010001u;
+                        B0[i] = __viaddmin_u16x2(O[j].x, d, B0[i]);
+                        B1[i] = __viaddmin_u16x2(O[j].y, d, B1[i]);
+                    }
+                if (!FULL && gr + i >= n) B0[i] = B1[i] = 0u;                // rows past the end: nothing to do
+            }
+            const int dlim = FULL ? H : min(min(rr, rows - 1 - (rr + 3)), H);
+            int dy = 1;
+            bool done = false;
+            // fast loop: both fetched rows are inside the staged tile (rows outside the volume hold the cap);
+            // two steps per termination test (a step past the bound only relaxes with valid candidates)
+            while (dy <= dlim) {
+                const uint32_t m2 = __vmaxu2(__vmaxu2(__vmaxu2(B0[0], B1[0]), __vmaxu2(B0[1], B1[1])),
+                                             __vmaxu2(__vmaxu2(B0[2], B1[2]), __vmaxu2(B0[3], B1[3])));
+                const uint32_t bm = max(m2 & 0xFFFFu, m2 >> 16);
+                if ((uint32_t)(dy * dy) >= bm) { done = true; break; }
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    if (dy > dlim) break;
+                    const uint2 top = tile[(rr - dy) * MP_TS + cq];
+                    const uint2 bot = tile[(rr + 3 + dy) * MP_TS + cq];
+                    const uint4 o4 = offt[dy];
+                    const uint32_t of[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        B0[i] = __viaddmin_u16x2(top.x, of[i], B0[i]); B1[i] = __viaddmin_u16x2(top.y, of[i], B1[i]);
+                        B0[i] = __viaddmin_u16x2(bot.x, of[3 - i], B0[i]); B1[i] = __viaddmin_u16x2(bot.y, of[3 - i], B1[i]);
+                    }
+                    ++dy;
                 }
-            if (gr + i >= n) B0[i] = B1[i] = 0u;                         // rows past the end: nothing to do
-        }
-        const int dlim = min(min(rr, rows - 1 - (rr + 3)), H);
-        int dy = 1;
-        bool done = false;
-        // fast loop: both fetched rows are inside the staged tile (rows outside the volume hold the cap);
-        // two steps per termination test (a step past the bound only relaxes with valid candidates)
-        while (dy <= dlim) {
-            const uint32_t m2 = __vmaxu2(__vmaxu2(__vmaxu2(B0[0], B1[0]), __vmaxu2(B0[1], B1[1])),
-                                         __vmaxu2(__vmaxu2(B0[2], B1[2]), __vmaxu2(B0[3], B1[3])));
-            const uint32_t bm = max(m2 & 0xFFFFu, m2 >> 16);
-            if ((uint32_t)(dy * dy) >= bm) { done = true; break; }
+            }
+            // slow loop (rare): rows beyond the staged halo come from global memory
+            while (!done) {
+                const uint32_t m2 = __vmaxu2(__vmaxu2(__vmaxu2(B0[0], B1[0]), __vmaxu2(B0[1], B1[1])),
+                                             __vmaxu2(__vmaxu2(B0[2], B1[2]), __vmaxu2(B0[3], B1[3])));
+                const uint32_t bm = max(m2 & 0xFFFFu, m2 >> 16);
+                const bool up_in = gr - dy >= 0, dn_in = gr + 3 + dy < n;
+                if ((uint32_t)dy * (uint32_t)dy >= bm || (!up_in && !dn_in)) break;
+                const uint32_t of[4] = {mp16_off(dy), mp16_off(dy + 1), mp16_off(dy + 2), mp16_off(dy + 3)};
+                if (up_in) {
+                    const uint2 top = (rr - dy >= 0) ? tile[(rr - dy) * MP_TS + cq]
+                                                     : mp16_pack(mp_load_row<Src>(sbase + (int64_t)(gr - dy) * rstride, xl, valid, vec));
 #pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                if (dy > dlim) break;
-                const uint2 top = tile[(rr - dy) * MP_TS + cq];
-                const uint2 bot = tile[(rr + 3 + dy) * MP_TS + cq];
-                const uint4 o4 = offt[dy];
-                const uint32_t of[4] = {o4.x, o4.y, o4.z, o4.w};
+                    for (int i = 0; i < 4; ++i) {
+                        B0[i] = __viaddmin_u16x2(top.x, of[i], B0[i]); B1[i] = __viaddmin_u16x2(top.y, of[i], B1[i]);
+                    }
+                }
+                if (dn_in) {
+                    const int rb = rr + 3 + dy;
+                    const uint2 bot = (rb < rows) ? tile[rb * MP_TS + cq]
+                                                  : mp16_pack(mp_load_row<Src>(sbase + (int64_t)(gr + 3 + dy) * rstride, xl, valid, vec));
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    B0[i] = __viaddmin_u16x2(top.x, of[i], B0[i]); B1[i] = __viaddmin_u16x2(top.y, of[i], B1[i]);
-                    B0[i] = __viaddmin_u16x2(bot.x, of[3 - i], B0[i]); B1[i] = __viaddmin_u16x2(bot.y, of[3 - i], B1[i]);
+                    for (int i = 0; i < 4; ++i) {
+                        B0[i] = __viaddmin_u16x2(bot.x, of[3 - i], B0[i]); B1[i] = __viaddmin_u16x2(bot.y, of[3 - i], B1[i]);
+                    }
                 }
                 ++dy;
             }
-        }
-        // slow loop (rare): rows beyond the staged halo come from global memory
-        while (!done) {
-            const uint32_t m2 = __vmaxu2(__vmaxu2(__vmaxu2(B0[0], B1[0]), __vmaxu2(B0[1], B1[1])),
-                                         __vmaxu2(__vmaxu2(B0[2], B1[2]), __vmaxu2(B0[3], B1[3])));
-            const uint32_t bm = max(m2 & 0xFFFFu, m2 >> 16);
-            const bool up_in = gr - dy >= 0, dn_in = gr + 3 + dy < n;
-            if ((uint32_t)dy * (uint32_t)dy >= bm || (!up_in && !dn_in)) break;
-            const uint32_t of[4] = {mp16_off(dy), mp16_off(dy + 1), mp16_off(dy + 2), mp16_off(dy + 3)};
-            if (up_in) {
-                const uint2 top = (rr - dy >= 0) ? tile[(rr - dy) * MP_TS + cq]
-                                                 : mp16_pack(mp_load_row<Src>(sbase + (int64_t)(gr - dy) * rstride, xl, valid, vec));
+            // ---- store the block
+            if (FULL) {
+                char *orow = reinterpret_cast<char *>(dst) + 4 * ((int64_t)blockIdx.y * ostride + x0 + (int64_t)gr * rstride + xl);
+                const uint32_t r01 = __vmaxu2(__vmaxu2(B0[0], B1[0]), __vmaxu2(B0[1], B1[1]));
+                const uint32_t r23 = __vmaxu2(__vmaxu2(B0[2], B1[2]), __vmaxu2(B0[3], B1[3]));
+                const uint32_t m2 = __vmaxu2(r01, r23);
+                amax = max(amax, max(m2 & 0xFFFFu, m2 >> 16));
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    B0[i] = __viaddmin_u16x2(top.x, of[i], B0[i]); B1[i] = __viaddmin_u16x2(top.y, of[i], B1[i]);
+                    const uint32_t o[4] = {B0[i] & 0xFFFFu, B0[i] >> 16, B1[i] & 0xFFFFu, B1[i] >> 16};
+                    if (gr + i >= mrow0 && gr + i < mrow1) {
+                        const uint32_t mi = __vmaxu2(B0[i], B1[i]);
+                        lmax = max(lmax, max(mi & 0xFFFFu, mi >> 16));
+                    }
+                    if (OUT == 0) *reinterpret_cast<uint4 *>(orow) = make_uint4(o[0], o[1], o[2], o[3]);
+                    else *reinterpret_cast<float4 *>(orow) = make_float4(sqrtf((float)o[0]), sqrtf((float)o[1]), sqrtf((float)o[2]), sqrtf((float)o[3]));
+                    orow += 4 * rstride;
                 }
+                continue;
             }
-            if (dn_in) {
-                const int rb = rr + 3 + dy;
-                const uint2 bot = (rb < rows) ? tile[rb * MP_TS + cq]
-                                              : mp16_pack(mp_load_row<Src>(sbase + (int64_t)(gr + 3 + dy) * rstride, xl, valid, vec));
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    B0[i] = __viaddmin_u16x2(bot.x, of[3 - i], B0[i]); B1[i] = __viaddmin_u16x2(bot.y, of[3 - i], B1[i]);
+            for (int i = 0; i < 4; ++i) {
+                const int g = gr + i;
+                if (g >= n || ry + i >= L) continue;
+                int64_t oi = (int64_t)blockIdx.y * ostride + x0 + (int64_t)g * rstride + xl;
+                if (split > 0) {
+                    // y pass of a z-slab: all-to-all send layout [dest d][z][y - d*split][x]
+                    const int d = g / split, yy = g - d * split;
+                    const int nyd = min(split, n - d * split);
+                    oi = ((int64_t)d * split * gridDim.y + (int64_t)blockIdx.y * nyd + yy) * rstride + x0 + xl;
                 }
-            }
-            ++dy;
-        }
-        // ---- store the block
+                const uint32_t o[4] = {B0[i] & 0xFFFFu, B0[i] >> 16, B1[i] & 0xFFFFu, B1[i] >> 16};
+                {   // row maximum: every row feeds the overflow test, the rows [mrow0, mrow1) feed gmax
+                    uint32_t rmax = 0;
+                    if (xl + 3 < valid) {
+                        const uint32_t m2 = __vmaxu2(B0[i], B1[i]);
+                        rmax = max(m2 & 0xFFFFu, m2 >> 16);
+                    } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int g = gr + i;
-            if (g >= n || ry + i >= L) continue;
-            int64_t oi = (int64_t)blockIdx.y * ostride + x0 + (int64_t)g * rstride + xl;
-            if (split > 0) {
-                // y pass of a z-slab: all-to-all send layout [dest d][z][y - d*split][x]
-                const int d = g / split, yy = g - d * split;
-                const int nyd = min(split, n - d * split);
-                oi = ((int64_t)d * split * gridDim.y + (int64_t)blockIdx.y * nyd + yy) * rstride + x0 + xl;
-            }
-            const uint32_t o[4] = {B0[i] & 0xFFFFu, B0[i] >> 16, B1[i] & 0xFFFFu, B1[i] >> 16};
-            {   // row maximum: every row feeds the overflow test, the rows [mrow0, mrow1) feed gmax
-                uint32_t rmax = 0;
-                if (xl + 3 < valid) {
-                    const uint32_t m2 = __vmaxu2(B0[i], B1[i]);
-                    rmax = max(m2 & 0xFFFFu, m2 >> 16);
+                        for (int j = 0; j < 4; ++j)
+                            if (xl + j < valid) rmax = max(rmax, o[j]);
+                    }
+                    amax = max(amax, rmax);
+                    if (g >= mrow0 && g < mrow1) lmax = max(lmax, rmax);
+                }
+                if (OUT == 0) {
+                    uint32_t *orow = reinterpret_cast<uint32_t *>(dst) + oi;
+                    if (vec && xl + 3 < valid) *reinterpret_cast<uint4 *>(orow) = make_uint4(o[0], o[1], o[2], o[3]);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (xl + j < valid) orow[j] = o[j];
+                    }
                 } else {
+                    float *orow = reinterpret_cast<float *>(dst) + oi;
+                    float f[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (xl + j < valid) rmax = max(rmax, o[j]);
-                }
-                amax = max(amax, rmax);
-                if (g >= mrow0 && g < mrow1) lmax = max(lmax, rmax);
-            }
-            if (OUT == 0) {
-                uint32_t *orow = reinterpret_cast<uint32_t *>(dst) + oi;
-                if (vec && xl + 3 < valid) *reinterpret_cast<uint4 *>(orow) = make_uint4(o[0], o[1], o[2], o[3]);
-                else {
+                    for (int j = 0; j < 4; ++j) f[j] = sqrtf((float)o[j]);
+                    if (vec && xl + 3 < valid) *reinterpret_cast<float4 *>(orow) = make_float4(f[0], f[1], f[2], f[3]);
+                    else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (xl + j < valid) orow[j] = o[j];
-                }
-            } else {
-                float *orow = reinterpret_cast<float *>(dst) + oi;
-                float f[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) f[j] = sqrtf((float)o[j]);
-                if (vec && xl + 3 < valid) *reinterpret_cast<float4 *>(orow) = make_float4(f[0], f[1], f[2], f[3]);
-                else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (xl + j < valid) orow[j] = f[j];
+                        for (int j = 0; j < 4; ++j)
+                            if (xl + j < valid) orow[j] = f[j];
+                    }
                 }
             }
         }
-    }
+    };
+    const bool full = vec && valid >= MP_TX && row0 + L <= n && (L & 3) == 0 && split == 0;
+    if (full) body(MpTrue());
+    else body(MpFalse());
     if (__any_sync(0xFFFFFFFFu, amax >= MP16_CAP) && lane == 0) *overflow = 1;
     if (gmax) {
         lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);

@@ -101,7 +101,7 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->xbits = 1;
     c->bitquad = 1;
     c->ydirect = 1;
-    c->edt_h = 48;
+    c->edt_h = 32;
     c->flag_slot = 0;
     CUDA_TRY(cudaMalloc(&c->flags, 64 * sizeof(int)));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
