@@ -315,20 +315,10 @@ lt_mark_written_kernel(const double *__restrict__ out, uint8_t *__restrict__ idx
 // =========================================================================================
 
 // ------------------------------------------------------------------------------ z sweeps
-// Thread = 4 adjacent columns of the [nz][plane] view.  Forward sweep rewrites reach in place
-// with the forward cone value; the backward sweep runs on those values (cones compose) and
-// writes the radius index where the voxel is covered and still unwritten.
-__device__ __forceinline__ uint32_t cone_step(uint32_t v, int (&c)[4])
-{
-    uint32_t pk = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        c[j] = max((int)byte_of(v, j), c[j] - 1);
-        pk |= (uint32_t)c[j] << (8 * j);
-    }
-    return pk;
-}
-
+// Thread = 4 adjacent columns of the [nz][plane] view, one byte lane each (SIMD-within-a-register:
+// c = max(v, c - 1) is __vmaxu4(v, __vsubus4(c, 1)) for the four columns at once).  Forward sweep rewrites reach in
+// place with the forward cone value (only where it differs); the backward sweep runs on those values (cones
+// compose) and writes the radius index where the voxel is covered and still unwritten.
 #define ZS_UNROLL 8
 // 8 blocks per SM (<= 32 registers): the plane/4 threads of a 1024^2 plane then fit in ONE wave
 // (262144 <= 148 * 2048); with 48 registers the launch ran 1.4 waves and its tail idled the SMs
@@ -340,8 +330,10 @@ lt_zsweep_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo, 
     if (gate && *gate == 0) return;
     const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (p >= plane) return;
-    int c[4] = {0, 0, 0, 0};
-    for (int z = 0; z < nlo; ++z) cone_step(__ldg(reinterpret_cast<const uint32_t *>(m_lo + (int64_t)z * plane + p)), c);
+    const uint32_t ONE4 = 0x01010101u, val4 = val * 0x01010101u;
+    uint32_t c = 0;
+    for (int z = 0; z < nlo; ++z)
+        c = __vmaxu4(__ldg(reinterpret_cast<const uint32_t *>(m_lo + (int64_t)z * plane + p)), __vsubus4(c, ONE4));
     uint32_t *col = reinterpret_cast<uint32_t *>(reach + p);
     const int64_t ps = plane >> 2;                 // plane stride in u32
     int z = 0;
@@ -352,18 +344,19 @@ lt_zsweep_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo, 
 #pragma unroll
         for (int i = 0; i < ZS_UNROLL; ++i) {
             // the forward value differs from the reach byte only inside a cone: most stores are not needed
-            const uint32_t f = cone_step(v[i], c);
-            if (f != v[i]) col[(int64_t)(z + i) * ps] = f;
+            c = __vmaxu4(v[i], __vsubus4(c, ONE4));
+            if (c != v[i]) col[(int64_t)(z + i) * ps] = c;
         }
     }
     for (; z < nz; ++z) {
-        const uint32_t v = col[(int64_t)z * ps], f = cone_step(v, c);
-        if (f != v) col[(int64_t)z * ps] = f;
+        const uint32_t v = col[(int64_t)z * ps];
+        c = __vmaxu4(v, __vsubus4(c, ONE4));
+        if (c != v) col[(int64_t)z * ps] = c;
     }
 
-#pragma unroll
-    for (int j = 0; j < 4; ++j) c[j] = 0;
-    for (int zz = nhi - 1; zz >= 0; --zz) cone_step(__ldg(reinterpret_cast<const uint32_t *>(m_hi + (int64_t)zz * plane + p)), c);
+    c = 0;
+    for (int zz = nhi - 1; zz >= 0; --zz)
+        c = __vmaxu4(__ldg(reinterpret_cast<const uint32_t *>(m_hi + (int64_t)zz * plane + p)), __vsubus4(c, ONE4));
     uint32_t *icol = reinterpret_cast<uint32_t *>(idx + p);
     z = nz - 1;
     for (; z - ZS_UNROLL + 1 >= 0; z -= ZS_UNROLL) {
@@ -372,26 +365,20 @@ lt_zsweep_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo, 
         for (int i = 0; i < ZS_UNROLL; ++i) v[i] = col[(int64_t)(z - i) * ps];
 #pragma unroll
         for (int i = 0; i < ZS_UNROLL; ++i) {
-            const uint32_t f = cone_step(v[i], c);
-            if (f) {
+            c = __vmaxu4(v[i], __vsubus4(c, ONE4));
+            if (c) {
                 const uint32_t old = icol[(int64_t)(z - i) * ps];
-                uint32_t nw = old;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (byte_of(f, j) && byte_of(old, j) == 0) nw |= val << (8 * j);
-                if (nw != old) icol[(int64_t)(z - i) * ps] = nw;
+                const uint32_t m = __vcmpne4(c, 0u) & __vcmpeq4(old, 0u);      // covered and still unwritten
+                if (m) icol[(int64_t)(z - i) * ps] = old | (val4 & m);
             }
         }
     }
     for (; z >= 0; --z) {
-        const uint32_t f = cone_step(col[(int64_t)z * ps], c);
-        if (f) {
+        c = __vmaxu4(col[(int64_t)z * ps], __vsubus4(c, ONE4));
+        if (c) {
             const uint32_t old = icol[(int64_t)z * ps];
-            uint32_t nw = old;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (byte_of(f, j) && byte_of(old, j) == 0) nw |= val << (8 * j);
-            if (nw != old) icol[(int64_t)z * ps] = nw;
+            const uint32_t m = __vcmpne4(c, 0u) & __vcmpeq4(old, 0u);
+            if (m) icol[(int64_t)z * ps] = old | (val4 & m);
         }
     }
 }
