@@ -177,6 +177,10 @@ class Context:
         8 rows, 1 = 32 x 16."""
         check(self.lib.psb200_set_option(self.handle, b"foot", int(foot)))
 
+    def set_zwide(self, on):
+        """z sweeps: 8 columns per thread, 16 planes in flight (default) / 4 columns, 8 planes."""
+        check(self.lib.psb200_set_option(self.handle, b"zwide", 1 if on else 0))
+
     def set_edt_h(self, rows):
         """Halo rows of the 16-bit EDT tiles (default 32)."""
         check(self.lib.psb200_set_option(self.handle, b"edt_h", int(rows)))

@@ -382,3 +382,76 @@ lt_zsweep_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo, 
         }
     }
 }
+
+// The same sweeps with 8 columns per thread (one 8-byte load per plane) and 16 planes in flight: half the threads,
+// four times the bytes in flight per thread -- the sweeps are bound by memory latency and bandwidth, not by the ALU.
+#define ZS2_UNROLL 16
+// 128-thread blocks, 7 per SM (<= 73 registers): the plane/8 threads of a 1024^2 plane are 1024 blocks <= 148 * 7
+__global__ void __launch_bounds__(128, 7)
+lt_zsweep8_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo, int nlo,
+                  const uint8_t *__restrict__ m_hi, int nhi, uint8_t *__restrict__ idx, int nz,
+                  int64_t plane, uint32_t val, const int *__restrict__ gate)
+{
+    if (gate && *gate == 0) return;
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (p >= plane) return;
+    const uint32_t ONE4 = 0x01010101u, val4 = val * 0x01010101u;
+    uint32_t c0 = 0, c1 = 0;
+    for (int z = 0; z < nlo; ++z) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(m_lo + (int64_t)z * plane + p));
+        c0 = __vmaxu4(v.x, __vsubus4(c0, ONE4));
+        c1 = __vmaxu4(v.y, __vsubus4(c1, ONE4));
+    }
+    uint2 *col = reinterpret_cast<uint2 *>(reach + p);
+    const int64_t ps = plane >> 3;                 // plane stride in uint2
+    int z = 0;
+    for (; z + ZS2_UNROLL <= nz; z += ZS2_UNROLL) {
+        uint2 v[ZS2_UNROLL];
+#pragma unroll
+        for (int i = 0; i < ZS2_UNROLL; ++i) v[i] = col[(int64_t)(z + i) * ps];
+#pragma unroll
+        for (int i = 0; i < ZS2_UNROLL; ++i) {
+            c0 = __vmaxu4(v[i].x, __vsubus4(c0, ONE4));
+            c1 = __vmaxu4(v[i].y, __vsubus4(c1, ONE4));
+            if (c0 != v[i].x || c1 != v[i].y) col[(int64_t)(z + i) * ps] = make_uint2(c0, c1);
+        }
+    }
+    for (; z < nz; ++z) {
+        const uint2 v = col[(int64_t)z * ps];
+        c0 = __vmaxu4(v.x, __vsubus4(c0, ONE4));
+        c1 = __vmaxu4(v.y, __vsubus4(c1, ONE4));
+        if (c0 != v.x || c1 != v.y) col[(int64_t)z * ps] = make_uint2(c0, c1);
+    }
+    c0 = c1 = 0;
+    for (int zz = nhi - 1; zz >= 0; --zz) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(m_hi + (int64_t)zz * plane + p));
+        c0 = __vmaxu4(v.x, __vsubus4(c0, ONE4));
+        c1 = __vmaxu4(v.y, __vsubus4(c1, ONE4));
+    }
+    uint2 *icol = reinterpret_cast<uint2 *>(idx + p);
+    auto commit = [&](int64_t zrow) {
+        if (c0 | c1) {
+            const uint2 old = icol[zrow * ps];
+            const uint32_t m0 = __vcmpne4(c0, 0u) & __vcmpeq4(old.x, 0u), m1 = __vcmpne4(c1, 0u) & __vcmpeq4(old.y, 0u);
+            if (m0 | m1) icol[zrow * ps] = make_uint2(old.x | (val4 & m0), old.y | (val4 & m1));
+        }
+    };
+    z = nz - 1;
+    for (; z - ZS2_UNROLL + 1 >= 0; z -= ZS2_UNROLL) {
+        uint2 v[ZS2_UNROLL];
+#pragma unroll
+        for (int i = 0; i < ZS2_UNROLL; ++i) v[i] = col[(int64_t)(z - i) * ps];
+#pragma unroll
+        for (int i = 0; i < ZS2_UNROLL; ++i) {
+            c0 = __vmaxu4(v[i].x, __vsubus4(c0, ONE4));
+            c1 = __vmaxu4(v[i].y, __vsubus4(c1, ONE4));
+            commit(z - i);
+        }
+    }
+    for (; z >= 0; --z) {
+        const uint2 v = col[(int64_t)z * ps];
+        c0 = __vmaxu4(v.x, __vsubus4(c0, ONE4));
+        c1 = __vmaxu4(v.y, __vsubus4(c1, ONE4));
+        commit(z);
+    }
+}

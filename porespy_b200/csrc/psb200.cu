@@ -102,6 +102,7 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->bitquad = 1;
     c->ydirect = 1;
     c->edt_h = 32;
+    c->zwide = 1;
     c->flag_slot = 0;
     CUDA_TRY(cudaMalloc(&c->flags, 64 * sizeof(int)));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -156,6 +157,10 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
     }
     if (!strcmp(name, "bit4")) {
         ctx->bit4 = value ? 1 : 0;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "zwide")) {
+        ctx->zwide = value ? 1 : 0;
         return PSB200_OK;
     }
     if (!strcmp(name, "edt_h")) {
@@ -876,11 +881,16 @@ static int lt_z_stream_impl(psb200_ctx *ctx, uint8_t *reach, const uint8_t *m_lo
     const int64_t plane = ny * nx;
     if (nlo > W) { m_lo += (int64_t)(nlo - W) * plane; nlo = W; }
     if (nhi > W) nhi = W;
-    const unsigned grid = (unsigned)((plane / 4 + 255) / 256);
+    const bool wide = ctx->zwide && plane % 8 == 0 &&
+                      ((((uintptr_t)reach | (uintptr_t)idx | (uintptr_t)m_lo | (uintptr_t)m_hi) & 7u) == 0);
     {
         ProfScope ps__(ctx, st, K_LT_Z);
-        lt_zsweep_kernel<<<grid, 256, 0, st>>>(reach, m_lo, nlo, m_hi, nhi, idx, (int)nz, plane,
-                                               (uint32_t)(k + 1), gate);
+        if (wide)
+            lt_zsweep8_kernel<<<(unsigned)((plane / 8 + 127) / 128), 128, 0, st>>>(reach, m_lo, nlo, m_hi, nhi, idx, (int)nz, plane,
+                                                                                 (uint32_t)(k + 1), gate);
+        else
+            lt_zsweep_kernel<<<(unsigned)((plane / 4 + 255) / 256), 256, 0, st>>>(reach, m_lo, nlo, m_hi, nhi, idx, (int)nz, plane,
+                                                                                (uint32_t)(k + 1), gate);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
