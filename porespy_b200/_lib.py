@@ -177,6 +177,10 @@ class Context:
         8 rows, 1 = 32 x 16."""
         check(self.lib.psb200_set_option(self.handle, b"foot", int(foot)))
 
+    def set_yflags(self, on):
+        """Byte path: activity flags from the x pass let the y pass skip idle tiles and rows (default on)."""
+        check(self.lib.psb200_set_option(self.handle, b"yflags", 1 if on else 0))
+
     def set_zwide(self, on):
         """z sweeps: 8 columns per thread, 16 planes in flight (default) / 4 columns, 8 planes."""
         check(self.lib.psb200_set_option(self.handle, b"zwide", 1 if on else 0))

@@ -510,13 +510,14 @@ __device__ __forceinline__ uint32_t sq_cap2(uint32_t a, uint32_t b, uint32_t W, 
 static inline size_t lt_y2_smem_bytes(int Ly, int W, uint32_t T, int direct)
 {
     const int rows = ((Ly + 3) & ~3) + 2 * W;
-    return (size_t)rows * MP_TS * 8 + 16 + (size_t)(W + 2) * 16 + (direct ? 0 : (size_t)Ly * 128) + (T <= LTY_LUT_MAX ? ((T + 16) & ~15u) : 0);
+    return (size_t)rows * MP_TS * 8 + 16 + (size_t)(W + 2) * 16 + (direct ? 0 : (size_t)Ly * 128) +
+           (T <= LTY_LUT_MAX ? ((T + 16) & ~15u) : 0) + (size_t)((rows + 15) & ~15);
 }
 
 template <int FOOT>
 __global__ void __launch_bounds__(256)
 lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny, int nx, uint32_t T,
-             int W, int Ly, const int *__restrict__ gate, int direct)
+             int W, int Ly, const int *__restrict__ gate, int direct, const uint8_t *__restrict__ xflag)
 {
     if (gate && *gate == 0) return;
     extern __shared__ uint4 lty2_smem[];
@@ -528,6 +529,7 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
     uint32_t *sout = reinterpret_cast<uint32_t *>(offt + (W + 2));    // [Ly][32] reach bytes of the tile (not with `direct`)
     uint8_t *lut = reinterpret_cast<uint8_t *>(sout + (direct ? 0 : (size_t)Ly * 32));   // lut[h] = ceil(sqrt(T - h)), lut[T] = 0
     const bool use_lut = T <= LTY_LUT_MAX;
+    uint8_t *rowuse = lut + (use_lut ? ((T + 16) & ~15u) : 0);    // [rows] with xflag: the row holds a value below T
     const int x0 = blockIdx.x * MP_TX, y0 = blockIdx.y * Ly;
     const int64_t zoff = (int64_t)blockIdx.z * ny;
     if (tid == 0) { range[0] = rows; range[1] = -1; }
@@ -541,10 +543,40 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
         offt[d] = make_uint4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
+    // ---- with activity flags from the x pass (one byte per 32-voxel word): which rows of the window can hold a value
+    // below T at all; a tile without any writes zeros and leaves, the others skip the loads of their idle rows
+    int lo = rows, hi = -1;
+    if (xflag) {
+        const int nw = nx >> 5, w0 = blockIdx.x * (MP_TX / 32);
+        for (int r = tid; r < rows; r += 256) {
+            const int y = y0 - W + r;
+            uint32_t f = 0;
+            if (y >= 0 && y < ny) {
+                const uint8_t *fr = xflag + (zoff + y) * nw;
+#pragma unroll
+                for (int q = 0; q < MP_TX / 32; ++q)
+                    if (w0 + q < nw) f |= fr[w0 + q];
+            }
+            rowuse[r] = f ? 1 : 0;
+            if (f) { lo = min(lo, r); hi = max(hi, r); }
+        }
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if (lane == 0 && hi >= 0) { atomicMin(&range[0], lo); atomicMax(&range[1], hi); }
+    }
+    __syncthreads();
+    if (xflag && range[1] < 0) {
+        for (int i = tid; i < Ly * 8; i += 256) {
+            const int r = i >> 3, ch = i & 7;
+            const int y = y0 + r, x = x0 + 16 * ch;
+            if (y < ny && x < nx) *reinterpret_cast<uint4 *>(reach + (zoff + y) * nx + x) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        return;
+    }
 
     // ---- stage: thread = 16 voxels of one row (8 threads per row, 32 rows per sweep)
     const uint32_t uW = (uint32_t)W;
-    int lo = rows, hi = -1;
+    lo = rows, hi = -1;
     for (int i0 = 0; i0 < rows * 8; i0 += 4 * 256) {
         uint4 v[4];
 #pragma unroll
@@ -552,7 +584,7 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
             const int i = i0 + u * 256 + tid, r = i >> 3, ch = i & 7;
             const int y = y0 - W + r, x = x0 + 16 * ch;
             v[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            if (r < rows && y >= 0 && y < ny && x < nx)
+            if (r < rows && y >= 0 && y < ny && x < nx && (!xflag || rowuse[r]))
                 v[u] = __ldg(reinterpret_cast<const uint4 *>(gx + (zoff + y) * nx + x));
         }
 #pragma unroll
@@ -575,9 +607,11 @@ lt_y2_kernel(const uint8_t *__restrict__ gx, uint8_t *__restrict__ reach, int ny
             if (useful) { lo = min(lo, r); hi = max(hi, r); }
         }
     }
-    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
-    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
-    if (lane == 0 && hi >= 0) { atomicMin(&range[0], lo); atomicMax(&range[1], hi); }
+    if (!xflag) {
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if (lane == 0 && hi >= 0) { atomicMin(&range[0], lo); atomicMax(&range[1], hi); }
+    }
     __syncthreads();
     const int rlo = range[0], rhi = range[1];
 

@@ -103,6 +103,7 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->ydirect = 1;
     c->edt_h = 32;
     c->zwide = 1;
+    c->yflags = 1;
     c->flag_slot = 0;
     CUDA_TRY(cudaMalloc(&c->flags, 64 * sizeof(int)));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -157,6 +158,10 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
     }
     if (!strcmp(name, "bit4")) {
         ctx->bit4 = value ? 1 : 0;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "yflags")) {
+        ctx->yflags = value ? 1 : 0;
         return PSB200_OK;
     }
     if (!strcmp(name, "zwide")) {
@@ -695,6 +700,7 @@ static size_t uf_list_entries(int64_t n) { return (size_t)(n < UF_SEG ? n : UF_S
 
 struct LtWorkspace {
     uint8_t *cls, *rcls, *reach, *gx;
+    uint8_t *xflag;                 // byte path: activity byte per 32-voxel word from the bit-based x pass
     uint32_t *seedbits, *written;   // bit path: one bit per voxel (seed bits of up to PACKN_MAX consecutive radii)
     size_t seed_words;              // words of one seed-bit volume inside seedbits
     uint32_t *parent;
@@ -716,6 +722,7 @@ static LtWorkspace carve_lt(const psb200_ctx *ctx, char *base, int64_t nz, int64
     w.cls = c.take<uint8_t>(n + 16);
     w.reach = c.take<uint8_t>(n + 16);
     w.gx = c.take<uint8_t>(n + 16);
+    w.xflag = c.take<uint8_t>(n / 32 + 64);
     w.seed_words = (n / 32 + 4 + 63) & ~(size_t)63;                 // keeps every volume 256-byte aligned
     w.seedbits = c.take<uint32_t>(w.seed_words * PACKN_MAX);
     w.written = c.take<uint32_t>(n / 32 + 4);
@@ -834,11 +841,13 @@ static bool streaming_ok(int64_t ny, int64_t nx, uint32_t T, const void *a, cons
 
 static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t T, uint8_t *gx,
                              uint8_t *reach, int64_t nz, int64_t ny, int64_t nx, const int *gate,
-                             cudaStream_t st, const uint32_t *seedbits = nullptr)
+                             cudaStream_t st, const uint32_t *seedbits = nullptr, uint8_t *xflag = nullptr)
 {
     const int W = (int)isqrt_u32(T - 1);
     int rc = PSB200_OK;
-    if (seedbits && nx % 32 == 0 && ctx->xbits) {
+    const bool from_bits = seedbits && nx % 32 == 0 && ctx->xbits;
+    if (!from_bits || !ctx->yflags) xflag = nullptr;
+    if (from_bits) {
         // the seed set of this radius is already packed: x pass from the bits (xdist_bits_kernel)
         const int nw = (int)(nx / 32);
         int warps = 8;
@@ -846,7 +855,7 @@ static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_
         {
             ProfScope ps__(ctx, st, K_LT_X);
             xdist_bits_kernel<<<grid_for(nz * ny, warps, ctx->sm_count, 32), warps * 32, (size_t)warps * 2 * nw * 4, st>>>(
-                seedbits, gx, nz * ny, nw, W + 1, gate);
+                seedbits, gx, nz * ny, nw, W + 1, gate, xflag);
         }
         LAUNCH_CHECK(ctx);
     } else
@@ -866,7 +875,7 @@ static int lt_xy_stream_impl(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_
             ProfScope ps__(ctx, st, K_LT_Y);
             // (the 32 x 16 warp footprint that helps the EDT passes is 1 % slower here: r2b)
             if (coarse) lt_y3_kernel<<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate, direct);
-            else lt_y2_kernel<0><<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate, direct);
+            else lt_y2_kernel<0><<<grid, 256, smem, st>>>(gx, reach, (int)ny, (int)nx, T, W, Ly, gate, direct, xflag);
         }
         LAUNCH_CHECK(ctx);
     }
@@ -917,9 +926,11 @@ extern "C" int psb200_lt_xy(psb200_ctx *ctx, const uint8_t *cls, int k, uint32_t
         const size_t off_bits = align256(n + 16);
         if (ctx->xbits && nx % 32 == 0 && ws_bytes >= used + off_bits + n / 8 + 256 && ((uintptr_t)cls & 15u) == 0) {
             uint32_t *bits = reinterpret_cast<uint32_t *>(gx + off_bits);
+            const size_t off_flag = off_bits + align256(n / 8 + 16);
+            uint8_t *xflag = ws_bytes >= used + off_flag + n / 32 + 256 ? gx + off_flag : nullptr;
             int rc2 = lt_pack_impl(ctx, cls, k, bits, (int64_t)(n / 32), nullptr, (cudaStream_t)stream);
             if (rc2) return rc2;
-            return lt_xy_stream_impl(ctx, cls, k, T, gx, reach, nz, ny, nx, nullptr, (cudaStream_t)stream, bits);
+            return lt_xy_stream_impl(ctx, cls, k, T, gx, reach, nz, ny, nx, nullptr, (cudaStream_t)stream, bits, xflag);
         }
         return lt_xy_stream_impl(ctx, cls, k, T, gx, reach, nz, ny, nx, nullptr, (cudaStream_t)stream);
     }
@@ -1386,7 +1397,7 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
                 rc = lt_seed_bits(ctx, w, cmap, k, nT, n / 32, st, packed_lo, packed_hi, &bits);
                 if (rc) return rc;
             }
-            rc = lt_xy_stream_impl(ctx, cmap, k, T, w.gx, w.reach, nz, ny, nx, gate, st, bits);
+            rc = lt_xy_stream_impl(ctx, cmap, k, T, w.gx, w.reach, nz, ny, nx, gate, st, bits, w.xflag);
             if (rc) return rc;
             rc = lt_z_stream_impl(ctx, w.reach, nullptr, 0, nullptr, 0, idx, k, T, nz, ny, nx, gate, st);
         } else {

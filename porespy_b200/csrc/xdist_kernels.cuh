@@ -201,10 +201,11 @@ xdist_kernel(const uint8_t *__restrict__ in, void *__restrict__ outp, int64_t nl
 // byte-SWAR compares -- most of xdist_kernel<XD_LT>'s instructions -- disappear; the distances are the same two
 // running-distance recurrences (VIADDMNMX.U16x2, voxel j and j + 16 in the halves of one register).
 //   gx[line][x] = min(distance along x to the nearest set bit of the line, cap)      cap = W + 1 <= 254
+//   xflag[line][w] (optional) = 1 iff some voxel of word w has gx < cap
 // nx = 32 * nw.  dyn smem = warps * 2 * nw ints.
 __global__ void __launch_bounds__(256)
 xdist_bits_kernel(const uint32_t *__restrict__ bits, uint8_t *__restrict__ gx, int64_t nlines, int nw, int cap,
-                  const int *__restrict__ gate)
+                  const int *__restrict__ gate, uint8_t *__restrict__ xflag)
 {
     if (gate && *gate == 0) return;
     extern __shared__ int xb_smem[];
@@ -272,6 +273,14 @@ xdist_bits_kernel(const uint32_t *__restrict__ bits, uint8_t *__restrict__ gx, i
                 const uint32_t s = (~(m >> j) & 0x00010001u) * 0xFFFFu;
                 run = __viaddmin_u16x2(run, 0x00010001u, s);
                 d[j] = __vminu2(__vminu2(f[j], run), cap2);
+            }
+            if (xflag) {
+                // activity flag of the word: some voxel lies within W = cap - 1 of a seed of its line (the y pass
+                // skips tiles and rows without any)
+                uint32_t mm = d[0];
+#pragma unroll
+                for (int j = 1; j < 16; ++j) mm = __vminu2(mm, d[j]);
+                xflag[line * nw + w] = min(mm & 0xFFFFu, mm >> 16) < (uint32_t)cap ? 1 : 0;
             }
             uint32_t olo[4], ohi[4];
 #pragma unroll

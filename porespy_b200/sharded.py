@@ -108,7 +108,8 @@ class CudaBackend:
     def lt_xy(self, cls, k, T, shape):
         nz, ny, nx = shape
         reach = self.empty(nz * ny * nx, self.torch.uint8)
-        ws = self.ctx.workspace(nz * ny * nx + nz * ny * nx // 8 + 4096)     # x-distance bytes + seed bits of the radius
+        n = nz * ny * nx
+        ws = self.ctx.workspace(n + n // 8 + n // 32 + 8192)     # x-distance bytes + seed bits + activity flags of the radius
         _lib.check(self.ctx.lib.psb200_lt_xy(self.ctx.handle, dev.ptr(cls), int(k), int(T), dev.ptr(reach),
                                              nz, ny, nx, dev.ptr(ws), ws.numel(), dev.stream_ptr()))
         return reach

@@ -15,6 +15,8 @@ if os.environ.get("BIT_TMAX"):
     ctx.set_bit_tmax(int(os.environ["BIT_TMAX"]))
 if os.environ.get("FOOT"):
     ctx.set_foot(int(os.environ["FOOT"]))
+if os.environ.get("YFLAGS"):
+    ctx.set_yflags(int(os.environ["YFLAGS"]))
 if os.environ.get("ZWIDE"):
     ctx.set_zwide(int(os.environ["ZWIDE"]))
 if os.environ.get("EDT_H"):
