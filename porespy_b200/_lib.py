@@ -177,6 +177,10 @@ class Context:
         8 rows, 1 = 32 x 16."""
         check(self.lib.psb200_set_option(self.handle, b"foot", int(foot)))
 
+    def set_uf_records(self, on):
+        """Flood: row-rooted forest + link records (default on) / the per-voxel job lists."""
+        check(self.lib.psb200_set_option(self.handle, b"uf_records", 1 if on else 0))
+
     def set_yflags(self, on):
         """Byte path: activity flags from the x pass let the y pass skip idle tiles and rows (default on)."""
         check(self.lib.psb200_set_option(self.handle, b"yflags", 1 if on else 0))

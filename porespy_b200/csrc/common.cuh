@@ -27,6 +27,7 @@ struct psb200_ctx {
     int bit_tmax;      // thresholds T <= bit_tmax use the bit-parallel dilation (0: never)
     int bit4;          // bit path: four-words-per-lane kernel for rows of 32 / 64 / 128 words
     int foot;          // warp footprint of the 16-bit EDT min-plus scans: 0 = 64 x 8 voxels, 1 = 32 x 16 (default: 3 % faster, r2b)
+    int uf_records;    // flood: row-rooted forest + link records (default) / per-voxel job lists
     int yflags;        // byte path: the bit-based x pass leaves an activity byte per word, the y pass skips idle tiles / rows
     int zwide;         // z sweeps with 8 columns per thread and 16 planes in flight (default) / 4 columns, 8 planes
     int edt_h;         // halo rows staged on each side of a 128-row tile of the 16-bit EDT passes (scans beyond it read global

@@ -551,3 +551,360 @@ flood_out_kernel(const uint8_t *__restrict__ rcls, uint8_t *__restrict__ out, in
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
         out[i] = rcls[i] == 0 ? 1 : 0;
 }
+
+// =====================================================================================================
+// Row-rooted forest + link records (the single-GPU porosimetry loop and psb200_flood).
+//
+// The per-voxel job lists above spend their time enumerating (voxel, neighbour) pairs of which only a
+// few per cent end in a union.  Which pairs matter can be decided from the class map alone:
+//
+//  * x edges.  Along a row, a voxel whose left neighbour activates no later than itself (class <=)
+//    is connected to it from the moment it is active; otherwise, if its right neighbour activates
+//    strictly earlier, to that one.  Those "downhill" edges form a forest of chains inside the row that
+//    needs no union at all: uf_prelink_kernel writes parent[] = the chain's end (a local class minimum
+//    of the row, found by pointer jumping in shared memory) together with the initialisation of the
+//    forest.  A voxel is only ever used in a find after it became active, and every voxel between it
+//    and its chain end is active by then, so the plain stores are exactly the unions the job kernel
+//    would have made.  What remains of the x edges are the local maxima of the class along the row
+//    (two chains meeting) and the cuts at the 1024-voxel segment boundaries.
+//  * every other neighbour direction (dz, dy, dx): with m(x) = max(class of (z, y, x), class of
+//    (z + dz, y + dy, x + dx)) -- the radius index at which the pair is active -- the pairs of one
+//    direction between two rows that are active at index k form intervals of x, and all voxels of an
+//    interval are x-connected inside both rows.  An interval that holds an older pair (m < k) is
+//    connected through that one; so one union per interval BORN at k suffices:  the pairs with
+//    m(x - 1) > m(x) <= m(x + 1), i.e. the local minima of m along x.
+//
+// uf_links_kernel counts those records per (radius index, direction), uf_scan_bins_kernel turns the
+// counts into slice starts, a second uf_links_kernel pass writes the voxel ids, and radius k runs
+// uf_union_rec_kernel over its slice: about 0.1 unions per voxel for all radii together instead of
+// 6 (26) jobs per voxel.
+#define UF_SEGX 128          // a warp owns a segment: 4 consecutive voxels per lane, chains do not cross segments
+#define UF_CHUNK 256         // segments per list reservation of the scatter pass
+#define UF_MAXFAM 13
+#define UF_NTIMES 254
+
+// directions as (dz, dy, dx); the first 3 are 6-connectivity, all 13 the forward half of 26-connectivity
+__constant__ int8_t c_uf_fam[UF_MAXFAM][3] = {{0, 0, 1},  {0, 1, 0},  {1, 0, 0},  {0, 1, -1}, {0, 1, 1},
+                                              {1, 0, -1}, {1, 0, 1},  {1, 1, -1}, {1, 1, 0},  {1, 1, 1},
+                                              {1, -1, -1}, {1, -1, 0}, {1, -1, 1}};
+
+// bit j set: voxel x + j of the row is an inlet
+__device__ __forceinline__ uint32_t uf_inlet_bits(const InletSpec &inl, int64_t rb, int z, int y, int x, int nz, int ny, int nx)
+{
+    uint32_t bits = 0;
+    if (inl.mode == 2) {
+        const uint32_t m = load4(inl.mask + rb, x, nx, 0u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (byte_of(m, j)) bits |= 1u << j;
+    } else if (inl.mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (x + j < nx && is_inlet(inl, rb + x + j, z, y, x + j, nz, ny, nx)) bits |= 1u << j;
+    }
+    return bits;
+}
+
+__global__ void __launch_bounds__(256)
+uf_prelink_kernel(const uint8_t *__restrict__ cls, InletSpec inl, int nz, int ny, int nx,
+                  uint32_t *__restrict__ parent, uint8_t *__restrict__ jtime, uint8_t *__restrict__ acls)
+{
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const int lane = lane_id();
+    const int nseg = (nx + UF_SEGX - 1) / UF_SEGX;
+    const int64_t total = (int64_t)nz * ny * nseg;
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    if (blockIdx.x == 0 && threadIdx.x == 0) parent[0] = 0u;
+    for (int64_t seg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); seg < total; seg += nwarps) {
+        const int64_t row = seg / nseg;
+        const int x0 = (int)(seg - row * nseg) * UF_SEGX;
+        const int z = (int)(row / ny), y = (int)(row - (int64_t)z * ny);
+        const int64_t rb = row * nx;
+        const int x = x0 + 4 * lane;
+        uint32_t a = 0xFFFFFFFFu, inb = 0;
+        if (x < nx) {
+            a = load4(cls + rb, x, nx, 255u);
+            inb = uf_inlet_bits(inl, rb, z, y, x, nz, ny, nx);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (inb >> j & 1u) a &= ~(0xFFu << (8 * j));
+            if (acls) store4(acls + rb, x, nx, a);
+        }
+        uint32_t lft = __shfl_up_sync(FULL, a, 1) >> 24, rgt = __shfl_down_sync(FULL, a, 1) & 0xFFu;
+        if (lane == 0) lft = 255u;
+        if (lane == 31) rgt = 255u;
+        const uint32_t av[6] = {lft, byte_of(a, 0), byte_of(a, 1), byte_of(a, 2), byte_of(a, 3), rgt};
+        bool pl[4], pr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t ac = av[j + 1];
+            const bool ok = !(inb >> j & 1u) && ac < CLS_NEVER;
+            pl[j] = ok && av[j] <= ac;
+            pr[j] = ok && !pl[j] && av[j + 2] < ac;
+        }
+        // chain ends: nearest voxel to the left that does not point left / to the right that does not point right
+        int L[4], R[4], run = -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { run = pl[j] ? run : 4 * lane + j; L[j] = run; }
+        int inc = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(FULL, inc, off);
+            if (lane >= off) inc = max(inc, t);
+        }
+        int exc = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 0) exc = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (L[j] < 0) L[j] = exc;
+        run = UF_SEGX;
+#pragma unroll
+        for (int j = 3; j >= 0; --j) { run = pr[j] ? run : 4 * lane + j; R[j] = run; }
+        inc = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_down_sync(FULL, inc, off);
+            if (lane + off < 32) inc = min(inc, t);
+        }
+        exc = __shfl_down_sync(FULL, inc, 1);
+        if (lane == 31) exc = UF_SEGX - 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (R[j] >= UF_SEGX) R[j] = exc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = pl[j] ? L[j] : pr[j] ? R[j] : 4 * lane + j;
+            const uint32_t rin = (__shfl_sync(FULL, inb, r >> 2) >> (r & 3)) & 1u;
+            if (x + j < nx) {
+                const bool hang = (inb >> j & 1u) || rin;       // inlets, and chains that end in one: children of node 0
+                parent[rb + x + j + 1] = hang ? 0u : (uint32_t)(rb + x0 + r + 1);
+                if (jtime) jtime[rb + x + j + 1] = hang ? 0 : UF_TIME_UNSET;
+            }
+        }
+    }
+}
+
+// words of a row around the lane's 4 voxels: P = x-4..x-1, C = x..x+3, N = x+4..x+7 (255 outside the row)
+__device__ __forceinline__ void uf_row_words(const uint8_t *__restrict__ rowp, bool ok, int x0, int x, int nx, int lane,
+                                             uint32_t &P, uint32_t &C, uint32_t &N)
+{
+    const uint32_t FULL = 0xFFFFFFFFu;
+    C = (ok && x < nx) ? load4(rowp, x, nx, 255u) : 0xFFFFFFFFu;
+    P = __shfl_up_sync(FULL, C, 1);
+    N = __shfl_down_sync(FULL, C, 1);
+    if (lane == 0) P = (ok && x0 >= 4) ? load4(rowp, x0 - 4, nx, 255u) : 0xFFFFFFFFu;
+    if (lane == 31) N = (ok && x + 4 < nx) ? load4(rowp, x + 4, nx, 255u) : 0xFFFFFFFFu;
+}
+
+// SCATTER = false: hist[time * nsub + f (+ nfam)] += 1 per record.   SCATTER = true: the voxel ids into list[], slice
+// starts in start[], running fill in cursor[] (zeroed by the scan kernel).
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+uf_links_kernel(const uint8_t *__restrict__ acls, InletSpec inl, int nz, int ny, int nx, int nfam, int nsub,
+                uint32_t *__restrict__ hist, const uint32_t *__restrict__ start, uint32_t *__restrict__ cursor,
+                uint32_t *__restrict__ list)
+{
+    extern __shared__ uint32_t uf_sm[];
+    const int nbins = UF_NTIMES * nsub;
+    const int nrows = nfam > 3 ? 5 : 3;
+    uint32_t *cnt = uf_sm;                                 // [nbins]
+    uint32_t *bas = cnt + nbins;                           // [nbins] (SCATTER)
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int nseg = (nx + UF_SEGX - 1) / UF_SEGX;
+    const int64_t total = (int64_t)nz * ny * nseg;
+    const int64_t nchunks = (total + UF_CHUNK - 1) / UF_CHUNK;
+    for (int i = threadIdx.x; i < nbins; i += 256) cnt[i] = 0u;
+    __syncthreads();
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int64_t s_end = min(total, (chunk + 1) * UF_CHUNK);
+        for (int pass = 0; pass < (SCATTER ? 2 : 1); ++pass) {
+            const bool place = SCATTER && pass == 1;
+            for (int64_t seg = chunk * UF_CHUNK + warp; seg < s_end; seg += 8) {
+                const int64_t row = seg / nseg;
+                const int x0 = (int)(seg - row * nseg) * UF_SEGX;
+                const int z = (int)(row / ny), y = (int)(row - (int64_t)z * ny);
+                const int64_t rb = row * nx;
+                const int x = x0 + 4 * lane;
+                uint32_t P, C, N;
+                uf_row_words(acls + rb, true, x0, x, nx, lane, P, C, N);
+                const uint32_t Am1 = __byte_perm(P, C, 0x6543), Ap1 = __byte_perm(C, N, 0x4321);
+                const bool live = __vcmpltu4(C, 0xFEFEFEFEu) != 0u;          // any voxel of the lane with a class
+                // ---- x edges (x, x + 1): unless one of the two points at the other in uf_prelink_kernel
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t ax = byte_of(C, j), ar = byte_of(Ap1, j);
+                        if (ax >= CLS_NEVER || ar >= CLS_NEVER) continue;
+                        const int xx = x + j;
+                        const bool inx = ax == 0 && is_inlet(inl, rb + xx, z, y, xx, nz, ny, nx);
+                        const bool inr = ar == 0 && is_inlet(inl, rb + xx + 1, z, y, xx + 1, nz, ny, nx);
+                        bool covered = inx && inr;
+                        if (!covered && !(lane == 31 && j == 3)) {
+                            const bool left_ok = !(lane == 0 && j == 0) && byte_of(Am1, j) <= ax;
+                            covered = (!inr && ax <= ar) || (!inx && !left_ok && ar < ax);
+                        }
+                        if (!covered) {
+                            const int b = (int)max(ax, ar) * nsub;
+                            if (!place) atomicAdd(&cnt[b], 1u);
+                            else list[bas[b] + atomicAdd(&cnt[b], 1u)] = (uint32_t)(rb + xx);
+                        }
+                    }
+                }
+                // ---- the other directions: local minima of m along x, four voxels per instruction
+                for (int r = 1; r < nrows; ++r) {
+                    const int zz = z + (r >= 2 ? 1 : 0), yy = y + (r == 1 || r == 3 ? 1 : r == 4 ? -1 : 0);
+                    const bool ok = zz < nz && yy >= 0 && yy < ny;
+                    if (!ok) continue;                                           // (uniform over the warp)
+                    uint32_t Bp, Bc, Bn;
+                    uf_row_words(acls + ((int64_t)zz * ny + yy) * nx, true, x0, x, nx, lane, Bp, Bc, Bn);
+                    if (!live) continue;
+                    const uint32_t Bm1 = __byte_perm(Bp, Bc, 0x6543), Bp1 = __byte_perm(Bc, Bn, 0x4321);
+                    // the directions of this row: dx = 0 first (rows 1, 2: f = r; rows 3, 4: the middle one), then dx = -1, +1
+                    const int f0 = r <= 2 ? r : (r == 3 ? 8 : 11);
+                    const int fm = r <= 2 ? 1 + 2 * r : f0 - 1, fp = fm + (r <= 2 ? 1 : 2);
+                    const int ndx = nfam > 3 ? 3 : 1;
+                    for (int d = 0; d < ndx; ++d) {
+                        uint32_t b0, bl, br;
+                        int f;
+                        if (d == 0) { b0 = Bc; bl = Bm1; br = Bp1; f = f0; }
+                        else if (d == 1) { b0 = Bm1; bl = __byte_perm(Bp, Bc, 0x5432); br = Bc; f = fm; }
+                        else { b0 = Bp1; bl = Bc; br = __byte_perm(Bc, Bn, 0x5432); f = fp; }
+                        const uint32_t m = __vmaxu4(C, b0), ml = __vmaxu4(Am1, bl), mr = __vmaxu4(Ap1, br);
+                        uint32_t cond = __vcmpgtu4(ml, m) & __vcmpgeu4(mr, m) & __vcmpltu4(m, 0xFEFEFEFEu);
+                        while (cond) {
+                            const int j = (__ffs(cond) - 1) >> 3;
+                            cond &= ~(0xFFu << (8 * j));
+                            // pairs of equal class (both voxels new at this index) go to the second half of the
+                            // index's slices: the unions that attach new voxels to older trees run first
+                            int b = (int)byte_of(m, j) * nsub + f;
+                            if (nsub > nfam && byte_of(C, j) == byte_of(b0, j)) b += nfam;
+                            if (!place) atomicAdd(&cnt[b], 1u);
+                            else list[bas[b] + atomicAdd(&cnt[b], 1u)] = (uint32_t)(rb + x + j);
+                        }
+                    }
+                }
+            }
+            if (SCATTER && pass == 0) {
+                __syncthreads();
+                for (int b = threadIdx.x; b < nbins; b += 256) {
+                    const uint32_t c = cnt[b];
+                    if (c) bas[b] = start[b] + atomicAdd(&cursor[b], c);
+                    cnt[b] = 0u;
+                }
+                __syncthreads();
+            }
+        }
+        if (SCATTER) {
+            __syncthreads();
+            for (int b = threadIdx.x; b < nbins; b += 256) cnt[b] = 0u;
+            __syncthreads();
+        }
+    }
+    if (!SCATTER) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += 256)
+            if (cnt[b]) atomicAdd(&hist[b], cnt[b]);
+    }
+}
+
+// start[] = exclusive prefix sums of hist[0 .. nbins), start[nbins] = total; cursor[] = 0
+__global__ void __launch_bounds__(1024)
+uf_scan_bins_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ start, uint32_t *__restrict__ cursor, int nbins)
+{
+    __shared__ uint32_t part[1024];
+    const int per = (nbins + 1023) / 1024;
+    const int b0 = threadIdx.x * per;
+    uint32_t s = 0;
+    for (int b = b0; b < min(nbins, b0 + per); ++b) s += hist[b];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int t = 0; t < 1024; ++t) { const uint32_t c = part[t]; part[t] = acc; acc += c; }
+        start[nbins] = acc;
+    }
+    __syncthreads();
+    uint32_t acc = part[threadIdx.x];
+    for (int b = b0; b < min(nbins, b0 + per); ++b) {
+        start[b] = acc;
+        acc += hist[b];
+        cursor[b] = 0u;
+    }
+}
+
+struct UfStrides { long long s[UF_MAXFAM]; };
+
+// the unions of radius index k: list[start[k nsub] .. start[(k + 1) nsub]), direction = (slice the entry is in) mod nfam
+__global__ void __launch_bounds__(256)
+uf_union_rec_kernel(uint32_t *parent, const uint32_t *__restrict__ list, const uint32_t *__restrict__ start, int k,
+                    int nfam, int nsub, const __grid_constant__ UfStrides st, uint8_t *jtime)
+{
+    __shared__ uint32_t edge[2 * UF_MAXFAM + 1];
+    if (threadIdx.x <= nsub) edge[threadIdx.x] = start[k * nsub + threadIdx.x];
+    __syncthreads();
+    const uint32_t lo = edge[0], hi = edge[nsub];
+    const uint32_t step = gridDim.x * blockDim.x;
+    for (uint32_t j = lo + blockIdx.x * blockDim.x + threadIdx.x; j < hi; j += step) {
+        int f = 0;
+        while (j >= edge[f + 1]) ++f;
+        if (f >= nfam) f -= nfam;
+        const uint32_t v = list[j];
+        uf_union(parent, v + 1u, (uint32_t)((long long)v + st.s[f]) + 1u, jtime, k);
+    }
+}
+
+// Before the resolve pass: full path compression from every chain end.  After the unions a voxel's path is
+// voxel -> (ancestors, all of them chain ends) -> top, and only the voxels that were the endpoint of a union
+// had their own pointer shortened; without this pass every voxel of a chain would walk the chain end's whole
+// path again.  Afterwards every chain end points at its top (the child of node 0, or the stranded root), so the
+// walk of uf_resolve_kernel is at most three loads.
+#define UF_CTILE 8192
+__global__ void __launch_bounds__(256)
+uf_compress_kernel(uint32_t *parent, const uint8_t *__restrict__ acls, int nz, int ny, int nx)
+{
+    // the chain ends of a tile are gathered first, so that every lane of the walks below has work
+    __shared__ uint32_t queue[UF_CTILE];
+    __shared__ uint32_t qn;
+    const int64_t n = (int64_t)nz * ny * nx;
+    const int64_t ntiles = (n + UF_CTILE - 1) / UF_CTILE;
+    volatile uint32_t *vp = parent;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x == 0) qn = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < UF_CTILE; i += 256) {
+            const int64_t v = tile * UF_CTILE + i;
+            if (v >= n) break;
+            const uint32_t ac = acls[v];
+            if (ac >= CLS_NEVER) continue;
+            const int x = (int)(v % nx);
+            const int s = x & (UF_SEGX - 1);
+            if (s > 0 && acls[v - 1] <= ac) continue;                                   // points left
+            if (s + 1 < UF_SEGX && x + 1 < nx && acls[v + 1] < ac) continue;            // points right
+            queue[atomicAdd(&qn, 1u)] = (uint32_t)v + 1u;
+        }
+        __syncthreads();
+        const uint32_t cnt = qn;
+        for (uint32_t q = threadIdx.x; q < cnt; q += 256) {
+            const uint32_t self = queue[q];
+            uint32_t xn = self, p = vp[xn];
+            if (p == 0u || p == xn) continue;                                           // child of node 0 / root
+            int hops = 0;
+            while (true) {
+                xn = p;
+                p = vp[xn];
+                if (p == 0u || p == xn) break;
+                ++hops;
+            }
+            if (hops == 0) continue;
+            const uint32_t top = xn;
+            uint32_t yn = self;
+            while (yn != top) {
+                const uint32_t nxt = vp[yn];
+                if (nxt == top || nxt == 0u) break;
+                vp[yn] = top;
+                yn = nxt;
+            }
+        }
+        __syncthreads();
+    }
+}

@@ -103,6 +103,7 @@ extern "C" int psb200_create(int device, psb200_ctx **out)
     c->ydirect = 1;
     c->edt_h = 32;
     c->zwide = 1;
+    c->uf_records = 1;
     c->yflags = 1;
     c->flag_slot = 0;
     CUDA_TRY(cudaMalloc(&c->flags, 64 * sizeof(int)));
@@ -158,6 +159,10 @@ extern "C" int psb200_set_option(psb200_ctx *ctx, const char *name, int64_t valu
     }
     if (!strcmp(name, "bit4")) {
         ctx->bit4 = value ? 1 : 0;
+        return PSB200_OK;
+    }
+    if (!strcmp(name, "uf_records")) {
+        ctx->uf_records = value ? 1 : 0;
         return PSB200_OK;
     }
     if (!strcmp(name, "yflags")) {
@@ -705,6 +710,8 @@ struct LtWorkspace {
     size_t seed_words;              // words of one seed-bit volume inside seedbits
     uint32_t *parent;
     uint32_t *uf_list;    // voxels activated at the current radius (one segment of UF_SEG voxels at a time)
+    size_t uf_list_cap;
+    uint32_t *uf_bins;    // histogram / slice starts / cursors of the link records
     int *gate;
     uint32_t *gen_d2;     // generic algo: full u32 distance map of ~seeds
     char *gen_stk;
@@ -729,7 +736,11 @@ static LtWorkspace carve_lt(const psb200_ctx *ctx, char *base, int64_t nz, int64
     if (inlet_mode != PSB200_INLETS_NONE) {
         w.rcls = c.take<uint8_t>(n + 16);
         w.parent = c.take<uint32_t>(n + 1);
-        w.uf_list = c.take<uint32_t>(n + 64);        // every foreground voxel once, bucketed by class
+        // link records of the row-rooted forest (flood_kernels.cuh): at most one x record per voxel and one per
+        // two voxels for each of y and z; also the per-voxel job list of the fallback / 26-connectivity path
+        w.uf_list_cap = 2 * n + 2 * (size_t)(nz * ny) + 64;
+        w.uf_list = c.take<uint32_t>(w.uf_list_cap);
+        w.uf_bins = c.take<uint32_t>(3 * (UF_NTIMES * UF_MAXFAM + 64));
     }
     if (ctx->algo == PSB200_ALGO_GENERIC) {
         w.gen_d2 = c.take<uint32_t>(n);
@@ -976,6 +987,72 @@ static int uf_activate_impl(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cl
         }
         LAUNCH_CHECK(ctx);
     }
+    return PSB200_OK;
+}
+
+// Forest initialisation with the x chains pre-linked, and the link records of all radius indices bucketed by
+// (index, direction) -- see flood_kernels.cuh.  `acls` receives the activation map (class, inlets folded to 0).
+// Returns the device array of slice starts through *start_out.  conn 26: the record count has no useful a-priori
+// bound, so the host reads the total and *fits tells whether the records were written.
+static int uf_forest_impl(psb200_ctx *ctx, LtWorkspace &w, const InletSpec &inl, const uint8_t *cls, uint8_t *acls,
+                          uint8_t *jtime, int conn, int64_t nz, int64_t ny, int64_t nx, cudaStream_t st,
+                          const uint32_t **start_out, bool *fits)
+{
+    const int nfam = conn == 6 ? 3 : UF_MAXFAM, nsub = conn == 6 ? 2 * nfam : nfam;
+    const int nbins = UF_NTIMES * nsub;
+    const int nseg = (int)((nx + UF_SEGX - 1) / UF_SEGX);
+    const int64_t segs = nz * ny * nseg;
+    const int grid_a = (int)std::min<int64_t>((segs + 7) / 8, (int64_t)ctx->sm_count * 8);
+    const int grid = (int)std::min<int64_t>((segs + UF_CHUNK - 1) / UF_CHUNK, (int64_t)ctx->sm_count * 8);
+    uint32_t *hist = w.uf_bins, *start = hist + nbins + 64, *cursor = start + nbins + 64;
+    {
+        ProfScope ps__(ctx, st, K_UF_INIT);
+        uf_prelink_kernel<<<grid_a, 256, 0, st>>>(cls, inl, (int)nz, (int)ny, (int)nx, w.parent, jtime, acls);
+    }
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(uint32_t), st));
+    {
+        ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+        uf_links_kernel<false><<<grid, 256, (size_t)nbins * 4, st>>>(acls, inl, (int)nz, (int)ny, (int)nx, nfam, nsub,
+                                                                                  hist, nullptr, nullptr, nullptr);
+    }
+    LAUNCH_CHECK(ctx);
+    {
+        ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+        uf_scan_bins_kernel<<<1, 1024, 0, st>>>(hist, start, cursor, nbins);
+    }
+    LAUNCH_CHECK(ctx);
+    *fits = true;
+    if (nfam > 3) {
+        uint32_t total = 0;
+        CUDA_TRY(cudaMemcpyAsync(&total, start + nbins, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if ((size_t)total > w.uf_list_cap) { *fits = false; return PSB200_OK; }
+    }
+    {
+        ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+        uf_links_kernel<true><<<grid, 256, (size_t)nbins * 8, st>>>(acls, inl, (int)nz, (int)ny, (int)nx, nfam, nsub,
+                                                                                 nullptr, start, cursor, w.uf_list);
+    }
+    LAUNCH_CHECK(ctx);
+    *start_out = start;
+    return PSB200_OK;
+}
+
+static int uf_union_records(psb200_ctx *ctx, LtWorkspace &w, const uint32_t *start, int k, int conn, int64_t ny,
+                            int64_t nx, uint8_t *jtime, cudaStream_t st)
+{
+    const int nfam = conn == 6 ? 3 : UF_MAXFAM, nsub = conn == 6 ? 2 * nfam : nfam;
+    static const int8_t fam[UF_MAXFAM][3] = {{0, 0, 1},  {0, 1, 0},  {1, 0, 0},  {0, 1, -1}, {0, 1, 1},
+                                             {1, 0, -1}, {1, 0, 1},  {1, 1, -1}, {1, 1, 0},  {1, 1, 1},
+                                             {1, -1, -1}, {1, -1, 0}, {1, -1, 1}};
+    UfStrides sd;
+    for (int f = 0; f < UF_MAXFAM; ++f) sd.s[f] = ((long long)fam[f][0] * ny + fam[f][1]) * nx + fam[f][2];
+    {
+        ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+        uf_union_rec_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(w.parent, w.uf_list, start, k, nfam, nsub, sd, jtime);
+    }
+    LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
 
@@ -1292,38 +1369,55 @@ extern "C" int psb200_local_thickness_idx(psb200_ctx *ctx, const uint32_t *d2, c
         int *kmin = w.gate + 1;
         CUDA_TRY(cudaMemsetAsync(w.gate, 0, sizeof(int), st));
         CUDA_TRY(cudaMemsetAsync(kmin, 0x7F, sizeof(int), st));
-        {
-            ProfScope ps__(ctx, st, K_UF_INIT);
-            uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx, jtime, w.cls, w.rcls);
-        }
-        LAUNCH_CHECK(ctx);
-        // until the resolve pass the rcls buffer holds the activation map (class, inlets folded to 0)
-        const uint8_t *acls = w.rcls;
-        const InletSpec folded{3, ndim, nullptr, 0, (int)nz};
-        uint32_t *hist = reinterpret_cast<uint32_t *>(w.gate) + 64, *start = hist + 256, *cursor = start + 320;
-        CUDA_TRY(cudaMemsetAsync(hist, 0, 256 * sizeof(uint32_t), st));
-        {
-            ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-            uf_hist_kernel<<<grid_for(n / 16 + 1, 256, ctx->sm_count, 8), 256, 0, st>>>(acls, n, hist);
-        }
-        LAUNCH_CHECK(ctx);
-        {
-            ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-            uf_scan_kernel<<<1, 256, 0, st>>>(hist, start, cursor);
-        }
-        LAUNCH_CHECK(ctx);
-        {
-            ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-            uf_bucket_kernel<<<grid_for((n + 63) / 64, 256, ctx->sm_count, 8), 256, 0, st>>>(acls, n, start, cursor, w.uf_list);
-        }
-        LAUNCH_CHECK(ctx);
-        for (int k = 0; k < nT; ++k) {
+        if (ctx->uf_records) {
+            // until the resolve pass the rcls buffer holds the activation map (class, inlets folded to 0)
+            const uint32_t *start = nullptr;
+            bool fits = true;
+            rc = uf_forest_impl(ctx, w, inl, w.cls, w.rcls, jtime, 6, nz, ny, nx, st, &start, &fits);
+            if (rc) return rc;
+            for (int k = 0; k < nT; ++k) {
+                rc = uf_union_records(ctx, w, start, k, 6, ny, nx, jtime, st);
+                if (rc) return rc;
+            }
             {
-                ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-                uf_union_list_kernel<<<ctx->sm_count * 16, 256, 0, st>>>(w.parent, acls, folded, k - 1, k, 6, (int)nz, (int)ny,
-                                                                         (int)nx, w.uf_list, nullptr, jtime, start);
+                ProfScope ps__(ctx, st, K_UF_MARK);
+                uf_compress_kernel<<<ctx->sm_count * 6, 256, 0, st>>>(w.parent, w.rcls, (int)nz, (int)ny, (int)nx);
             }
             LAUNCH_CHECK(ctx);
+        } else {
+            {
+                ProfScope ps__(ctx, st, K_UF_INIT);
+                uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx, jtime, w.cls, w.rcls);
+            }
+            LAUNCH_CHECK(ctx);
+            // until the resolve pass the rcls buffer holds the activation map (class, inlets folded to 0)
+            const uint8_t *acls = w.rcls;
+            const InletSpec folded{3, ndim, nullptr, 0, (int)nz};
+            uint32_t *hist = reinterpret_cast<uint32_t *>(w.gate) + 64, *start = hist + 256, *cursor = start + 320;
+            CUDA_TRY(cudaMemsetAsync(hist, 0, 256 * sizeof(uint32_t), st));
+            {
+                ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+                uf_hist_kernel<<<grid_for(n / 16 + 1, 256, ctx->sm_count, 8), 256, 0, st>>>(acls, n, hist);
+            }
+            LAUNCH_CHECK(ctx);
+            {
+                ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+                uf_scan_kernel<<<1, 256, 0, st>>>(hist, start, cursor);
+            }
+            LAUNCH_CHECK(ctx);
+            {
+                ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+                uf_bucket_kernel<<<grid_for((n + 63) / 64, 256, ctx->sm_count, 8), 256, 0, st>>>(acls, n, start, cursor, w.uf_list);
+            }
+            LAUNCH_CHECK(ctx);
+            for (int k = 0; k < nT; ++k) {
+                {
+                    ProfScope ps__(ctx, st, K_UF_ACTIVATE);
+                    uf_union_list_kernel<<<ctx->sm_count * 16, 256, 0, st>>>(w.parent, acls, folded, k - 1, k, 6, (int)nz, (int)ny,
+                                                                             (int)nx, w.uf_list, nullptr, jtime, start);
+                }
+                LAUNCH_CHECK(ctx);
+            }
         }
         {
             ProfScope ps__(ctx, st, K_UF_MARK);
@@ -1647,13 +1741,36 @@ extern "C" int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t 
         uf_rcls_init_kernel<<<g, 256, 0, st>>>(w.cls, w.rcls, n);
     }
     LAUNCH_CHECK(ctx);
-    {
-        ProfScope ps__(ctx, st, K_UF_INIT);
-        uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx, nullptr);
+    bool done = false;
+    if (ctx->uf_records) {
+        // row-rooted forest + link records (the activation map goes to the reach buffer, unused here)
+        const uint32_t *start = nullptr;
+        rc = uf_forest_impl(ctx, w, inl, w.cls, w.reach, nullptr, c3, nz, ny, nx, st, &start, &done);
+        if (rc) return rc;
+        if (done) {
+            rc = uf_union_records(ctx, w, start, 0, c3, ny, nx, nullptr, st);
+            if (rc) return rc;
+            {
+                ProfScope ps__(ctx, st, K_UF_MARK);
+                uf_compress_kernel<<<ctx->sm_count * 6, 256, 0, st>>>(w.parent, w.reach, (int)nz, (int)ny, (int)nx);
+            }
+            LAUNCH_CHECK(ctx);
+            {
+                ProfScope ps__(ctx, st, K_UF_MARK);
+                uf_mark_kernel<<<grid_for((n + 15) / 16, 256, ctx->sm_count, 16), 256, 0, st>>>(w.parent, w.cls, w.rcls, 0, n, w.gate);
+            }
+            LAUNCH_CHECK(ctx);
+        }
     }
-    LAUNCH_CHECK(ctx);
-    rc = uf_step(ctx, w, inl, -1, 0, c3, nz, ny, nx, st);
-    if (rc) return rc;
+    if (!done) {
+        {
+            ProfScope ps__(ctx, st, K_UF_INIT);
+            uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx, nullptr);
+        }
+        LAUNCH_CHECK(ctx);
+        rc = uf_step(ctx, w, inl, -1, 0, c3, nz, ny, nx, st);
+        if (rc) return rc;
+    }
     {
         ProfScope ps__(ctx, st, K_FLOOD_MISC);
         flood_out_kernel<<<g, 256, 0, st>>>(w.rcls, out, n);
