@@ -458,23 +458,55 @@ uf_resolve_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, const uint8
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     volatile uint32_t *vp = parent;
     uint32_t lmin = 255u;
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += step) {
+    const bool aligned = ((((uintptr_t)cls) | ((uintptr_t)rcls)) & 3u) == 0;
+    // four voxels per thread, the first three levels of their walks as independent loads (after
+    // uf_compress_kernel a walk is: voxel -> chain end -> top -> node 0)
+    const int64_t ngroups = aligned ? n / 4 : 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += step) {
+        const uint32_t cw = __ldg(reinterpret_cast<const uint32_t *>(cls) + g);
+        uint32_t out = 0;
+        uint32_t x[4], p[4];
+        bool live[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = byte_of(cw, j);
+            live[j] = c < CLS_NEVER;
+            x[j] = (uint32_t)(4 * g + j + 1);
+            p[j] = live[j] ? vp[x[j]] : x[j];
+        }
+#pragma unroll
+        for (int lvl = 0; lvl < 2; ++lvl) {
+            uint32_t q[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) q[j] = (p[j] != 0u && p[j] != x[j]) ? vp[p[j]] : p[j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (p[j] != 0u && p[j] != x[j]) { x[j] = p[j]; p[j] = q[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = byte_of(cw, j);
+            uint32_t r = c == CLS_BG ? CLS_BG : CLS_NEVER;
+            if (live[j]) {
+                uint32_t xx = x[j], pp = p[j];
+                while (pp != 0u && pp != xx) { xx = pp; pp = vp[xx]; }          // deeper than three levels: rare
+                if (pp == 0u) {
+                    r = max(c, (uint32_t)jtime[xx]);
+                    lmin = min(lmin, r);
+                }
+            }
+            out |= r << (8 * j);
+        }
+        reinterpret_cast<uint32_t *>(rcls)[g] = out;
+    }
+    for (int64_t v = 4 * ngroups + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += step) {
         const uint32_t c = cls[v];
         uint32_t r = c == CLS_BG ? CLS_BG : CLS_NEVER;      // background stays background
         if (c < CLS_NEVER) {
-            const uint32_t self = (uint32_t)(v + 1);
-            uint32_t x = self, p = vp[x], top = 0u;         // top: child of node 0 on the path, 0: none
-            int hops = 0;
-            while (true) {
-                if (p == 0u) { top = x; break; }
-                if (p == x) break;                          // a root other than node 0: not connected
-                x = p;
-                p = vp[x];
-                ++hops;
-            }
-            if (hops > 1) vp[self] = x;                     // compress (top or the stranded root)
-            if (top != 0u) {
-                r = max(c, (uint32_t)jtime[top]);
+            uint32_t x = (uint32_t)(v + 1), p = vp[x];
+            while (p != 0u && p != x) { x = p; p = vp[x]; }
+            if (p == 0u) {                                  // x: the child of node 0 on the path
+                r = max(c, (uint32_t)jtime[x]);
                 lmin = min(lmin, r);
             }
         }
@@ -684,126 +716,204 @@ uf_prelink_kernel(const uint8_t *__restrict__ cls, InletSpec inl, int nz, int ny
     }
 }
 
-// words of a row around the lane's 4 voxels: P = x-4..x-1, C = x..x+3, N = x+4..x+7 (255 outside the row)
-__device__ __forceinline__ void uf_row_words(const uint8_t *__restrict__ rowp, bool ok, int x0, int x, int nx, int lane,
-                                             uint32_t &P, uint32_t &C, uint32_t &N)
+// words of a row around the lane's 4 voxels: P = x-4..x-1, C = x..x+3, N = x+4..x+7 (255 outside the row).
+// uf_row_load issues the loads (the lane's own word, and on lanes 0 / 31 the word beyond the segment's end),
+// uf_row_finish exchanges the neighbours' words -- split so that the loads of all rows are in flight together.
+__device__ __forceinline__ void uf_row_load(const uint8_t *__restrict__ rowp, bool ok, int x0, int x, int nx, int lane,
+                                            uint32_t &C, uint32_t &E)
+{
+    C = (ok && x < nx) ? load4(rowp, x, nx, 255u) : 0xFFFFFFFFu;
+    E = 0xFFFFFFFFu;
+    if (lane == 0 && ok && x0 >= 4) E = load4(rowp, x0 - 4, nx, 255u);
+    if (lane == 31 && ok && x + 4 < nx) E = load4(rowp, x + 4, nx, 255u);
+}
+__device__ __forceinline__ void uf_row_finish(uint32_t C, uint32_t E, int lane, uint32_t &P, uint32_t &N)
 {
     const uint32_t FULL = 0xFFFFFFFFu;
-    C = (ok && x < nx) ? load4(rowp, x, nx, 255u) : 0xFFFFFFFFu;
     P = __shfl_up_sync(FULL, C, 1);
     N = __shfl_down_sync(FULL, C, 1);
-    if (lane == 0) P = (ok && x0 >= 4) ? load4(rowp, x0 - 4, nx, 255u) : 0xFFFFFFFFu;
-    if (lane == 31) N = (ok && x + 4 < nx) ? load4(rowp, x + 4, nx, 255u) : 0xFFFFFFFFu;
+    if (lane == 0) P = E;
+    if (lane == 31) N = E;
 }
 
-// SCATTER = false: hist[time * nsub + f (+ nfam)] += 1 per record.   SCATTER = true: the voxel ids into list[], slice
-// starts in start[], running fill in cursor[] (zeroed by the scan kernel).
-template <bool SCATTER>
+// ---- records.  One pass over the class map (uf_emit_kernel) appends the records of a chunk of UF_CHUNK
+// segments to the chunk's own region of raw[] as (voxel - first voxel of the chunk) << 13 | tag, with
+// tag = index * nsub + direction (+ nfam when both voxels of the pair are new at that index: those slices come
+// second, so that the unions which attach new voxels to older trees run first and the trees stay flat), and
+// counts the tags; uf_scan_bins_kernel turns the counts into slice starts; uf_sort_kernel moves the records of
+// every chunk into their slices of list[] as voxel ids.
+#define UF_TAGBITS 13
+
+struct UfEmit {
+    uint32_t *cnt;           // shared: records per tag (all chunks of the block)
+    uint32_t *fill;          // shared: records of the current chunk
+    uint32_t *raw;           // the chunk's region
+    uint32_t cap;
+    int nfam, nsub, lane;
+};
+
+// cond: 0xFF in byte j = voxel (local id vloc + j) has a record of direction f at index byte j of m; eq: byte mask of
+// the pairs whose two classes are equal
+__device__ __forceinline__ void uf_emit(const UfEmit &e, uint32_t cond, uint32_t m, uint32_t eq, int f, uint32_t vloc)
+{
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t c = (uint32_t)__popc(cond) >> 3;
+    const uint32_t b0 = __ballot_sync(FULL, c & 1u), b1 = __ballot_sync(FULL, c & 2u), b2 = __ballot_sync(FULL, c & 4u);
+    if ((b0 | b1 | b2) == 0u) return;
+    const uint32_t lt = (1u << e.lane) - 1u;
+    const uint32_t before = __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
+    const uint32_t tot = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+    uint32_t base = 0;
+    if (e.lane == 0) base = atomicAdd(e.fill, tot);
+    uint32_t pos = __shfl_sync(FULL, base, 0) + before;
+    while (cond) {
+        const int j = (__ffs(cond) - 1) >> 3;
+        cond &= ~(0xFFu << (8 * j));
+        uint32_t tag = byte_of(m, j) * (uint32_t)e.nsub + (uint32_t)f;
+        if (e.nsub > e.nfam && byte_of(eq, j)) tag += (uint32_t)e.nfam;
+        atomicAdd(&e.cnt[tag], 1u);
+        if (pos < e.cap) e.raw[pos] = ((vloc + (uint32_t)j) << UF_TAGBITS) | tag;
+        ++pos;
+    }
+}
+
+template <int NROWS>
 __global__ void __launch_bounds__(256)
-uf_links_kernel(const uint8_t *__restrict__ acls, InletSpec inl, int nz, int ny, int nx, int nfam, int nsub,
-                uint32_t *__restrict__ hist, const uint32_t *__restrict__ start, uint32_t *__restrict__ cursor,
-                uint32_t *__restrict__ list)
+uf_emit_kernel(const uint8_t *__restrict__ acls, InletSpec inl, int nz, int ny, int nx, int nfam, int nsub,
+               uint32_t *__restrict__ hist, uint32_t *__restrict__ raw, uint32_t *__restrict__ chunk_count, uint32_t cap,
+               int *__restrict__ overflow)
 {
     extern __shared__ uint32_t uf_sm[];
+    __shared__ uint32_t fill;
     const int nbins = UF_NTIMES * nsub;
-    const int nrows = nfam > 3 ? 5 : 3;
     uint32_t *cnt = uf_sm;                                 // [nbins]
-    uint32_t *bas = cnt + nbins;                           // [nbins] (SCATTER)
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int nseg = (nx + UF_SEGX - 1) / UF_SEGX;
     const int64_t total = (int64_t)nz * ny * nseg;
     const int64_t nchunks = (total + UF_CHUNK - 1) / UF_CHUNK;
     for (int i = threadIdx.x; i < nbins; i += 256) cnt[i] = 0u;
-    __syncthreads();
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        if (threadIdx.x == 0) fill = 0u;
+        __syncthreads();
         const int64_t s_end = min(total, (chunk + 1) * UF_CHUNK);
-        for (int pass = 0; pass < (SCATTER ? 2 : 1); ++pass) {
-            const bool place = SCATTER && pass == 1;
-            for (int64_t seg = chunk * UF_CHUNK + warp; seg < s_end; seg += 8) {
-                const int64_t row = seg / nseg;
-                const int x0 = (int)(seg - row * nseg) * UF_SEGX;
-                const int z = (int)(row / ny), y = (int)(row - (int64_t)z * ny);
-                const int64_t rb = row * nx;
-                const int x = x0 + 4 * lane;
-                uint32_t P, C, N;
-                uf_row_words(acls + rb, true, x0, x, nx, lane, P, C, N);
-                const uint32_t Am1 = __byte_perm(P, C, 0x6543), Ap1 = __byte_perm(C, N, 0x4321);
-                const bool live = __vcmpltu4(C, 0xFEFEFEFEu) != 0u;          // any voxel of the lane with a class
-                // ---- x edges (x, x + 1): unless one of the two points at the other in uf_prelink_kernel
-                if (live) {
+        const int64_t row0 = chunk * UF_CHUNK / nseg;
+        const int64_t v0 = row0 * nx + (chunk * UF_CHUNK - row0 * nseg) * UF_SEGX;
+        const UfEmit e{cnt, &fill, raw + chunk * cap, cap, nfam, nsub, lane};
+        for (int64_t seg = chunk * UF_CHUNK + warp; seg < s_end; seg += 8) {
+            const int64_t row = seg / nseg;
+            const int x0 = (int)(seg - row * nseg) * UF_SEGX;
+            const int z = (int)(row / ny), y = (int)(row - (int64_t)z * ny);
+            const int64_t rb = row * nx;
+            const int x = x0 + 4 * lane;
+            const uint32_t vloc = (uint32_t)(rb + x - v0);
+            // rows: 0 own, 1 (y+1), 2 (z+1), 3 (z+1, y+1), 4 (z+1, y-1)
+            uint32_t Cw[NROWS], Ew[NROWS];
+            bool okr[NROWS];
+#pragma unroll
+            for (int r = 0; r < NROWS; ++r) {
+                const int zz = z + (r >= 2 ? 1 : 0), yy = y + (r == 1 || r == 3 ? 1 : r == 4 ? -1 : 0);
+                okr[r] = zz < nz && yy >= 0 && yy < ny;
+                uf_row_load(acls + ((int64_t)zz * ny + yy) * nx, okr[r], x0, x, nx, lane, Cw[r], Ew[r]);
+            }
+            uint32_t P, N;
+            const uint32_t C = Cw[0];
+            uf_row_finish(C, Ew[0], lane, P, N);
+            const uint32_t Am1 = __byte_perm(P, C, 0x6543), Ap1 = __byte_perm(C, N, 0x4321);
+            const uint32_t vC = __vcmpltu4(C, 0xFEFEFEFEu);                  // voxels of the lane with a class
+            // ---- x edges (x, x + 1): unless one of the two points at the other in uf_prelink_kernel
+            {
+                uint32_t pair = vC & __vcmpltu4(Ap1, 0xFEFEFEFEu);
+                uint32_t covered;
+                const uint32_t sameseg = lane == 31 ? 0x00FFFFFFu : 0xFFFFFFFFu;
+                const uint32_t notfirst = lane == 0 ? 0xFFFFFF00u : 0xFFFFFFFFu;
+                const uint32_t le = __vcmpleu4(C, Ap1);
+                const uint32_t left_ok = __vcmpleu4(Am1, C) & notfirst;
+                covered = sameseg & (le | (~left_ok & ~le));
+                const uint32_t zero = (__vcmpeq4(C, 0u) | __vcmpeq4(Ap1, 0u)) & pair;
+                if (zero) {
+                    // class 0 may be an inlet (parent = node 0, never pre-linked): the exact rule, voxel by voxel
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+                        if (!byte_of(zero, j)) continue;
                         const uint32_t ax = byte_of(C, j), ar = byte_of(Ap1, j);
-                        if (ax >= CLS_NEVER || ar >= CLS_NEVER) continue;
                         const int xx = x + j;
                         const bool inx = ax == 0 && is_inlet(inl, rb + xx, z, y, xx, nz, ny, nx);
                         const bool inr = ar == 0 && is_inlet(inl, rb + xx + 1, z, y, xx + 1, nz, ny, nx);
-                        bool covered = inx && inr;
-                        if (!covered && !(lane == 31 && j == 3)) {
-                            const bool left_ok = !(lane == 0 && j == 0) && byte_of(Am1, j) <= ax;
-                            covered = (!inr && ax <= ar) || (!inx && !left_ok && ar < ax);
+                        bool cov = inx && inr;
+                        if (!cov && !(lane == 31 && j == 3)) {
+                            const bool lok = !(lane == 0 && j == 0) && byte_of(Am1, j) <= ax;
+                            cov = (!inr && ax <= ar) || (!inx && !lok && ar < ax);
                         }
-                        if (!covered) {
-                            const int b = (int)max(ax, ar) * nsub;
-                            if (!place) atomicAdd(&cnt[b], 1u);
-                            else list[bas[b] + atomicAdd(&cnt[b], 1u)] = (uint32_t)(rb + xx);
-                        }
+                        covered = (covered & ~(0xFFu << (8 * j))) | (cov ? 0xFFu << (8 * j) : 0u);
                     }
                 }
-                // ---- the other directions: local minima of m along x, four voxels per instruction
-                for (int r = 1; r < nrows; ++r) {
-                    const int zz = z + (r >= 2 ? 1 : 0), yy = y + (r == 1 || r == 3 ? 1 : r == 4 ? -1 : 0);
-                    const bool ok = zz < nz && yy >= 0 && yy < ny;
-                    if (!ok) continue;                                           // (uniform over the warp)
-                    uint32_t Bp, Bc, Bn;
-                    uf_row_words(acls + ((int64_t)zz * ny + yy) * nx, true, x0, x, nx, lane, Bp, Bc, Bn);
-                    if (!live) continue;
-                    const uint32_t Bm1 = __byte_perm(Bp, Bc, 0x6543), Bp1 = __byte_perm(Bc, Bn, 0x4321);
-                    // the directions of this row: dx = 0 first (rows 1, 2: f = r; rows 3, 4: the middle one), then dx = -1, +1
-                    const int f0 = r <= 2 ? r : (r == 3 ? 8 : 11);
-                    const int fm = r <= 2 ? 1 + 2 * r : f0 - 1, fp = fm + (r <= 2 ? 1 : 2);
-                    const int ndx = nfam > 3 ? 3 : 1;
-                    for (int d = 0; d < ndx; ++d) {
-                        uint32_t b0, bl, br;
-                        int f;
-                        if (d == 0) { b0 = Bc; bl = Bm1; br = Bp1; f = f0; }
-                        else if (d == 1) { b0 = Bm1; bl = __byte_perm(Bp, Bc, 0x5432); br = Bc; f = fm; }
-                        else { b0 = Bp1; bl = Bc; br = __byte_perm(Bc, Bn, 0x5432); f = fp; }
-                        const uint32_t m = __vmaxu4(C, b0), ml = __vmaxu4(Am1, bl), mr = __vmaxu4(Ap1, br);
-                        uint32_t cond = __vcmpgtu4(ml, m) & __vcmpgeu4(mr, m) & __vcmpltu4(m, 0xFEFEFEFEu);
-                        while (cond) {
-                            const int j = (__ffs(cond) - 1) >> 3;
-                            cond &= ~(0xFFu << (8 * j));
-                            // pairs of equal class (both voxels new at this index) go to the second half of the
-                            // index's slices: the unions that attach new voxels to older trees run first
-                            int b = (int)byte_of(m, j) * nsub + f;
-                            if (nsub > nfam && byte_of(C, j) == byte_of(b0, j)) b += nfam;
-                            if (!place) atomicAdd(&cnt[b], 1u);
-                            else list[bas[b] + atomicAdd(&cnt[b], 1u)] = (uint32_t)(rb + x + j);
-                        }
-                    }
-                }
+                uf_emit(e, pair & ~covered, __vmaxu4(C, Ap1), 0u, 0, vloc);
             }
-            if (SCATTER && pass == 0) {
-                __syncthreads();
-                for (int b = threadIdx.x; b < nbins; b += 256) {
-                    const uint32_t c = cnt[b];
-                    if (c) bas[b] = start[b] + atomicAdd(&cursor[b], c);
-                    cnt[b] = 0u;
+            // ---- the other directions: local minima of m along x, four voxels per instruction
+#pragma unroll
+            for (int r = 1; r < NROWS; ++r) {
+                if (!okr[r]) continue;                                       // (uniform over the warp)
+                uint32_t Bp, Bn;
+                const uint32_t Bc = Cw[r];
+                uf_row_finish(Bc, Ew[r], lane, Bp, Bn);
+                const uint32_t Bm1 = __byte_perm(Bp, Bc, 0x6543), Bp1 = __byte_perm(Bc, Bn, 0x4321);
+                // the directions of this row: dx = 0 first (rows 1, 2: f = r; rows 3, 4: the middle one), then dx = -1, +1
+                const int f0 = r <= 2 ? r : (r == 3 ? 8 : 11);
+                const int fm = r <= 2 ? 1 + 2 * r : f0 - 1, fp = fm + (r <= 2 ? 1 : 2);
+                const int ndx = NROWS > 3 ? 3 : 1;
+#pragma unroll
+                for (int d = 0; d < ndx; ++d) {
+                    uint32_t b0, bl, br;
+                    int f;
+                    if (d == 0) { b0 = Bc; bl = Bm1; br = Bp1; f = f0; }
+                    else if (d == 1) { b0 = Bm1; bl = __byte_perm(Bp, Bc, 0x5432); br = Bc; f = fm; }
+                    else { b0 = Bp1; bl = Bc; br = __byte_perm(Bc, Bn, 0x5432); f = fp; }
+                    const uint32_t m = __vmaxu4(C, b0), ml = __vmaxu4(Am1, bl), mr = __vmaxu4(Ap1, br);
+                    const uint32_t cond = __vcmpgtu4(ml, m) & __vcmpgeu4(mr, m) & __vcmpltu4(m, 0xFEFEFEFEu);
+                    uf_emit(e, cond, m, __vcmpeq4(C, b0), f, vloc);
                 }
-                __syncthreads();
             }
         }
-        if (SCATTER) {
-            __syncthreads();
-            for (int b = threadIdx.x; b < nbins; b += 256) cnt[b] = 0u;
-            __syncthreads();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            chunk_count[chunk] = min(fill, cap);
+            if (fill > cap) *overflow = 1;
         }
     }
-    if (!SCATTER) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += 256)
+        if (cnt[b]) atomicAdd(&hist[b], cnt[b]);
+}
+
+__global__ void __launch_bounds__(256)
+uf_sort_kernel(const uint32_t *__restrict__ raw, const uint32_t *__restrict__ chunk_count, uint32_t cap, int64_t nchunks,
+               int nseg, int nx, int nbins, const uint32_t *__restrict__ start, uint32_t *__restrict__ cursor,
+               uint32_t *__restrict__ list)
+{
+    extern __shared__ uint32_t uf_sm[];
+    uint32_t *cnt = uf_sm, *bas = cnt + nbins;
+    for (int i = threadIdx.x; i < nbins; i += 256) cnt[i] = 0u;
+    __syncthreads();
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const uint32_t c = chunk_count[chunk];
+        const uint32_t *rec = raw + chunk * cap;
+        const int64_t row0 = chunk * UF_CHUNK / nseg;
+        const uint32_t v0 = (uint32_t)(row0 * nx + (chunk * UF_CHUNK - row0 * nseg) * UF_SEGX);
+        for (uint32_t i = threadIdx.x; i < c; i += 256) atomicAdd(&cnt[rec[i] & ((1u << UF_TAGBITS) - 1u)], 1u);
         __syncthreads();
-        for (int b = threadIdx.x; b < nbins; b += 256)
-            if (cnt[b]) atomicAdd(&hist[b], cnt[b]);
+        for (int b = threadIdx.x; b < nbins; b += 256) {
+            const uint32_t k = cnt[b];
+            if (k) bas[b] = start[b] + atomicAdd(&cursor[b], k);
+            cnt[b] = 0u;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < c; i += 256) {
+            const uint32_t r = rec[i], tag = r & ((1u << UF_TAGBITS) - 1u);
+            list[bas[tag] + atomicAdd(&cnt[tag], 1u)] = v0 + (r >> UF_TAGBITS);
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += 256) cnt[b] = 0u;
+        __syncthreads();
     }
 }
 
@@ -849,7 +959,16 @@ uf_union_rec_kernel(uint32_t *parent, const uint32_t *__restrict__ list, const u
         while (j >= edge[f + 1]) ++f;
         if (f >= nfam) f -= nfam;
         const uint32_t v = list[j];
-        uf_union(parent, v + 1u, (uint32_t)((long long)v + st.s[f]) + 1u, jtime, k);
+        // the first two levels of both finds as independent loads: after the pre-linking almost every voxel is at
+        // most one step from its tree's root (or from a child of node 0)
+        const uint32_t a = v + 1u, b = (uint32_t)((long long)v + st.s[f]) + 1u;
+        const volatile uint32_t *vp = parent;
+        const uint32_t pa = vp[a], pb = vp[b];
+        const uint32_t ga = pa ? vp[pa] : 0u, gb = pb ? vp[pb] : 0u;
+        const bool da = pa == 0u || ga == 0u || ga == pa, db = pb == 0u || gb == 0u || gb == pb;     // root known
+        const uint32_t ra = (pa == 0u || ga == 0u) ? 0u : pa, rb = (pb == 0u || gb == 0u) ? 0u : pb;
+        if (da && db && ra == rb) continue;
+        uf_union(parent, da ? ra : a, db ? rb : b, jtime, k);
     }
 }
 
@@ -906,5 +1025,21 @@ uf_compress_kernel(uint32_t *parent, const uint8_t *__restrict__ acls, int nz, i
             }
         }
         __syncthreads();
+    }
+}
+
+// standalone flood after uf_compress_kernel: out[v] = 1 for the voxels of the mask (cls == 0) whose tree hangs under node 0
+__global__ void __launch_bounds__(256)
+uf_reach_out_kernel(const uint32_t *__restrict__ parent, const uint8_t *__restrict__ cls, uint8_t *__restrict__ out, int64_t n)
+{
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += step) {
+        uint8_t r = 0;
+        if (cls[v] == 0) {
+            uint32_t x = (uint32_t)(v + 1), p = parent[x];
+            while (p != 0u && p != x) { x = p; p = parent[x]; }
+            r = p == 0u ? 1 : 0;
+        }
+        out[v] = r;
     }
 }

@@ -711,6 +711,10 @@ struct LtWorkspace {
     uint32_t *parent;
     uint32_t *uf_list;    // voxels activated at the current radius (one segment of UF_SEG voxels at a time)
     size_t uf_list_cap;
+    uint32_t *uf_raw;     // unsorted records, one region of uf_cap entries per chunk; uf_ccount: records per chunk
+    uint32_t *uf_ccount;
+    int64_t uf_chunks;
+    uint32_t uf_cap;
     uint32_t *uf_bins;    // histogram / slice starts / cursors of the link records
     int *gate;
     uint32_t *gen_d2;     // generic algo: full u32 distance map of ~seeds
@@ -736,10 +740,16 @@ static LtWorkspace carve_lt(const psb200_ctx *ctx, char *base, int64_t nz, int64
     if (inlet_mode != PSB200_INLETS_NONE) {
         w.rcls = c.take<uint8_t>(n + 16);
         w.parent = c.take<uint32_t>(n + 1);
-        // link records of the row-rooted forest (flood_kernels.cuh): at most one x record per voxel and one per
-        // two voxels for each of y and z; also the per-voxel job list of the fallback / 26-connectivity path
-        w.uf_list_cap = 2 * n + 2 * (size_t)(nz * ny) + 64;
+        // link records of the row-rooted forest (flood_kernels.cuh): per chunk of UF_CHUNK segments at most one x
+        // record per voxel and one per two voxels (+ one per segment) for each of y and z -- raw[] has that much
+        // room per chunk, list[] (the records sorted into slices; also the job list of the fallback path) in total
+        const int64_t segs = nz * ny * ((nx + UF_SEGX - 1) / UF_SEGX);
+        w.uf_chunks = (segs + UF_CHUNK - 1) / UF_CHUNK;
+        w.uf_cap = (uint32_t)(2 * UF_CHUNK * (nx < UF_SEGX ? nx : UF_SEGX) + 2 * UF_CHUNK + 64);
+        w.uf_list_cap = std::max<size_t>(n + 64, (size_t)w.uf_chunks * w.uf_cap);
         w.uf_list = c.take<uint32_t>(w.uf_list_cap);
+        w.uf_raw = c.take<uint32_t>((size_t)w.uf_chunks * w.uf_cap);
+        w.uf_ccount = c.take<uint32_t>((size_t)w.uf_chunks + 64);
         w.uf_bins = c.take<uint32_t>(3 * (UF_NTIMES * UF_MAXFAM + 64));
     }
     if (ctx->algo == PSB200_ALGO_GENERIC) {
@@ -1010,11 +1020,17 @@ static int uf_forest_impl(psb200_ctx *ctx, LtWorkspace &w, const InletSpec &inl,
         uf_prelink_kernel<<<grid_a, 256, 0, st>>>(cls, inl, (int)nz, (int)ny, (int)nx, w.parent, jtime, acls);
     }
     LAUNCH_CHECK(ctx);
+    int *ovf = w.gate + 2;
     CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(ovf, 0, sizeof(int), st));
     {
         ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-        uf_links_kernel<false><<<grid, 256, (size_t)nbins * 4, st>>>(acls, inl, (int)nz, (int)ny, (int)nx, nfam, nsub,
-                                                                                  hist, nullptr, nullptr, nullptr);
+        if (nfam > 3)
+            uf_emit_kernel<5><<<grid, 256, (size_t)nbins * 4, st>>>(acls, inl, (int)nz, (int)ny, (int)nx, nfam, nsub, hist,
+                                                                  w.uf_raw, w.uf_ccount, w.uf_cap, ovf);
+        else
+            uf_emit_kernel<3><<<grid, 256, (size_t)nbins * 4, st>>>(acls, inl, (int)nz, (int)ny, (int)nx, nfam, nsub, hist,
+                                                                  w.uf_raw, w.uf_ccount, w.uf_cap, ovf);
     }
     LAUNCH_CHECK(ctx);
     {
@@ -1024,15 +1040,16 @@ static int uf_forest_impl(psb200_ctx *ctx, LtWorkspace &w, const InletSpec &inl,
     LAUNCH_CHECK(ctx);
     *fits = true;
     if (nfam > 3) {
-        uint32_t total = 0;
-        CUDA_TRY(cudaMemcpyAsync(&total, start + nbins, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        // 26-connectivity has no useful a-priori bound on the records of a chunk
+        int over = 0;
+        CUDA_TRY(cudaMemcpyAsync(&over, ovf, sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        if ((size_t)total > w.uf_list_cap) { *fits = false; return PSB200_OK; }
+        if (over) { *fits = false; return PSB200_OK; }
     }
     {
         ProfScope ps__(ctx, st, K_UF_ACTIVATE);
-        uf_links_kernel<true><<<grid, 256, (size_t)nbins * 8, st>>>(acls, inl, (int)nz, (int)ny, (int)nx, nfam, nsub,
-                                                                                 nullptr, start, cursor, w.uf_list);
+        uf_sort_kernel<<<grid, 256, (size_t)nbins * 8, st>>>(w.uf_raw, w.uf_ccount, w.uf_cap, w.uf_chunks, nseg, (int)nx, nbins,
+                                                           start, cursor, w.uf_list);
     }
     LAUNCH_CHECK(ctx);
     *start_out = start;
@@ -1736,11 +1753,6 @@ extern "C" int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t 
         flood_cls_kernel<<<g, 256, 0, st>>>(mask, w.cls, n);
     }
     LAUNCH_CHECK(ctx);
-    {
-        ProfScope ps__(ctx, st, K_UF_INIT);
-        uf_rcls_init_kernel<<<g, 256, 0, st>>>(w.cls, w.rcls, n);
-    }
-    LAUNCH_CHECK(ctx);
     bool done = false;
     if (ctx->uf_records) {
         // row-rooted forest + link records (the activation map goes to the reach buffer, unused here)
@@ -1757,12 +1769,18 @@ extern "C" int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t 
             LAUNCH_CHECK(ctx);
             {
                 ProfScope ps__(ctx, st, K_UF_MARK);
-                uf_mark_kernel<<<grid_for((n + 15) / 16, 256, ctx->sm_count, 16), 256, 0, st>>>(w.parent, w.cls, w.rcls, 0, n, w.gate);
+                uf_reach_out_kernel<<<g, 256, 0, st>>>(w.parent, w.cls, out, n);
             }
             LAUNCH_CHECK(ctx);
+            return PSB200_OK;
         }
     }
     if (!done) {
+        {
+            ProfScope ps__(ctx, st, K_UF_INIT);
+            uf_rcls_init_kernel<<<g, 256, 0, st>>>(w.cls, w.rcls, n);
+        }
+        LAUNCH_CHECK(ctx);
         {
             ProfScope ps__(ctx, st, K_UF_INIT);
             uf_init_kernel<<<g, 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx, nullptr);
