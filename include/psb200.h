@@ -250,6 +250,33 @@ int psb200_uf_activate(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, co
                        int inlet_mode, int ndim, int klo, int khi, int64_t nz, int64_t ny,
                        int64_t nx, int64_t z0, int64_t nz_global, void *ws, size_t ws_bytes,
                        psb200_stream stream);   /* ws: psb200_uf_workspace_bytes() of scratch */
+/* The same flood on the row-rooted forest + link records + join times of the single-GPU loop
+ * (csrc/flood_kernels.cuh).  `rec` (psb200_uf_records_bytes() bytes) is owned by the caller and kept untouched
+ * across the radius loop:
+ *   psb200_uf_begin_records    : forest with the x chains pre-linked, link records of ALL radius indices bucketed
+ *   psb200_uf_activate_records : the unions of the indices klo < k <= khi
+ *   psb200_uf_face_records / psb200_uf_inject_records : as psb200_uf_face / _inject; a tree that is connected
+ *                                through a slab face at index k records k as its join time
+ *   psb200_uf_resolve_records  : after the LAST index (all activations and exchanges done), one pass:
+ *                                rcls[v] = first index at which v is a seed connected to the inlets
+ *                                = max(cls[v], join time of v's tree); CLS 254 = never, 255 = background.
+ * There is no per-radius marking: the radius loop runs on the final rcls map afterwards. */
+size_t psb200_uf_records_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx);
+int psb200_uf_begin_records(psb200_ctx *ctx, const uint8_t *cls, uint32_t *parent, const uint8_t *inlets,
+                            int inlet_mode, int ndim, int64_t nz, int64_t ny, int64_t nx, int64_t z0,
+                            int64_t nz_global, void *rec, size_t rec_bytes, psb200_stream stream);
+int psb200_uf_activate_records(psb200_ctx *ctx, uint32_t *parent, int klo, int khi, int64_t nz, int64_t ny,
+                               int64_t nx, void *rec, size_t rec_bytes, psb200_stream stream);
+int psb200_uf_face_records(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
+                           int inlet_mode, int ndim, int k, int64_t zplane, uint8_t *flags_out, int64_t nz,
+                           int64_t ny, int64_t nx, int64_t z0, int64_t nz_global, void *rec, size_t rec_bytes,
+                           psb200_stream stream);
+int psb200_uf_inject_records(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
+                             int inlet_mode, int ndim, int k, int64_t zplane, const uint8_t *nb_flags,
+                             int *changed_dev, int64_t nz, int64_t ny, int64_t nx, int64_t z0,
+                             int64_t nz_global, void *rec, size_t rec_bytes, psb200_stream stream);
+int psb200_uf_resolve_records(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, uint8_t *rcls, int64_t nz,
+                              int64_t ny, int64_t nx, void *rec, size_t rec_bytes, psb200_stream stream);
 int psb200_uf_face(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
                    int inlet_mode, int ndim, int k, int64_t zplane, uint8_t *flags_out, int64_t nz,
                    int64_t ny, int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream);

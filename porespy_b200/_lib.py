@@ -85,6 +85,14 @@ SIGNATURES = {
     "psb200_mark_written": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "psb200_uf_begin": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _vp]),
     "psb200_uf_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
+    "psb200_uf_records_bytes": (_sz, [_vp, _i64, _i64, _i64]),
+    "psb200_uf_begin_records": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "psb200_uf_activate_records": (_i32, [_vp, _vp, _i32, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "psb200_uf_face_records": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _i64, _i64, _i64, _i64, _i64,
+                                      _vp, _sz, _vp]),
+    "psb200_uf_inject_records": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _vp, _i64, _i64, _i64, _i64,
+                                        _i64, _vp, _sz, _vp]),
+    "psb200_uf_resolve_records": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_uf_activate": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64,
                                   _vp, _sz, _vp]),
     "psb200_uf_face": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),

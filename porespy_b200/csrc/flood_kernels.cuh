@@ -526,7 +526,7 @@ __global__ void uf_gate_kernel(int *gate, const int *__restrict__ kmin, int k) {
 // out[i] = 1 if voxel i of local plane z is a graph node (inlet or cls <= k) whose root is 0.
 __global__ void __launch_bounds__(256)
 uf_face_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpec inl, int k, int z,
-               int nz, int ny, int nx, uint8_t *__restrict__ out)
+               int nz, int ny, int nx, uint8_t *__restrict__ out, uint8_t *jtime = nullptr)
 {
     const int64_t plane = (int64_t)ny * nx;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
@@ -534,7 +534,7 @@ uf_face_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpec inl,
         const int64_t v = (int64_t)z * plane + i;
         const int y = (int)(i / nx), x = (int)(i % nx);
         const bool node = (int)cls[v] <= k || is_inlet(inl, v, z, y, x, nz, ny, nx);
-        out[i] = (node && uf_find(parent, (uint32_t)(v + 1)) == 0u) ? 1 : 0;
+        out[i] = (node && uf_find(parent, (uint32_t)(v + 1), jtime) == 0u) ? 1 : 0;
     }
 }
 
@@ -543,7 +543,7 @@ uf_face_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpec inl,
 // is set when that reached a component that was not connected before.
 __global__ void __launch_bounds__(256)
 uf_inject_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpec inl, int k, int z,
-                 int nz, int ny, int nx, const uint8_t *__restrict__ nb, int *changed)
+                 int nz, int ny, int nx, const uint8_t *__restrict__ nb, int *changed, uint8_t *jtime = nullptr)
 {
     const int64_t plane = (int64_t)ny * nx;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
@@ -552,8 +552,8 @@ uf_inject_kernel(uint32_t *parent, const uint8_t *__restrict__ cls, InletSpec in
         const int64_t v = (int64_t)z * plane + i;
         const int y = (int)(i / nx), x = (int)(i % nx);
         if (!((int)cls[v] <= k || is_inlet(inl, v, z, y, x, nz, ny, nx))) continue;
-        if (uf_find(parent, (uint32_t)(v + 1)) == 0u) continue;
-        uf_union(parent, (uint32_t)(v + 1), 0u);
+        if (uf_find(parent, (uint32_t)(v + 1), jtime) == 0u) continue;
+        uf_union(parent, (uint32_t)(v + 1), 0u, jtime, k);      // with join times: connected through the face at index k
         *changed = 1;
     }
 }

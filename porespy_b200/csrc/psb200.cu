@@ -1666,6 +1666,165 @@ extern "C" int psb200_uf_activate(psb200_ctx *ctx, uint32_t *parent, const uint8
                             (cudaStream_t)stream);
 }
 
+// Record store of the step-level flood (psb200_uf_*_records): the same row-rooted forest + link records + join
+// times as the single-GPU loop (flood_kernels.cuh), built once for all radius indices and kept by the caller across
+// the radius loop.
+static size_t carve_uf_records(char *base, int64_t nz, int64_t ny, int64_t nx, LtWorkspace &w, uint8_t **acls,
+                               uint8_t **jtime)
+{
+    const size_t n = (size_t)nz * ny * nx;
+    Carver c{base, 0};
+    w.gate = c.take<int>(64);
+    w.uf_bins = c.take<uint32_t>(3 * (UF_NTIMES * UF_MAXFAM + 64));
+    *acls = c.take<uint8_t>(n + 16);
+    *jtime = c.take<uint8_t>(n + 16);
+    const int64_t segs = nz * ny * ((nx + UF_SEGX - 1) / UF_SEGX);
+    w.uf_chunks = (segs + UF_CHUNK - 1) / UF_CHUNK;
+    w.uf_cap = (uint32_t)(2 * UF_CHUNK * (nx < UF_SEGX ? nx : UF_SEGX) + 2 * UF_CHUNK + 64);
+    w.uf_list_cap = (size_t)w.uf_chunks * w.uf_cap;
+    w.uf_list = c.take<uint32_t>(w.uf_list_cap);
+    w.uf_raw = c.take<uint32_t>((size_t)w.uf_chunks * w.uf_cap);
+    w.uf_ccount = c.take<uint32_t>((size_t)w.uf_chunks + 64);
+    return c.off + 256;
+}
+
+struct UfRecords {
+    LtWorkspace w;
+    uint8_t *acls, *jtime;
+    const uint32_t *start;
+};
+
+static int uf_records_open(const char *who, void *rec, size_t rec_bytes, int64_t nz, int64_t ny, int64_t nx, UfRecords &r)
+{
+    if (!rec) return fail(PSB200_ERR_INVALID, "%s: record store is NULL", who);
+    char *base = (char *)(((uintptr_t)rec + 255) & ~(uintptr_t)255);
+    r.w = LtWorkspace{};
+    const size_t need = carve_uf_records(base, nz, ny, nx, r.w, &r.acls, &r.jtime);
+    if (rec_bytes < need + (size_t)(base - (char *)rec))
+        return fail(PSB200_ERR_WORKSPACE, "%s needs %zu bytes of record store, got %zu", who, need + 256, rec_bytes);
+    r.start = r.w.uf_bins + UF_NTIMES * 6 + 64;          // (uf_forest_impl: 6-connectivity, 6 slices per radius index)
+    return PSB200_OK;
+}
+
+extern "C" size_t psb200_uf_records_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx)
+{
+    if (!ctx || nz < 1 || ny < 1 || nx < 1) return 0;
+    LtWorkspace w{};
+    uint8_t *acls = nullptr, *jtime = nullptr;
+    return carve_uf_records(nullptr, nz, ny, nx, w, &acls, &jtime) + 256;
+}
+
+extern "C" int psb200_uf_begin_records(psb200_ctx *ctx, const uint8_t *cls, uint32_t *parent, const uint8_t *inlets,
+                                       int inlet_mode, int ndim, int64_t nz, int64_t ny, int64_t nx, int64_t z0,
+                                       int64_t nz_global, void *rec, size_t rec_bytes, psb200_stream stream)
+{
+    int rc = uf_args("uf_begin_records", ctx, parent, cls, inlets, inlet_mode, ndim, nz, ny, nx, z0, nz_global);
+    if (rc) return rc;
+    UfRecords r;
+    rc = uf_records_open("uf_begin_records", rec, rec_bytes, nz, ny, nx, r);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    r.w.parent = parent;
+    InletSpec inl{inlet_mode, ndim, inlets, (int)z0, (int)nz_global};
+    const uint32_t *start = nullptr;
+    bool fits = true;
+    return uf_forest_impl(ctx, r.w, inl, cls, r.acls, r.jtime, 6, nz, ny, nx, (cudaStream_t)stream, &start, &fits);
+}
+
+extern "C" int psb200_uf_activate_records(psb200_ctx *ctx, uint32_t *parent, int klo, int khi, int64_t nz, int64_t ny,
+                                          int64_t nx, void *rec, size_t rec_bytes, psb200_stream stream)
+{
+    if (!ctx || !parent) return fail(PSB200_ERR_INVALID, "uf_activate_records: NULL argument");
+    int rc = check_dims("uf_activate_records", nz, ny, nx);
+    if (rc) return rc;
+    if (klo < -1 || khi >= UF_NTIMES || klo > khi) return fail(PSB200_ERR_INVALID, "uf_activate_records: bad radius range");
+    UfRecords r;
+    rc = uf_records_open("uf_activate_records", rec, rec_bytes, nz, ny, nx, r);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    r.w.parent = parent;
+    for (int k = klo + 1; k <= khi; ++k) {
+        rc = uf_union_records(ctx, r.w, r.start, k, 6, ny, nx, r.jtime, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return PSB200_OK;
+}
+
+extern "C" int psb200_uf_face_records(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
+                                      int inlet_mode, int ndim, int k, int64_t zplane, uint8_t *flags_out, int64_t nz,
+                                      int64_t ny, int64_t nx, int64_t z0, int64_t nz_global, void *rec, size_t rec_bytes,
+                                      psb200_stream stream)
+{
+    int rc = uf_args("uf_face_records", ctx, parent, cls, inlets, inlet_mode, ndim, nz, ny, nx, z0, nz_global);
+    if (rc) return rc;
+    if (!flags_out || zplane < 0 || zplane >= nz) return fail(PSB200_ERR_INVALID, "uf_face_records: bad plane / output");
+    UfRecords r;
+    rc = uf_records_open("uf_face_records", rec, rec_bytes, nz, ny, nx, r);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    InletSpec inl{inlet_mode, ndim, inlets, (int)z0, (int)nz_global};
+    {
+        ProfScope ps__(ctx, st, K_UF_FACE);
+        uf_face_kernel<<<grid_for(ny * nx, 256, ctx->sm_count, 8), 256, 0, st>>>(parent, cls, inl, k, (int)zplane, (int)nz,
+                                                                               (int)ny, (int)nx, flags_out, r.jtime);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_uf_inject_records(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
+                                        int inlet_mode, int ndim, int k, int64_t zplane, const uint8_t *nb_flags,
+                                        int *changed_dev, int64_t nz, int64_t ny, int64_t nx, int64_t z0,
+                                        int64_t nz_global, void *rec, size_t rec_bytes, psb200_stream stream)
+{
+    int rc = uf_args("uf_inject_records", ctx, parent, cls, inlets, inlet_mode, ndim, nz, ny, nx, z0, nz_global);
+    if (rc) return rc;
+    if (!nb_flags || !changed_dev || zplane < 0 || zplane >= nz)
+        return fail(PSB200_ERR_INVALID, "uf_inject_records: bad plane / flags / changed pointer");
+    UfRecords r;
+    rc = uf_records_open("uf_inject_records", rec, rec_bytes, nz, ny, nx, r);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    InletSpec inl{inlet_mode, ndim, inlets, (int)z0, (int)nz_global};
+    {
+        ProfScope ps__(ctx, st, K_UF_FACE);
+        uf_inject_kernel<<<grid_for(ny * nx, 256, ctx->sm_count, 8), 256, 0, st>>>(parent, cls, inl, k, (int)zplane, (int)nz,
+                                                                                 (int)ny, (int)nx, nb_flags, changed_dev,
+                                                                                 r.jtime);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_uf_resolve_records(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, uint8_t *rcls, int64_t nz,
+                                         int64_t ny, int64_t nx, void *rec, size_t rec_bytes, psb200_stream stream)
+{
+    if (!ctx || !parent || !cls || !rcls) return fail(PSB200_ERR_INVALID, "uf_resolve_records: NULL argument");
+    int rc = check_dims("uf_resolve_records", nz, ny, nx);
+    if (rc) return rc;
+    UfRecords r;
+    rc = uf_records_open("uf_resolve_records", rec, rec_bytes, nz, ny, nx, r);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = nz * ny * nx;
+    int *kmin = r.w.gate + 1;
+    CUDA_TRY(cudaMemsetAsync(kmin, 0x7F, sizeof(int), st));
+    {
+        ProfScope ps__(ctx, st, K_UF_MARK);
+        uf_compress_kernel<<<ctx->sm_count * 6, 256, 0, st>>>(parent, r.acls, (int)nz, (int)ny, (int)nx);
+    }
+    LAUNCH_CHECK(ctx);
+    {
+        ProfScope ps__(ctx, st, K_UF_MARK);
+        uf_resolve_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(parent, cls, r.jtime, rcls, n, kmin);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
 extern "C" int psb200_uf_face(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const uint8_t *inlets,
                               int inlet_mode, int ndim, int k, int64_t zplane, uint8_t *flags_out, int64_t nz,
                               int64_t ny, int64_t nx, int64_t z0, int64_t nz_global, psb200_stream stream)

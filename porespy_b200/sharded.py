@@ -53,6 +53,7 @@ class CudaBackend:
         self.ctx = ctx
         self.device = torch.device("cuda", ctx.device)
         self.bit_tmax = 200
+        self.uf_records = True      # step-level flood on the row-rooted forest + link records (False: per-voxel job lists)
 
     # -- allocation
     def empty(self, n, dtype):
@@ -167,6 +168,15 @@ class CudaBackend:
         st.rcls = self.empty(nz * ny * nx, self.torch.uint8)
         st.parent = self.empty(nz * ny * nx + 1, self.torch.int32)
         st.flags = self.zeros(2, self.torch.int32)            # [changed, any marked]
+        st.rec = None
+        if self.uf_records:
+            # row-rooted forest + link records of all radii + join times, built once (csrc/flood_kernels.cuh); the store
+            # is the state of the loop, so it is its own allocation rather than the context's shared scratch
+            st.rec = self.empty(self.ctx.lib.psb200_uf_records_bytes(self.ctx.handle, nz, ny, nx), self.torch.uint8)
+            _lib.check(self.ctx.lib.psb200_uf_begin_records(self.ctx.handle, dev.ptr(cls), dev.ptr(st.parent),
+                                                            dev.ptr(st.inlets), st.mode, 3, nz, ny, nx, st.z0, st.nzg,
+                                                            dev.ptr(st.rec), st.rec.numel(), dev.stream_ptr()))
+            return st
         _lib.check(self.ctx.lib.psb200_uf_begin(self.ctx.handle, dev.ptr(cls), dev.ptr(st.rcls), dev.ptr(st.parent),
                                                 dev.ptr(st.inlets), st.mode, 3, nz, ny, nx, st.z0, st.nzg,
                                                 dev.stream_ptr()))
@@ -174,6 +184,11 @@ class CudaBackend:
 
     def uf_activate(self, st, klo, khi):
         nz, ny, nx = st.shape
+        if st.rec is not None:
+            _lib.check(self.ctx.lib.psb200_uf_activate_records(self.ctx.handle, dev.ptr(st.parent), int(klo), int(khi),
+                                                               nz, ny, nx, dev.ptr(st.rec), st.rec.numel(),
+                                                               dev.stream_ptr()))
+            return
         ws = self.ctx.workspace(self.ctx.lib.psb200_uf_workspace_bytes(self.ctx.handle, nz, ny, nx))
         _lib.check(self.ctx.lib.psb200_uf_activate(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls),
                                                    dev.ptr(st.inlets), st.mode, 3, int(klo), int(khi), nz, ny, nx,
@@ -182,6 +197,12 @@ class CudaBackend:
     def uf_face(self, st, k, zplane):
         nz, ny, nx = st.shape
         out = self.empty(ny * nx, self.torch.uint8)
+        if st.rec is not None:
+            _lib.check(self.ctx.lib.psb200_uf_face_records(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls),
+                                                           dev.ptr(st.inlets), st.mode, 3, int(k), int(zplane), dev.ptr(out),
+                                                           nz, ny, nx, st.z0, st.nzg, dev.ptr(st.rec), st.rec.numel(),
+                                                           dev.stream_ptr()))
+            return out
         _lib.check(self.ctx.lib.psb200_uf_face(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls), dev.ptr(st.inlets),
                                                st.mode, 3, int(k), int(zplane), dev.ptr(out), nz, ny, nx, st.z0,
                                                st.nzg, dev.stream_ptr()))
@@ -189,6 +210,12 @@ class CudaBackend:
 
     def uf_inject(self, st, k, zplane, nb_flags):
         nz, ny, nx = st.shape
+        if st.rec is not None:
+            _lib.check(self.ctx.lib.psb200_uf_inject_records(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls),
+                                                             dev.ptr(st.inlets), st.mode, 3, int(k), int(zplane),
+                                                             dev.ptr(nb_flags), dev.ptr(st.flags), nz, ny, nx, st.z0,
+                                                             st.nzg, dev.ptr(st.rec), st.rec.numel(), dev.stream_ptr()))
+            return
         _lib.check(self.ctx.lib.psb200_uf_inject(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls),
                                                  dev.ptr(st.inlets), st.mode, 3, int(k), int(zplane),
                                                  dev.ptr(nb_flags), dev.ptr(st.flags), nz, ny, nx, st.z0, st.nzg,
@@ -205,6 +232,22 @@ class CudaBackend:
         _lib.check(self.ctx.lib.psb200_uf_mark(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls), dev.ptr(st.rcls),
                                                int(k), ctypes.c_void_p(st.flags.data_ptr() + 4), st.cls.numel(),
                                                dev.stream_ptr()))
+
+
+    def uf_settle(self, st, k):
+        """After the exchanges of radius index k.  Job lists: mark the seeds reached at k.  Records: nothing -- the
+        join times hold that information until uf_resolve."""
+        if st.rec is None:
+            self.uf_mark(st, k)
+
+    def uf_resolve(self, st):
+        """After the last radius index: rcls = first index at which a voxel is a seed connected to the inlets."""
+        if st.rec is not None:
+            nz, ny, nx = st.shape
+            _lib.check(self.ctx.lib.psb200_uf_resolve_records(self.ctx.handle, dev.ptr(st.parent), dev.ptr(st.cls),
+                                                              dev.ptr(st.rcls), nz, ny, nx, dev.ptr(st.rec),
+                                                              st.rec.numel(), dev.stream_ptr()))
+            st.rec = None              # the store is dead from here on
 
 
 class UfState:
@@ -522,14 +565,24 @@ class ShardedVolume:
                     raise Exception("inlets not valid, refer to docstring for info")
                 inl = be.to_u8(inlets)
             st = be.uf_begin(cls, inl, lshape, self.zstarts[self.rank], nz)
+            # F:1181-1183 for every radius before the first dilation: the seed sets are nested, so the union-find only
+            # links the voxels that became seeds at each radius, and the dilation of radius k only asks whether a
+            # voxel's FIRST radius as a reached seed is k (or <= k) -- the final map answers that for every k
             self.flood_sweeps = []
+            for k in range(len(T)):
+                be.uf_activate(st, k - 1, k)
+                self.flood_sweeps.append(self._flood_exchange(st, k))
+                be.uf_settle(st, k)
+            be.uf_resolve(st)
+            cls = st.rcls
+            st.parent = None
         written = None
         packed, packed_bits = None, None
-        # Not access-limited: the seed bits of every bit-path radius are a function of the class map
-        # alone, so the class bytes of the deepest bit-path halo travel ONCE and each rank packs its
+        # The seed bits of every bit-path radius are a function of the (reached-)class map alone, which is final
+        # here, so the class bytes of the deepest bit-path halo travel ONCE and each rank packs its
         # extended slab itself -- one halo exchange instead of one per bit-path radius.
         cls_ext, ext_lo, ext_hi = None, 0, 0
-        if st is None and self.world > 1:
+        if self.world > 1:
             wb = [host.isqrt(int(Tk) - 1) for Tk in T if be.bit_ok(lshape, int(Tk))]
             if wb and max(wb) > 0:
                 ext_lo, ext_hi = self._halo_depths(max(wb))
@@ -544,13 +597,6 @@ class ShardedVolume:
             Tk = int(Tk)
             W = host.isqrt(Tk - 1)
             nlo, nhi = self._halo_depths(W)
-            if st is not None:
-                # F:1181-1183: keep only the seeds connected to the inlets; seed sets are nested, so
-                # the union-find only links the voxels that became seeds at this radius
-                be.uf_activate(st, k - 1, k)
-                self.flood_sweeps.append(self._flood_exchange(st, k))
-                be.uf_mark(st, k)
-                cls = st.rcls
             if be.bit_ok(lshape, Tk):
                 nw = nx // 32
                 plane = ny * nw

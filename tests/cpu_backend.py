@@ -168,3 +168,10 @@ class CpuBackend:
         conn = self._connected(st, k)[1]
         r = st.rcls.numpy().reshape(st.shape)
         r[(st.cls <= k) & conn & (r == mf.CLS_NEVER)] = k
+
+    # the driver's view of the two GPU flavours: per-radius marking (here) or join times + one resolve pass
+    def uf_settle(self, st, k):
+        self.uf_mark(st, k)
+
+    def uf_resolve(self, st):
+        pass

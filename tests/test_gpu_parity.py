@@ -271,6 +271,42 @@ def _porosimetry_vs_oracle(psb, shape, por):
         psb.filters.porosimetry(im, inlets=np.zeros(shape))
 
 
+@pytest.mark.parametrize("shape,por", [((20, 24, 300), 0.55), ((40, 517), 0.6), ((9, 33, 131), 0.5)])
+@pytest.mark.parametrize("records", [True, False])
+def test_porosimetry_flood_paths(psb, shape, por, records):
+    """Access-limited loop on the row-rooted forest + link records (default) and on the per-voxel job lists:
+    rows of several 128-voxel segments, partial segments, rows that are not a multiple of 4 voxels."""
+    from porespy_b200 import _lib
+    ctx = _lib.context()
+    ctx.set_uf_records(records)
+    try:
+        _porosimetry_vs_oracle(psb, shape, por)
+    finally:
+        ctx.set_uf_records(True)
+
+
+@pytest.mark.parametrize("records", [True, False])
+def test_flood_random_shapes(psb, records):
+    """psb200_flood, 6/26 (4/8) connectivity, near the percolation threshold where components are large and
+    tortuous; shapes with partial segments and odd row lengths; inlets inside the solid as well."""
+    from porespy_b200 import _lib
+    ctx = _lib.context()
+    ctx.set_uf_records(records)
+    try:
+        rng = np.random.default_rng(5)
+        for shape, p in (((12, 14, 130), 0.33), ((7, 9, 261), 0.3), ((60, 259), 0.6), ((3, 5, 7), 0.5),
+                         ((1, 1, 400), 0.9), ((16, 1, 129), 0.7)):
+            im = rng.random(shape) < p
+            inl = np.zeros_like(im)
+            inl[..., 0] = True
+            inl |= rng.random(shape) < 0.002
+            for strel in (None, oc._cross(len(shape))):
+                assert_same(psb.filters.trim_disconnected_blobs(im, inl, strel=strel),
+                            oc.trim_disconnected_blobs(im, inl, strel=strel), f"{shape} {strel is None}")
+    finally:
+        ctx.set_uf_records(True)
+
+
 def test_trim_disconnected_blobs(psb, golden):
     g = golden.trim
     im, inl = g.mask("im2d"), g.mask("inlets2d")
@@ -329,16 +365,19 @@ def test_sharded_two_gpus(psb):
     assert r.returncode == 0 and "SHARDED_GPU_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("records", [True, False])
 @pytest.mark.parametrize("nslabs", [2, 3])
-def test_flood_face_exchange_one_gpu(psb, nslabs):
-    """psb200_uf_begin / activate / face / inject / mark: the slab-local union-finds of a volume cut
-    into z-slabs, coupled only through the face flags (what ShardedVolume._flood_exchange sends
-    between ranks), must reproduce trim_disconnected_blobs on the whole volume for every radius."""
+def test_flood_face_exchange_one_gpu(psb, nslabs, records):
+    """psb200_uf_begin / activate / face / inject / mark (job lists) and psb200_uf_*_records (link records + join
+    times, one resolve pass): the slab-local union-finds of a volume cut into z-slabs, coupled only through the
+    face flags (what ShardedVolume._flood_exchange sends between ranks), must reproduce
+    trim_disconnected_blobs on the whole volume for every radius."""
     import torch
     from porespy_b200 import _lib, _host
     from porespy_b200.sharded import CudaBackend, split_counts
     be = CudaBackend(_lib.context())
-    shape = (60, 48, 64)
+    be.uf_records = records           # link records (default) / per-voxel job lists
+    shape = (60, 48, 200) if records else (60, 48, 64)     # 200: a full and a partial 128-voxel segment per row
     nz, ny, nx = shape
     im = oc.blobs(list(shape), porosity=0.55, blobiness=1.5, seed=11)
     d2 = oc.edt_sq(im)
@@ -374,11 +413,14 @@ def test_flood_face_exchange_one_gpu(psb, nslabs):
                     break
                 assert sweeps < 50
             for st in sts:
-                be.uf_mark(st, k)
+                be.uf_settle(st, k)
+        for st in sts:
+            be.uf_resolve(st)
+        for k, Tk in enumerate(T):
             seeds = d2 >= Tk
             want = oc.trim_disconnected_blobs(seeds, inlets_full, strel=oc._cross(3))
             got = np.concatenate([(st.rcls.cpu().numpy().reshape(st.shape) <= k) for st in sts], axis=0)
-            assert_same(got, want, f"reached seeds, inlets={inl_kind}, k={k}, T={Tk}, {sweeps} sweeps")
+            assert_same(got, want, f"reached seeds, inlets={inl_kind}, k={k}, T={Tk}")
 
 
 @pytest.mark.parametrize("permille,threads", [(0, 0), (500, 3), (1000, 0), (730, 16)])
