@@ -228,6 +228,18 @@ int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t *inlets, ui
                  int conn, int64_t nz, int64_t ny, int64_t nx,
                  void *ws, size_t ws_bytes, psb200_stream stream);
 
+/* Device-side bit packing of a 0 / non-zero byte mask and its inverse (0 / 1 bytes): bits[i] bit j = (src[8 i + j] != 0).
+ * The z-slab shards exchange their EDT input halo planes in this form (an eighth of the bytes).  dst: 8-byte aligned. */
+int psb200_mask_pack_u8(psb200_ctx *ctx, const uint8_t *src, uint8_t *bits, int64_t n, psb200_stream stream);
+int psb200_mask_unpack_u8(psb200_ctx *ctx, const uint8_t *bits, uint8_t *dst, int64_t n, psb200_stream stream);
+
+/* z-slab shards: the cone value a neighbour's sweep receives from this slab's reach bytes (psb200_lt_xy output),
+ * one byte per column: out[y][x] = max_j (reach[plane j from the face] - j), j < depth (the reach W of the radius).
+ * side 0: the face towards the lower neighbour (plane 0), side 1: towards the upper one (plane nz-1).  The
+ * neighbour passes the plane to psb200_lt_z as a one-plane halo (nhi = 1 resp. nlo = 1). */
+int psb200_lt_halo_cone(psb200_ctx *ctx, const uint8_t *reach, int64_t nz, int64_t ny, int64_t nx, int depth,
+                        int side, uint8_t *out, psb200_stream stream);
+
 /* Step-level access-limited flooding (F:1181-1183 inside the radius loop) for volumes sharded
  * into z-slabs: this rank holds planes [z0, z0+nz) of nz_global.  The union-find
  * (parent: nz*ny*nx + 1 uint32, node 0 = virtual inlet root) is slab-local and kept across radii;

@@ -84,6 +84,9 @@ SIGNATURES = {
     "psb200_upload_mask_u8": (_i32, [_vp, _vp, _i64, _vp, _vp, _sz, _vp, _sz, _i32, _vp]),
     "psb200_mark_written": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "psb200_uf_begin": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "psb200_mask_pack_u8": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "psb200_mask_unpack_u8": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "psb200_lt_halo_cone": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp]),
     "psb200_uf_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
     "psb200_uf_records_bytes": (_sz, [_vp, _i64, _i64, _i64]),
     "psb200_uf_begin_records": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),

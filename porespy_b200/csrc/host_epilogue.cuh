@@ -163,6 +163,26 @@ mask_unpack_kernel(const uint8_t *__restrict__ bits, uint8_t *__restrict__ out, 
     }
 }
 
+// the device-side counterpart (z-slab shards send their EDT halo planes as bits): bits[i] bit j = (src[8 i + j] != 0)
+__global__ void __launch_bounds__(256)
+mask_pack_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ bits, int64_t nbytes_bits, int64_t n)
+{
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    const bool aligned = (((uintptr_t)src) & 7u) == 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes_bits; i += step) {
+        uint32_t b = 0;
+        if (aligned && 8 * i + 8 <= n) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src + 8 * i));
+            // non-zero byte -> its bit 7 set (carry-free SWAR), then gather the four bit-7s of a word into a nibble
+            const uint32_t lo = ((v.x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v.x, hi = ((v.y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v.y;
+            b = ((((lo >> 7) & 0x01010101u) * 0x01020408u) >> 24) | (((((hi >> 7) & 0x01010101u) * 0x01020408u) >> 24) << 4);
+        } else {
+            for (int j = 0; j < 8 && 8 * i + j < n; ++j) b |= (src[8 * i + j] != 0 ? 1u : 0u) << j;
+        }
+        bits[i] = (uint8_t)b;
+    }
+}
+
 // bits[i] bit j = (src[8 i + j] != 0) for the voxels [v0, v1); v0 % 8 == 0
 static void host_pack_slice(const uint8_t *src, uint8_t *bits, int64_t v0, int64_t v1)
 {

@@ -455,3 +455,37 @@ lt_zsweep8_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo,
         commit(z);
     }
 }
+
+// ---- z-slab shards: what a neighbour needs from this slab's reach bytes for ITS cone sweeps is one number per
+// column -- the cone value arriving at the shared face, c = max_j (m_j - j) over the `depth` planes next to the
+// face (j = 0: the face plane).  The neighbour feeds it to its sweep as a single halo plane (nlo / nhi = 1):
+// W planes of halo traffic per radius become one.
+// side 0: cone running down through planes depth-1 .. 0 (for the lower neighbour); side 1: up through
+// nz-depth .. nz-1 (for the upper neighbour).
+__global__ void __launch_bounds__(256)
+lt_halo_cone_kernel(const uint8_t *__restrict__ reach, int nz, int64_t plane, int depth, int side,
+                    uint8_t *__restrict__ out)
+{
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = (plane & 3) == 0 && ((((uintptr_t)reach) | ((uintptr_t)out)) & 3u) == 0;
+    if (vec) {
+        for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; p < plane; p += step * 4) {
+            uint32_t c = 0;
+            for (int j = depth - 1; j >= 0; --j) {
+                const int z = side ? nz - 1 - j : j;
+                c = __vmaxu4(__ldg(reinterpret_cast<const uint32_t *>(reach + (int64_t)z * plane + p)), __vsubus4(c, 0x01010101u));
+            }
+            *reinterpret_cast<uint32_t *>(out + p) = c;
+        }
+    } else {
+        for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += step) {
+            uint32_t c = 0;
+            for (int j = depth - 1; j >= 0; --j) {
+                const int z = side ? nz - 1 - j : j;
+                const uint32_t v = reach[(int64_t)z * plane + p];
+                c = max(v, c ? c - 1u : 0u);
+            }
+            out[p] = (uint8_t)c;
+        }
+    }
+}

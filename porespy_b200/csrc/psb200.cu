@@ -974,6 +974,24 @@ extern "C" int psb200_lt_z(psb200_ctx *ctx, uint8_t *reach, const uint8_t *m_lo,
     return lt_z_impl(ctx, reach, m_lo, nlo, m_hi, nhi, idx, k, T, nz, ny, nx, nullptr, (cudaStream_t)stream);
 }
 
+extern "C" int psb200_lt_halo_cone(psb200_ctx *ctx, const uint8_t *reach, int64_t nz, int64_t ny, int64_t nx, int depth,
+                                   int side, uint8_t *out, psb200_stream stream)
+{
+    if (!ctx || !reach || !out || depth < 0 || (side != 0 && side != 1)) return fail(PSB200_ERR_INVALID, "lt_halo_cone: bad argument");
+    int rc = check_dims("lt_halo_cone", nz, ny, nx);
+    if (rc) return rc;
+    if (depth > nz) depth = (int)nz;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t plane = ny * nx;
+    {
+        ProfScope ps__(ctx, st, K_LT_Z);
+        lt_halo_cone_kernel<<<grid_for((plane + 3) / 4, 256, ctx->sm_count, 8), 256, 0, st>>>(reach, (int)nz, plane, depth, side, out);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
 static int uf_activate_impl(psb200_ctx *ctx, uint32_t *parent, const uint8_t *cls, const InletSpec &inl, int klo,
                             int khi, int conn, int64_t nz, int64_t ny, int64_t nx, uint32_t *list,
                             cudaStream_t st, uint8_t *jtime = nullptr)
@@ -2331,3 +2349,35 @@ extern "C" int psb200_set_zero_codes_u8(psb200_ctx *ctx, uint8_t *codes, const u
     LAUNCH_CHECK(ctx);
     return PSB200_OK;
 }
+
+extern "C" int psb200_mask_pack_u8(psb200_ctx *ctx, const uint8_t *src, uint8_t *bits, int64_t n, psb200_stream stream)
+{
+    if (!ctx || !src || !bits || n < 0) return fail(PSB200_ERR_INVALID, "mask_pack_u8: bad argument");
+    if (n == 0) return PSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nb = (n + 7) / 8;
+    {
+        ProfScope ps__(ctx, st, K_EDT_X);
+        mask_pack_kernel<<<grid_for(nb, 256, ctx->sm_count, 16), 256, 0, st>>>(src, bits, nb, n);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_mask_unpack_u8(psb200_ctx *ctx, const uint8_t *bits, uint8_t *dst, int64_t n, psb200_stream stream)
+{
+    if (!ctx || !bits || !dst || n < 0) return fail(PSB200_ERR_INVALID, "mask_unpack_u8: bad argument");
+    if (n == 0) return PSB200_OK;
+    if (((uintptr_t)dst) & 7u) return fail(PSB200_ERR_INVALID, "mask_unpack_u8: dst must be 8-byte aligned");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nb = (n + 7) / 8;
+    {
+        ProfScope ps__(ctx, st, K_EDT_X);
+        mask_unpack_kernel<<<grid_for(nb, 256, ctx->sm_count, 16), 256, 0, st>>>(bits, dst, nb, n);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+

@@ -122,6 +122,26 @@ class CudaBackend:
         _lib.check(self.ctx.lib.psb200_lt_z(self.ctx.handle, dev.ptr(reach), dev.ptr(m_lo), nlo, dev.ptr(m_hi),
                                             nhi, dev.ptr(idx), int(k), int(T), nz, ny, nx, dev.stream_ptr()))
 
+    def mask_pack(self, src_u8):
+        """0 / non-zero bytes -> bits (psb200_mask_pack_u8)."""
+        n = src_u8.numel()
+        bits = self.empty((n + 7) // 8, self.torch.uint8)
+        _lib.check(self.ctx.lib.psb200_mask_pack_u8(self.ctx.handle, dev.ptr(src_u8), dev.ptr(bits), n, dev.stream_ptr()))
+        return bits
+
+    def mask_unpack(self, bits, dst_u8):
+        """bits -> 0 / 1 bytes into dst_u8 (psb200_mask_unpack_u8)."""
+        _lib.check(self.ctx.lib.psb200_mask_unpack_u8(self.ctx.handle, dev.ptr(bits), dev.ptr(dst_u8), dst_u8.numel(),
+                                                      dev.stream_ptr()))
+
+    def halo_cone(self, reach, shape, depth, side):
+        """One plane for a z-neighbour: the cone value its sweep receives through the shared face (psb200_lt_halo_cone)."""
+        nz, ny, nx = shape
+        out = self.empty(ny * nx, self.torch.uint8)
+        _lib.check(self.ctx.lib.psb200_lt_halo_cone(self.ctx.handle, dev.ptr(reach), nz, ny, nx, int(depth), int(side),
+                                                    dev.ptr(out), dev.stream_ptr()))
+        return out
+
     def pack(self, cls, k, out_bits, shape):
         nz, ny, nx = shape
         _lib.check(self.ctx.lib.psb200_lt_pack(self.ctx.handle, dev.ptr(cls), int(k), dev.ptr(out_bits),
@@ -417,9 +437,21 @@ class ShardedVolume:
         flat = local_u8.reshape(-1)
         ext = be.empty((lo + nzl + hi) * plane, torch.uint8)
         ext[lo * plane:(lo + nzl) * plane] = flat
-        self.exchange_halo(flat[:H * plane] if self.rank > 0 else None,
-                           flat[(nzl - H) * plane:] if self.rank < P - 1 else None,
-                           ext[:lo * plane] if lo else None, ext[(lo + nzl) * plane:] if hi else None)
+        if hasattr(be, "mask_pack") and (H * plane) % 8 == 0 and (lo * plane) % 8 == 0 and ((lo + nzl) * plane) % 8 == 0:
+            # the halo planes travel as bits: an eighth of the bytes
+            nb = H * plane // 8
+            r_lo = be.empty(nb, torch.uint8) if lo else None
+            r_hi = be.empty(nb, torch.uint8) if hi else None
+            self.exchange_halo(be.mask_pack(flat[:H * plane]) if self.rank > 0 else None,
+                               be.mask_pack(flat[(nzl - H) * plane:]) if self.rank < P - 1 else None, r_lo, r_hi)
+            if lo:
+                be.mask_unpack(r_lo, ext[:lo * plane])
+            if hi:
+                be.mask_unpack(r_hi, ext[(lo + nzl) * plane:])
+        else:
+            self.exchange_halo(flat[:H * plane] if self.rank > 0 else None,
+                               flat[(nzl - H) * plane:] if self.rank < P - 1 else None,
+                               ext[:lo * plane] if lo else None, ext[(lo + nzl) * plane:] if hi else None)
         own, lmax = be.edt_ext(ext, (lo + nzl + hi, ny, nx), lo, nzl)
         del ext
         gmax = self._allreduce_max(lmax)
@@ -632,10 +664,13 @@ class ShardedVolume:
             else:
                 reach = be.lt_xy(cls, k, Tk, lshape)
                 plane = ny * nx
-                m_lo = be.empty(nlo * plane, torch.uint8) if nlo else None
-                m_hi = be.empty(nhi * plane, torch.uint8) if nhi else None
-                self.exchange_halo(reach[:W * plane] if self.rank > 0 and W else None,
-                                   reach[(nzl - W) * plane:] if nhi else None, m_lo, m_hi)
+                # a neighbour's cone sweep needs one number per column from this slab: the cone value arriving at the
+                # shared face (cones are shorter than the thinnest slab, so nothing passes through a whole slab) --
+                # one plane per direction and radius instead of W
+                m_lo = be.empty(plane, torch.uint8) if nlo else None
+                m_hi = be.empty(plane, torch.uint8) if nhi else None
+                self.exchange_halo(be.halo_cone(reach, lshape, W, 0) if self.rank > 0 and W else None,
+                                   be.halo_cone(reach, lshape, W, 1) if nhi else None, m_lo, m_hi)
                 be.lt_z(reach, m_lo, m_hi, idx, k, Tk, lshape)
                 del reach
         lut = np.concatenate([[0.0], R])

@@ -75,6 +75,21 @@ class CpuBackend:
     def lt_xy(self, cls, k, T, shape):
         return torch.from_numpy(mf.reach_map(cls.numpy().reshape(shape), k, int(T)).reshape(-1).copy())
 
+    def mask_pack(self, src_u8):
+        return torch.from_numpy(np.packbits(src_u8.numpy() != 0, bitorder="little"))
+
+    def mask_unpack(self, bits, dst_u8):
+        dst_u8.numpy()[:] = np.unpackbits(bits.numpy(), bitorder="little")[:dst_u8.numel()]
+
+    def halo_cone(self, reach, shape, depth, side):
+        """psb200_lt_halo_cone: max_j (reach[plane j from the face] - j), j < depth."""
+        nz, ny, nx = shape
+        r = reach.numpy().reshape(shape).astype(np.int64)
+        out = np.zeros((ny, nx), dtype=np.int64)
+        for j in range(min(int(depth), nz)):
+            out = np.maximum(out, r[nz - 1 - j if side else j] - j)
+        return torch.from_numpy(out.astype(np.uint8).reshape(-1))
+
     def lt_z(self, reach, m_lo, m_hi, idx, k, T, shape):
         nz, ny, nx = shape
         parts, nlo = [], 0

@@ -423,6 +423,31 @@ def test_flood_face_exchange_one_gpu(psb, nslabs, records):
             assert_same(got, want, f"reached seeds, inlets={inl_kind}, k={k}, T={Tk}")
 
 
+def test_shard_halo_helpers(psb):
+    """psb200_mask_pack_u8 / psb200_mask_unpack_u8 (EDT halo planes as bits) and psb200_lt_halo_cone (one plane of cone
+    values per face instead of W planes of reach bytes) against numpy."""
+    import torch
+    from porespy_b200 import _lib
+    from porespy_b200.sharded import CudaBackend
+    from tests.cpu_backend import CpuBackend
+    be, cb = CudaBackend(_lib.context()), CpuBackend()
+    rng = np.random.default_rng(3)
+    for n in (64, 8 * 1000 + 8, 4096 * 33):
+        src = (rng.random(n) < 0.4).astype(np.uint8) * rng.integers(1, 255, n).astype(np.uint8)
+        bits = be.mask_pack(torch.from_numpy(src).cuda())
+        assert np.array_equal(bits.cpu().numpy(), np.packbits(src != 0, bitorder="little"))
+        back = torch.empty(n, dtype=torch.uint8, device="cuda")
+        be.mask_unpack(bits, back)
+        assert np.array_equal(back.cpu().numpy(), (src != 0).astype(np.uint8))
+    for shape in ((9, 12, 16), (5, 7, 9), (40, 8, 12)):
+        reach = rng.integers(0, 12, shape).astype(np.uint8) * (rng.random(shape) < 0.3)
+        t = torch.from_numpy(reach.reshape(-1).copy())
+        for depth in (1, 4, 60):
+            for side in (0, 1):
+                got = be.halo_cone(t.cuda(), shape, depth, side).cpu().numpy()
+                assert np.array_equal(got, cb.halo_cone(t, shape, depth, side).numpy()), (shape, depth, side)
+
+
 @pytest.mark.parametrize("permille,threads", [(0, 0), (500, 3), (1000, 0), (730, 16)])
 def test_host_epilogue_split(psb, permille, threads):
     """psb200_expand_idx_f64_to_host: any split between host-thread widening of index bytes and
