@@ -6,13 +6,13 @@ import re
 import sys
 from collections import OrderedDict
 
-FAMILY = [("xdist_kernel<0>", "edt_x"), ("xdist_kernel<1>", "lt_x"), ("edt_minplus_kernel<MpSrcU16", "edt_y"),
+FAMILY = [("xdist_kernel<0>", "edt_x"), ("xdist_kernel<1>", "lt_x"), ("xdist_bits", "lt_x"), ("edt_col_kernel", "edt_fallback"), ("edt_minplus_kernel<MpSrcU16", "edt_y"),
           ("edt_minplus_kernel<MpSrcU32", "edt_z"), ("edt_minplus16_kernel<MpSrcU16", "edt_y"),
           ("edt_minplus16_kernel<MpSrcU32", "edt_z"), ("edt_fix_inf", "edt_fix_inf"), ("lt_classify", "lt_classify"),
           ("lt_y2", "lt_y"), ("lt_y3", "lt_y"), ("lt_zsweep", "lt_z"), ("lt_z_kernel", "lt_z"), ("lt_xy", "lt_xy"), ("lt_pack", "lt_pack"),
           ("lt_wmask", "lt_wmask"), ("lt_bitball", "lt_bitball"), ("lt_ballz", "lt_bitball"), ("lt_expand", "lt_expand"),
           ("lt_point", "lt_point"), ("uf_", "flood"), ("noise_philox", "blobs"), ("gauss_", "blobs"),
-          ("stats_kernel", "blobs"), ("blobs_finish", "blobs"), ("mask_unpack", "upload")]
+          ("stats_kernel", "blobs"), ("blobs_finish", "blobs"), ("mask_unpack", "upload"), ("mask_pack", "upload")]
 
 
 def family(name):
