@@ -35,7 +35,8 @@ def main(launch_csv, bench_json=None, steps_in_list=None):
     ev = {}
     if bench_json:
         line = [l for l in open(bench_json) if l.startswith("{")][-1]
-        ev = json.loads(line)["roofline"]["kernels_ms_per_step"]
+        roof = json.loads(line)["roofline"]
+        ev = roof.get("kernels_ms_per_step") or {k: v["ms_per_step"] for k, v in roof["kernels"].items()}
     evtot = sum(ev.values()) or 1.0
     print(f"# {launch_csv}: {len(rows) - 1} launches, {total:.2f} ms under ncu (cold-cache, serialised)")
     print(f"{'kernel':14s} {'launches':>8s} {'ncu ms':>9s} {'ncu share':>9s} {'event ms/step':>13s} {'event share':>11s}")
