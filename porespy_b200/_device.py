@@ -92,6 +92,24 @@ def expand_idx_to_host(ctx, idx, lut, shape, chunk=1 << 26, cpu_permille=None, n
     return host.numpy().reshape(shape)
 
 
+def expand_idx_slice_to_host(ctx, idx, off, cnt, lut, host, host_off, ready_event, side_stream, ws, nthreads=None):
+    """One slab of the host-result epilogue, callable from a worker thread: widen idx[off : off + cnt] (uint8,
+    device) into host[host_off : host_off + cnt] (float64, page-locked) once `ready_event` has fired.  The call
+    returns when the slab is complete in host memory; it only touches `side_stream`, the library's copy streams
+    and host threads, so the caller's compute stream keeps running the next slab meanwhile."""
+    torch = _torch()
+    torch.cuda.set_device(ctx.device)
+    side_stream.wait_event(ready_event)
+    nthreads = HOST_WIDEN_THREADS if nthreads is None else int(nthreads)
+    stage = torch.empty(max(cnt, 1), dtype=torch.uint8, pin_memory=True)
+    lut = np.ascontiguousarray(lut, dtype=np.float64)
+    _lib.check(ctx.lib.psb200_expand_idx_f64_to_host(
+        ctx.handle, ctypes.c_void_p(idx.data_ptr() + off), lut.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(lut),
+        ctypes.c_void_p(host.data_ptr() + 8 * host_off), cnt, ctypes.c_void_p(stage.data_ptr()), stage.numel(),
+        ptr(ws), ws.numel(), HOST_WIDEN_PERMILLE, nthreads, 0, ctypes.c_void_p(side_stream.cuda_stream)))
+    del stage
+
+
 def to_device_u8(arr, ctx, positive=False):
     """Host array or torch tensor -> contiguous uint8 device tensor whose non-zero bytes mark the
     foreground (the kernels test `byte != 0`, so bool / uint8 data is passed through as is).

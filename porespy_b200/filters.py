@@ -37,6 +37,52 @@ def _result_for_no_background(shape, radii):
     return out
 
 
+# numpy results of large 3-D volumes without access limitation: the radius loop runs z-slab by z-slab (halo = the
+# largest reach, so every slab is exact on its own -- DESIGN.md lemma i) and the host epilogue of a finished slab
+# (index bytes over PCIe, widened to float64 by host threads: 8 B/voxel of host-memory writes, the longest leg of
+# the numpy -> numpy call) overlaps the kernels of the next one.
+SLAB_PIPELINE = {"min_voxels": 1 << 28, "slabs": 6, "enabled": True}
+
+
+def _slab_plan(shape3_, T):
+    """[(z0, z1, e0, e1)] -- own planes and extended planes of every slab -- or None when slabs do not pay."""
+    nz, ny, nx = shape3_
+    cfg = SLAB_PIPELINE
+    if not cfg["enabled"] or nz * ny * nx < cfg["min_voxels"] or len(T) == 0 or len(T) > _lib.MAX_THRESHOLDS:
+        return None
+    W = host.isqrt(int(T[0]) - 1)                       # thresholds descend: the first radius reaches farthest
+    nslabs = int(cfg["slabs"])
+    if nslabs < 2 or nz // nslabs < 2 * W + 1:          # halo work above the slab's own
+        return None
+    cuts = [(nz * i) // nslabs for i in range(nslabs + 1)]
+    return [(z0, z1, max(0, z0 - W), min(nz, z1 + W)) for z0, z1 in zip(cuts[:-1], cuts[1:])]
+
+
+def _run_loop_slabs(ctx, d2, shape, T, R, plan):
+    from concurrent.futures import ThreadPoolExecutor
+    torch = dev._torch()
+    nz, ny, nx = host.shape3(shape)
+    plane = ny * nx
+    n = nz * plane
+    lut = np.concatenate([[0.0], R])
+    out = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    side = torch.cuda.Stream(device=d2.device)
+    ws = torch.empty(2 * (1 << 22) * 8 + 256, dtype=torch.uint8, device=d2.device)       # epilogue's own device chunks
+    comp = torch.cuda.current_stream()
+    with ThreadPoolExecutor(max_workers=1) as pool:      # one epilogue at a time: each uses every host thread
+        jobs = []
+        for z0, z1, e0, e1 in plan:
+            idx = torch.empty((e1 - e0) * plane, dtype=torch.uint8, device=d2.device)
+            dev.local_thickness_idx(ctx, d2[e0 * plane:e1 * plane], T, idx, None, _lib.INLETS_NONE, 3, (e1 - e0, ny, nx), 0)
+            ready = torch.cuda.Event()
+            ready.record(comp)
+            jobs.append(pool.submit(dev.expand_idx_slice_to_host, ctx, idx, (z0 - e0) * plane, (z1 - z0) * plane, lut,
+                                    out, z0 * plane, ready, side, ws))
+        for j in jobs:
+            j.result()
+    return out.numpy().reshape(shape)
+
+
 def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True, as_index=False):
     """Device loop over the effective thresholds (in groups of <= 253) -> float64 radius map, or with
     `as_index` the map in index form (sizemap.IndexMap: index byte per voxel + radius table)."""
@@ -51,6 +97,11 @@ def _run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=True, 
             dev.local_thickness_idx(ctx, d2, T, idx, inlets_u8, inlet_mode, ndim, shape, 0)
             return IndexMap(ctx, idx, np.concatenate([[0.0], R]), shape)
         return IndexMap.from_array(_run_loop(ctx, d2, shape, ndim, T, R, inlets_u8, inlet_mode, as_numpy=False), ctx)
+    if ngroups == 1 and as_numpy and inlet_mode == _lib.INLETS_NONE and ndim == 3:
+        plan = _slab_plan(host.shape3(shape), T)
+        if plan is not None:
+            del idx
+            return _run_loop_slabs(ctx, d2, shape, T, R, plan)
     if ngroups == 1 and as_numpy:
         # common case: the float64 map (F:1178) is only materialised on the host
         dev.local_thickness_idx(ctx, d2, T, idx, inlets_u8, inlet_mode, ndim, shape, 0)

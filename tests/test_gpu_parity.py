@@ -423,6 +423,27 @@ def test_flood_face_exchange_one_gpu(psb, nslabs, records):
             assert_same(got, want, f"reached seeds, inlets={inl_kind}, k={k}, T={Tk}")
 
 
+def test_slab_pipelined_numpy_result(psb):
+    """numpy -> numpy local_thickness with the radius loop run slab by slab and the host epilogue of each slab
+    overlapping the next slab's kernels (filters.SLAB_PIPELINE) equals the one-piece path and the oracle."""
+    from porespy_b200 import filters as F
+    im = oc.blobs([120, 72, 96], porosity=0.6, blobiness=1.5, seed=4)
+    saved = dict(F.SLAB_PIPELINE)
+    try:
+        F.SLAB_PIPELINE.update(enabled=False)
+        whole = psb.filters.local_thickness(im, sizes=12)
+        for slabs in (2, 3, 4):
+            F.SLAB_PIPELINE.update(enabled=True, min_voxels=1, slabs=slabs)
+            assert F._slab_plan((120, 72, 96), [50, 20, 5]) is not None
+            got = psb.filters.local_thickness(im, sizes=12)
+            assert got.dtype == np.float64 and got.shape == im.shape
+            assert_same(got, whole, f"{slabs} slabs vs one piece")
+        assert_same(whole, oc.local_thickness_c(im, sizes=12), "vs oracle")
+    finally:
+        F.SLAB_PIPELINE.clear()
+        F.SLAB_PIPELINE.update(saved)
+
+
 def test_shard_halo_helpers(psb):
     """psb200_mask_pack_u8 / psb200_mask_unpack_u8 (EDT halo planes as bits) and psb200_lt_halo_cone (one plane of cone
     values per face instead of W planes of reach bytes) against numpy."""
