@@ -228,6 +228,15 @@ int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t *inlets, ui
                  int conn, int64_t nz, int64_t ny, int64_t nx,
                  void *ws, size_t ws_bytes, psb200_stream stream);
 
+/* The same flood for NESTED sets (steps 0 .. nsteps-1): cls[v] = first step at which voxel v is a node (254: never,
+ * 255: not a node); rcls[v] = first step at which it is a node connected to the inlets (>= cls[v]; 254 never, 255
+ * where cls is 255).  Inlet voxels are nodes from step 0 on (trim_disconnected_blobs, F:1265).  One time-ordered
+ * union pass with join times replaces one flood per step: drainage's pressure loop `simulations/_drainage.py:133-154`.
+ * Workspace: psb200_flood_workspace_bytes(). */
+int psb200_flood_classes(psb200_ctx *ctx, const uint8_t *cls, const uint8_t *inlets, uint8_t *rcls, int nsteps,
+                         int conn, int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
+                         psb200_stream stream);
+
 /* Device-side bit packing of a 0 / non-zero byte mask and its inverse (0 / 1 bytes): bits[i] bit j = (src[8 i + j] != 0).
  * The z-slab shards exchange their EDT input halo planes in this form (an eighth of the bytes).  dst: 8-byte aligned. */
 int psb200_mask_pack_u8(psb200_ctx *ctx, const uint8_t *src, uint8_t *bits, int64_t n, psb200_stream stream);
@@ -375,6 +384,16 @@ int psb200_drain_threshold(psb200_ctx *ctx, const float *dt, const uint8_t *im, 
                            double rho_g, int prec_flags, double p, uint8_t *temp, psb200_stream stream);
 int psb200_drain_newly(psb200_ctx *ctx, const uint8_t *reached, const uint8_t *mask, uint8_t *seeds, const float *dt,
                        uint16_t *rad, int64_t n, uint64_t *count_dev, int *maxr_dev, psb200_stream stream);
+/* Ascending pressures: every step from ONE flood.  psb200_drain_classify: cls[v] = first step k whose set
+ * (fn <= ps[k]) * im [+ residual] holds v (254 never, 255 outside im and residual); psb200_flood_classes gives the
+ * first step at which v is invaded; psb200_drain_newly_rcls is psb200_drain_newly for step k from that map
+ * (newly = (rcls == k) [* mask]). */
+int psb200_drain_classify(psb200_ctx *ctx, const float *dt, const uint8_t *im, const double *pc_user,
+                          const uint8_t *residual, int64_t n, int64_t inner, double c0, double voxel_size,
+                          double rho_g, int prec_flags, const double *ps_host, int np, uint8_t *cls,
+                          psb200_stream stream);
+int psb200_drain_newly_rcls(psb200_ctx *ctx, const uint8_t *rcls, int k, const uint8_t *mask, const float *dt,
+                            uint16_t *rad, int64_t n, uint64_t *count_dev, int *maxr_dev, psb200_stream stream);
 size_t psb200_drain_paint_workspace_bytes(const psb200_ctx *ctx, int64_t nz, int64_t ny, int64_t nx);
 int psb200_drain_paint(psb200_ctx *ctx, const uint16_t *rad, int rmax, uint8_t *inv, int val, int64_t nz, int64_t ny,
                        int64_t nx, void *ws, size_t ws_bytes, psb200_stream stream);

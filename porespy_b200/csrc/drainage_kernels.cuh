@@ -93,6 +93,60 @@ drain_threshold_kernel(const float *__restrict__ dt, const uint8_t *__restrict__
     }
 }
 
+// All pressure steps at once (ascending pressures: the sets (fn <= p_k) * im [+ residual] are nested): the class of a
+// voxel is the first step k at which it belongs to the set (254: never, 255: not a node).  One flood over the
+// classes (psb200_flood_classes: union-find with join times) then replaces the flood of every step.
+struct DrainPs { double p[254]; };
+__global__ void __launch_bounds__(256)
+drain_classify_kernel(const float *__restrict__ dt, const uint8_t *__restrict__ im, const double *__restrict__ pc_user,
+                      const uint8_t *__restrict__ residual, int64_t n, const __grid_constant__ DrainFn q,
+                      const __grid_constant__ DrainPs ps, int np, uint8_t *__restrict__ cls)
+{
+    __shared__ double sp[254];
+    for (int i = threadIdx.x; i < np; i += blockDim.x) sp[i] = ps.p[i];
+    __syncthreads();
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += step) {
+        const bool pore = im[v] != 0;
+        uint32_t c = 255u;
+        if (residual && residual[v]) c = 0u;                       // temp = ... + residual: a node at every step
+        else if (pore) {
+            const double f = drain_fn_at(q, dt[v], pore, pc_user, v);
+            // first k with f <= p_k (p ascending): binary search; NaN compares false everywhere -> never
+            int lo = 0, hi = np;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (f <= sp[mid]) hi = mid; else lo = mid + 1;
+            }
+            c = lo < np ? (uint32_t)lo : 254u;
+        }
+        cls[v] = (uint8_t)c;
+    }
+}
+
+// step k of the loop from the flood of all steps: newly = (rcls == k) [* mask]; rad = int(dt) there, else 0
+__global__ void __launch_bounds__(256)
+drain_newly_rcls_kernel(const uint8_t *__restrict__ rcls, int k, const uint8_t *__restrict__ mask,
+                        const float *__restrict__ dt, uint16_t *__restrict__ rad, int64_t n, unsigned long long *__restrict__ count,
+                        int *__restrict__ maxr)
+{
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long c = 0;
+    int m = 0;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += step) {
+        uint32_t r = 0;
+        if ((int)rcls[v] == k && (!mask || mask[v] != 0)) {
+            r = (uint32_t)min((int)dt[v], 65535);
+            ++c;
+            m = max(m, (int)r);
+        }
+        rad[v] = (uint16_t)r;
+    }
+    c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c);
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if (lane_id() == 0 && c) { atomicAdd(count, c); atomicMax(maxr, m); }
+}
+
 // new_seeds = reached [* mask]; newly = new_seeds & ~seeds; seeds |= new_seeds; rad = int(dt) at newly voxels
 // (F:142-152).  stats[0] += number of newly invaded voxels, stats[1] = max radius among them.
 __global__ void __launch_bounds__(256)

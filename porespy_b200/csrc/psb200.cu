@@ -1974,6 +1974,75 @@ extern "C" int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t 
     return PSB200_OK;
 }
 
+// Flood of nested sets: cls[v] = first step at which voxel v is a node (254: never, 255: not a node), rcls[v] = first
+// step at which it is a node connected to the inlets (inlet voxels are nodes from step 0 on, F:1265).  The machinery of
+// the access-limited radius loop (join times) for any caller whose per-step masks are nested: drainage's pressure
+// steps (simulations/_drainage.py:133-154).
+extern "C" int psb200_flood_classes(psb200_ctx *ctx, const uint8_t *cls, const uint8_t *inlets, uint8_t *rcls, int nsteps,
+                                    int conn, int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
+                                    psb200_stream stream)
+{
+    if (!ctx || !cls || !inlets || !rcls) return fail(PSB200_ERR_INVALID, "flood_classes: NULL argument");
+    int rc = check_dims("flood_classes", nz, ny, nx);
+    if (rc) return rc;
+    if (nsteps < 1 || nsteps > UF_NTIMES) return fail(PSB200_ERR_INVALID, "flood_classes: 1..254 steps, got %d", nsteps);
+    int c3;
+    if (conn == 6 || conn == 4) c3 = 6;
+    else if (conn == 26 || conn == 8) c3 = 26;
+    else return fail(PSB200_ERR_INVALID, "flood_classes: conn must be 4/8 (2-D) or 6/26 (3-D), got %d", conn);
+    if ((conn == 4 || conn == 8) && nz != 1)
+        return fail(PSB200_ERR_INVALID, "flood_classes: conn %d is 2-D connectivity but nz=%lld", conn, (long long)nz);
+    const int64_t n = nz * ny * nx;
+    if (n > 0xFFFFFFF0LL) return fail(PSB200_ERR_UNSUPPORTED, "flood_classes supports < 2^32 voxels per GPU");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    psb200_ctx tmp = *ctx;
+    tmp.algo = PSB200_ALGO_FAST;
+    char *base = ws ? (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
+    LtWorkspace w = carve_lt(&tmp, base, nz, ny, nx, PSB200_INLETS_MASK);
+    if (!ws || w.total + 256 > ws_bytes)
+        return fail(PSB200_ERR_WORKSPACE, "flood_classes needs %zu workspace bytes, got %zu", w.total + 256, ws_bytes);
+    InletSpec inl{PSB200_INLETS_MASK, 3, inlets, 0, (int)nz};
+    uint8_t *jtime = w.reach, *acls = w.rcls;
+    int *kmin = w.gate + 1;
+    CUDA_TRY(cudaMemsetAsync(kmin, 0x7F, sizeof(int), st));
+    const uint32_t *start = nullptr;
+    bool fits = false;
+    if (ctx->uf_records) {
+        rc = uf_forest_impl(ctx, w, inl, cls, acls, jtime, c3, nz, ny, nx, st, &start, &fits);
+        if (rc) return rc;
+    }
+    if (fits) {
+        for (int k = 0; k < nsteps; ++k) {
+            rc = uf_union_records(ctx, w, start, k, c3, ny, nx, jtime, st);
+            if (rc) return rc;
+        }
+        {
+            ProfScope ps__(ctx, st, K_UF_MARK);
+            uf_compress_kernel<<<ctx->sm_count * 6, 256, 0, st>>>(w.parent, acls, (int)nz, (int)ny, (int)nx);
+        }
+        LAUNCH_CHECK(ctx);
+    } else {
+        // per-voxel job lists (record overflow with 26-connectivity, or the option switched off)
+        {
+            ProfScope ps__(ctx, st, K_UF_INIT);
+            uf_init_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(w.parent, inl, (int)nz, (int)ny, (int)nx, jtime, cls, acls);
+        }
+        LAUNCH_CHECK(ctx);
+        const InletSpec folded{3, 3, nullptr, 0, (int)nz};
+        for (int k = 0; k < nsteps; ++k) {
+            rc = uf_activate_impl(ctx, w.parent, acls, folded, k - 1, k, c3, nz, ny, nx, w.uf_list, st, jtime);
+            if (rc) return rc;
+        }
+    }
+    {
+        ProfScope ps__(ctx, st, K_UF_MARK);
+        uf_resolve_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(w.parent, cls, jtime, rcls, n, kmin);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
 // ------------------------------------------------------------------------- blobs generator
 // (blobs_kernels.cuh; reference generators/_imgen.py:1023-1051, tools/_funcs.py:963-969)
 extern "C" int psb200_noise_philox_f64(psb200_ctx *ctx, double *out, int64_t n, uint64_t seed, uint64_t first,
@@ -2264,6 +2333,46 @@ extern "C" int psb200_drain_newly(psb200_ctx *ctx, const uint8_t *reached, const
         ProfScope ps__(ctx, st, K_DRAIN);
         drain_newly_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(
             reached, mask, seeds, dt, rad, n, reinterpret_cast<unsigned long long *>(count_dev), maxr_dev);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_drain_classify(psb200_ctx *ctx, const float *dt, const uint8_t *im, const double *pc_user,
+                                     const uint8_t *residual, int64_t n, int64_t inner, double c0, double voxel_size,
+                                     double rho_g, int prec_flags, const double *ps_host, int np, uint8_t *cls,
+                                     psb200_stream stream)
+{
+    if (!ctx || !dt || !im || !cls || !ps_host || n < 1 || inner < 1 || np < 1 || np > 254)
+        return fail(PSB200_ERR_INVALID, "drain_classify: bad argument");
+    for (int i = 1; i < np; ++i)
+        if (!(ps_host[i] >= ps_host[i - 1])) return fail(PSB200_ERR_INVALID, "drain_classify: pressures must ascend");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DrainFn q = make_drain_fn(c0, voxel_size, rho_g, prec_flags, inner, pc_user != nullptr);
+    DrainPs ps;
+    for (int i = 0; i < 254; ++i) ps.p[i] = i < np ? ps_host[i] : 0.0;
+    {
+        ProfScope ps__(ctx, st, K_DRAIN);
+        drain_classify_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(dt, im, pc_user, residual, n, q, ps, np, cls);
+    }
+    LAUNCH_CHECK(ctx);
+    return PSB200_OK;
+}
+
+extern "C" int psb200_drain_newly_rcls(psb200_ctx *ctx, const uint8_t *rcls, int k, const uint8_t *mask, const float *dt,
+                                       uint16_t *rad, int64_t n, uint64_t *count_dev, int *maxr_dev, psb200_stream stream)
+{
+    if (!ctx || !rcls || !dt || !rad || !count_dev || !maxr_dev || n < 1 || k < 0 || k > 253)
+        return fail(PSB200_ERR_INVALID, "drain_newly_rcls: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(count_dev, 0, sizeof(uint64_t), st));
+    CUDA_TRY(cudaMemsetAsync(maxr_dev, 0, sizeof(int), st));
+    {
+        ProfScope ps__(ctx, st, K_DRAIN);
+        drain_newly_rcls_kernel<<<grid_for(n, 256, ctx->sm_count, 16), 256, 0, st>>>(
+            rcls, k, mask, dt, rad, n, reinterpret_cast<unsigned long long *>(count_dev), maxr_dev);
     }
     LAUNCH_CHECK(ctx);
     return PSB200_OK;

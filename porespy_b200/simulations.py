@@ -22,6 +22,7 @@ from .sizemap import IndexMap, Results
 __all__ = ["drainage"]
 
 MAX_PRESSURES = 250
+ONE_FLOOD = True          # ascending pressures: one flood with join times for all steps (False: one flood per step)
 
 
 def _fn_args(ndim, voxel_size, delta_rho, g, sigma, theta, inner):
@@ -94,18 +95,37 @@ def drainage(im, voxel_size, pc=None, inlets=None, outlets=None, residual=None, 
     if (residual is not None) and (outlets is not None):                            # F:129-132
         mask_d = flood(im_u8 * (1 - res_d))
     inv = torch.zeros(n, dtype=torch.uint8, device=device)
-    seeds = torch.zeros(n, dtype=torch.uint8, device=device)
-    temp = torch.empty(n, dtype=torch.uint8, device=device)
     rad = torch.empty(n, dtype=torch.int16, device=device)
     stats = torch.zeros(4, dtype=torch.int64, device=device)                        # [count (u64), max radius (int)]
     pws = ctx.lib.psb200_drain_paint_workspace_bytes(h_, *shape3)
+    # Ascending pressures (the default bins, and any sorted user list): the sets (fn <= p) * im [+ residual] are
+    # nested, so the first step at which every voxel is invaded comes from ONE flood with join times
+    # (psb200_flood_classes) instead of one flood per step; otherwise the reference's loop step by step.
+    pf = np.asarray([float(p) for p in Ps], dtype=np.float64)
+    nested = ONE_FLOOD and len(pf) <= 253 and not np.isnan(pf).any() and bool(np.all(np.diff(pf) >= 0))
+    rcls = None
+    if nested:
+        cls = torch.empty(n, dtype=torch.uint8, device=device)
+        _lib.check(lib.psb200_drain_classify(h_, dev.ptr(dt), dev.ptr(im_u8), dev.ptr(pc_d), dev.ptr(res_d), *fnargs,
+                                             pf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(pf), dev.ptr(cls),
+                                             dev.stream_ptr()))
+        rcls = dev.flood_classes(ctx, cls, inl_d, len(pf), conn, shape3)
+        del cls
+    else:
+        seeds = torch.zeros(n, dtype=torch.uint8, device=device)
+        temp = torch.empty(n, dtype=torch.uint8, device=device)
     for k, p in enumerate(Ps):                                                      # F:133-154
-        _lib.check(lib.psb200_drain_threshold(h_, dev.ptr(dt), dev.ptr(im_u8), dev.ptr(pc_d), dev.ptr(res_d), *fnargs,
-                                              float(p), dev.ptr(temp), dev.stream_ptr()))
-        reached = flood(temp)
-        _lib.check(lib.psb200_drain_newly(h_, dev.ptr(reached), dev.ptr(mask_d), dev.ptr(seeds), dev.ptr(dt), dev.ptr(rad), n,
-                                          ctypes.c_void_p(stats.data_ptr()), ctypes.c_void_p(stats.data_ptr() + 8),
-                                          dev.stream_ptr()))
+        if nested:
+            _lib.check(lib.psb200_drain_newly_rcls(h_, dev.ptr(rcls), k, dev.ptr(mask_d), dev.ptr(dt), dev.ptr(rad), n,
+                                                   ctypes.c_void_p(stats.data_ptr()), ctypes.c_void_p(stats.data_ptr() + 8),
+                                                   dev.stream_ptr()))
+        else:
+            _lib.check(lib.psb200_drain_threshold(h_, dev.ptr(dt), dev.ptr(im_u8), dev.ptr(pc_d), dev.ptr(res_d), *fnargs,
+                                                  float(p), dev.ptr(temp), dev.stream_ptr()))
+            reached = flood(temp)
+            _lib.check(lib.psb200_drain_newly(h_, dev.ptr(reached), dev.ptr(mask_d), dev.ptr(seeds), dev.ptr(dt), dev.ptr(rad), n,
+                                              ctypes.c_void_p(stats.data_ptr()), ctypes.c_void_p(stats.data_ptr() + 8),
+                                              dev.stream_ptr()))
         st = stats.cpu().numpy()
         count, rmax = int(st[0]), int(st[1:2].view(np.int32)[0])
         if count == 0 or rmax == 0 or float(p) == 0.0:       # (a value of 0 leaves the reference's array "unwritten")
@@ -113,7 +133,7 @@ def drainage(im, voxel_size, pc=None, inlets=None, outlets=None, residual=None, 
         ws = ctx.workspace(pws)
         _lib.check(lib.psb200_drain_paint(h_, dev.ptr(rad), rmax, dev.ptr(inv), k + 1, *shape3, dev.ptr(ws), ws.numel(),
                                           dev.stream_ptr()))
-    del temp, rad, seeds
+    del rad, rcls
 
     # ---- epilogue on the code map: values[code] is the invasion pressure
     nP = len(Ps)

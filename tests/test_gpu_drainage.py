@@ -10,12 +10,17 @@ from oracle import cpu as oc                       # noqa: E402  (checker only)
 from tests.test_gpu_parity import assert_same      # noqa: E402
 
 
-@pytest.fixture(scope="module")
-def psb():
+@pytest.fixture(scope="module", params=["one_flood", "flood_per_step"])
+def psb(request):
+    """Both forms of the pressure loop: one flood with join times for all (ascending) steps, and one flood per step."""
     import torch
     assert torch.cuda.is_available()
     import porespy_b200 as psb
-    return psb
+    from porespy_b200 import simulations
+    saved = simulations.ONE_FLOOD
+    simulations.ONE_FLOOD = request.param == "one_flood"
+    yield psb
+    simulations.ONE_FLOOD = saved
 
 
 def same(r, want, name):
@@ -72,3 +77,34 @@ def test_vs_numpy_restatement(psb, shape, seed):
     out[-1] = True
     for kw in (dict(), dict(outlets=out, bins=12), dict(g=0, bins=9, sigma=0.03)):
         same(psb.simulations.drainage(im=im, voxel_size=2e-5, **kw), oc.drainage(im, 2e-5, **kw), f"{shape} {sorted(kw)}")
+
+
+@pytest.mark.parametrize("conn", [6, 26])
+def test_flood_classes_vs_labelling(conn):
+    """psb200_flood_classes: first step at which a voxel of nested sets is connected to the inlets, against one
+    scipy labelling per step (inlet voxels are nodes from step 0 on, F:1265)."""
+    import scipy.ndimage as spim
+    import torch
+    from porespy_b200 import _device as dev
+    from porespy_b200 import _lib
+    ctx = _lib.context()
+    rng = np.random.default_rng(7)
+    for shape, nsteps in (((24, 30, 140), 6), ((1, 60, 131), 4), ((9, 11, 13), 9)):
+        sm = spim.gaussian_filter(rng.random(shape), 2.0)
+        cls = np.clip(((sm - sm.min()) / np.ptp(sm) * (nsteps + 2)).astype(int), 0, nsteps + 1)
+        cls = np.where(cls >= nsteps, 254, cls)
+        cls = np.where(rng.random(shape) < 0.25, 255, cls).astype(np.uint8)
+        inl = np.zeros(shape, dtype=bool)
+        inl[..., 0] = True
+        inl |= rng.random(shape) < 0.001
+        c = conn if shape[0] > 1 else (4 if conn == 6 else 8)
+        got = dev.flood_classes(ctx, torch.from_numpy(cls.reshape(-1)).cuda(), torch.from_numpy(inl.reshape(-1).view(np.uint8)).cuda(),
+                                nsteps, c, shape).cpu().numpy().reshape(shape)
+        st = spim.generate_binary_structure(3, 1 if conn == 6 else 3)
+        want = np.where(cls == 255, 255, 254).astype(np.uint8)
+        for k in range(nsteps - 1, -1, -1):
+            nodes = (cls <= k) | inl
+            lab = spim.label(nodes, structure=st)[0]
+            keep = np.unique(lab[inl])
+            want[np.isin(lab, keep[keep > 0]) & (cls <= k)] = k
+        assert np.array_equal(got, want), (shape, conn, np.argwhere(got != want)[:5])
