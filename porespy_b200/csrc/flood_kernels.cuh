@@ -606,10 +606,11 @@ flood_out_kernel(const uint8_t *__restrict__ rcls, uint8_t *__restrict__ out, in
 //    connected through that one; so one union per interval BORN at k suffices:  the pairs with
 //    m(x - 1) > m(x) <= m(x + 1), i.e. the local minima of m along x.
 //
-// uf_links_kernel counts those records per (radius index, direction), uf_scan_bins_kernel turns the
-// counts into slice starts, a second uf_links_kernel pass writes the voxel ids, and radius k runs
-// uf_union_rec_kernel over its slice: about 0.1 unions per voxel for all radii together instead of
-// 6 (26) jobs per voxel.
+// uf_emit_kernel writes those records (and counts them per radius index and direction), uf_scan_bins_kernel turns
+// the counts into slice starts, uf_sort_kernel moves the records into their slices, and radius k runs
+// uf_union_rec_kernel over its slice: about 0.2 unions per voxel for all radii together instead of 6 (26) jobs
+// per voxel.  (Two records per thread and iteration, to have twice the loads in flight, changed nothing: the union
+// launches are bound by DRAM sector throughput on random 32-byte accesses, not by latency -- r3i.)
 #define UF_SEGX 128          // a warp owns a segment: 4 consecutive voxels per lane, chains do not cross segments
 #define UF_CHUNK 256         // segments per list reservation of the scatter pass
 #define UF_MAXFAM 13
