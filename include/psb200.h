@@ -230,11 +230,13 @@ int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t *inlets, ui
 
 /* The same flood for NESTED sets (steps 0 .. nsteps-1): cls[v] = first step at which voxel v is a node (254: never,
  * 255: not a node); rcls[v] = first step at which it is a node connected to the inlets (>= cls[v]; 254 never, 255
- * where cls is 255).  Inlet voxels are nodes from step 0 on (trim_disconnected_blobs, F:1265).  One time-ordered
- * union pass with join times replaces one flood per step: drainage's pressure loop `simulations/_drainage.py:133-154`.
+ * where cls is 255).  inlets_in_set = 0: inlet voxels are nodes from step 0 on (trim_disconnected_blobs, F:1265);
+ * 1: an inlet voxel only counts from its own step on (find_trapped_regions looks the outlets up inside the labelled
+ * set `seq >= i`, F:131-137).  One time-ordered union pass with join times replaces one flood per step: drainage's
+ * pressure loop `simulations/_drainage.py:133-154`, find_trapped_regions' bin loop `filters/_funcs.py:131-137`.
  * Workspace: psb200_flood_workspace_bytes(). */
-int psb200_flood_classes(psb200_ctx *ctx, const uint8_t *cls, const uint8_t *inlets, uint8_t *rcls, int nsteps,
-                         int conn, int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
+int psb200_flood_classes(psb200_ctx *ctx, const uint8_t *cls, const uint8_t *inlets, int inlets_in_set, uint8_t *rcls,
+                         int nsteps, int conn, int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
                          psb200_stream stream);
 
 /* Device-side bit packing of a 0 / non-zero byte mask and its inverse (0 / 1 bytes): bits[i] bit j = (src[8 i + j] != 0).

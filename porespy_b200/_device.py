@@ -219,13 +219,14 @@ def mark_written(ctx, out, idx):
     _lib.check(ctx.lib.psb200_mark_written(ctx.handle, ptr(out), ptr(idx), idx.numel(), stream_ptr()))
 
 
-def flood_classes(ctx, cls_u8, inlets_u8, nsteps, conn, shape):
-    """Nested-set flood (psb200_flood_classes): first step at which every voxel is a node connected to the inlets."""
+def flood_classes(ctx, cls_u8, inlets_u8, nsteps, conn, shape, inlets_in_set=False):
+    """Nested-set flood (psb200_flood_classes): first step at which every voxel is a node connected to the inlets.
+    `inlets_in_set`: an inlet voxel only counts from the step at which it joins the set."""
     torch = _torch()
     nz, ny, nx = shape3(shape)
     out = torch.empty(nz * ny * nx, dtype=torch.uint8, device=cls_u8.device)
     ws = ctx.workspace(ctx.lib.psb200_flood_workspace_bytes(ctx.handle, nz, ny, nx))
-    _lib.check(ctx.lib.psb200_flood_classes(ctx.handle, ptr(cls_u8), ptr(inlets_u8), ptr(out), int(nsteps), conn,
+    _lib.check(ctx.lib.psb200_flood_classes(ctx.handle, ptr(cls_u8), ptr(inlets_u8), 1 if inlets_in_set else 0, ptr(out), int(nsteps), conn,
                                             nz, ny, nx, ptr(ws), ws.numel(), stream_ptr()))
     return out
 

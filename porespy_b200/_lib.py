@@ -122,7 +122,7 @@ SIGNATURES = {
     "psb200_drain_classify": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _c.c_double, _c.c_double, _c.c_double, _i32,
                                      _vp, _i32, _vp, _vp]),
     "psb200_drain_newly_rcls": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
-    "psb200_flood_classes": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "psb200_flood_classes": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_drain_paint_workspace_bytes": (_sz, [_vp, _i64, _i64, _i64]),
     "psb200_drain_paint": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
     "psb200_set_where_u8": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp]),

@@ -28,7 +28,8 @@
 #define UF_TIME_UNSET 0xFFu   // jtime of a node that never hung directly under node 0
 
 struct InletSpec {
-    int mode;                 // 1 = faces predicate, 2 = mask, 3 = none (already folded into the class map)
+    int mode;                 // 1 = faces predicate, 2 = mask, 3 = none (already folded into the class map),
+                              // 4 = mask, but a voxel only acts as an inlet from its own class on (not a node before)
     int ndim;                 // dimensionality of the squeezed image (faces predicate)
     const uint8_t *mask;      // mode 2 (the local slab of the mask)
     int z0, nzg;              // z-slab shard: local plane z is global plane z + z0 of nzg planes
@@ -37,7 +38,7 @@ struct InletSpec {
 __device__ __forceinline__ bool is_inlet(const InletSpec &s, int64_t v, int z, int y, int x,
                                          int nz, int ny, int nx)
 {
-    if (s.mode == 2) return s.mask[v] != 0;
+    if (s.mode == 2 || s.mode == 4) return s.mask[v] != 0;      // (mode 4: callers test the voxel's class as well)
     if (s.mode == 3) return false;          // inlets are folded into the class map (class 0), see uf_init_kernel
     // get_border(shape, mode='faces') (generators/_borders.py:93-100); ndim 1: all True
     if (s.ndim >= 3) return z + s.z0 == 0 || z + s.z0 == s.nzg - 1 || y == 0 || y == ny - 1 || x == 0 || x == nx - 1;
@@ -108,12 +109,14 @@ uf_init_kernel(uint32_t *__restrict__ parent, InletSpec inl, int nz, int ny, int
         const int x = (int)(v % nx);
         const int64_t t = v / nx;
         const int y = (int)(t % ny), z = (int)(t / ny);
-        const bool in = is_inlet(inl, v, z, y, x, nz, ny, nx);
+        bool in = is_inlet(inl, v, z, y, x, nz, ny, nx);
+        if (inl.mode == 4) in = in && cls && cls[v] < CLS_NEVER;
         parent[v + 1] = in ? 0u : (uint32_t)(v + 1);
         if (jtime) jtime[v + 1] = in ? 0 : UF_TIME_UNSET;
         // activation map: an inlet voxel is a graph node from the first radius on, whatever its class
-        // (F:1265), so the link kernels need neither the inlet predicate nor the inlet mask
-        if (acls) acls[v] = in ? 0 : cls[v];
+        // (F:1265), so the link kernels need neither the inlet predicate nor the inlet mask.  Mode 4: it keeps
+        // its class (a node from then on; hanging under node 0 from the start is harmless, nothing finds it earlier)
+        if (acls) acls[v] = (in && inl.mode != 4) ? 0 : cls[v];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) parent[0] = 0u;
 }
@@ -625,7 +628,7 @@ __constant__ int8_t c_uf_fam[UF_MAXFAM][3] = {{0, 0, 1},  {0, 1, 0},  {1, 0, 0},
 __device__ __forceinline__ uint32_t uf_inlet_bits(const InletSpec &inl, int64_t rb, int z, int y, int x, int nz, int ny, int nx)
 {
     uint32_t bits = 0;
-    if (inl.mode == 2) {
+    if (inl.mode == 2 || inl.mode == 4) {
         const uint32_t m = load4(inl.mask + rb, x, nx, 0u);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -658,9 +661,16 @@ uf_prelink_kernel(const uint8_t *__restrict__ cls, InletSpec inl, int nz, int ny
         if (x < nx) {
             a = load4(cls + rb, x, nx, 255u);
             inb = uf_inlet_bits(inl, rb, z, y, x, nz, ny, nx);
+            if (inl.mode == 4) {
+                // inlets only from their own class on: the class stays, voxels without a class are no inlets
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (inb >> j & 1u) a &= ~(0xFFu << (8 * j));
+                for (int j = 0; j < 4; ++j)
+                    if (byte_of(a, j) >= CLS_NEVER) inb &= ~(1u << j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (inb >> j & 1u) a &= ~(0xFFu << (8 * j));
+            }
             if (acls) store4(acls + rb, x, nx, a);
         }
         uint32_t lft = __shfl_up_sync(FULL, a, 1) >> 24, rgt = __shfl_down_sync(FULL, a, 1) & 0xFFu;
@@ -830,16 +840,18 @@ uf_emit_kernel(const uint8_t *__restrict__ acls, InletSpec inl, int nz, int ny, 
                 const uint32_t le = __vcmpleu4(C, Ap1);
                 const uint32_t left_ok = __vcmpleu4(Am1, C) & notfirst;
                 covered = sameseg & (le | (~left_ok & ~le));
-                const uint32_t zero = (__vcmpeq4(C, 0u) | __vcmpeq4(Ap1, 0u)) & pair;
+                // class 0 may be an inlet (parent = node 0, never pre-linked): the exact rule, voxel by voxel; with
+                // inlets that keep their class (mode 4) any voxel may be one
+                const bool any_class = inl.mode == 4;
+                const uint32_t zero = any_class ? pair : (__vcmpeq4(C, 0u) | __vcmpeq4(Ap1, 0u)) & pair;
                 if (zero) {
-                    // class 0 may be an inlet (parent = node 0, never pre-linked): the exact rule, voxel by voxel
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (!byte_of(zero, j)) continue;
                         const uint32_t ax = byte_of(C, j), ar = byte_of(Ap1, j);
                         const int xx = x + j;
-                        const bool inx = ax == 0 && is_inlet(inl, rb + xx, z, y, xx, nz, ny, nx);
-                        const bool inr = ar == 0 && is_inlet(inl, rb + xx + 1, z, y, xx + 1, nz, ny, nx);
+                        const bool inx = (any_class || ax == 0) && is_inlet(inl, rb + xx, z, y, xx, nz, ny, nx);
+                        const bool inr = (any_class || ar == 0) && is_inlet(inl, rb + xx + 1, z, y, xx + 1, nz, ny, nx);
                         bool cov = inx && inr;
                         if (!cov && !(lane == 31 && j == 3)) {
                             const bool lok = !(lane == 0 && j == 0) && byte_of(Am1, j) <= ax;

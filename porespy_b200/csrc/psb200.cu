@@ -1975,12 +1975,14 @@ extern "C" int psb200_flood(psb200_ctx *ctx, const uint8_t *mask, const uint8_t 
 }
 
 // Flood of nested sets: cls[v] = first step at which voxel v is a node (254: never, 255: not a node), rcls[v] = first
-// step at which it is a node connected to the inlets (inlet voxels are nodes from step 0 on, F:1265).  The machinery of
+// step at which it is a node connected to the inlets.  inlets_in_set = 0: inlet voxels are nodes from step 0 on
+// (trim_disconnected_blobs, F:1265); 1: an inlet voxel only counts from the step at which it joins the set
+// (find_trapped_regions labels `seq >= i` and looks up the outlets inside it, F:131-137).  The machinery of
 // the access-limited radius loop (join times) for any caller whose per-step masks are nested: drainage's pressure
 // steps (simulations/_drainage.py:133-154).
-extern "C" int psb200_flood_classes(psb200_ctx *ctx, const uint8_t *cls, const uint8_t *inlets, uint8_t *rcls, int nsteps,
-                                    int conn, int64_t nz, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
-                                    psb200_stream stream)
+extern "C" int psb200_flood_classes(psb200_ctx *ctx, const uint8_t *cls, const uint8_t *inlets, int inlets_in_set,
+                                    uint8_t *rcls, int nsteps, int conn, int64_t nz, int64_t ny, int64_t nx, void *ws,
+                                    size_t ws_bytes, psb200_stream stream)
 {
     if (!ctx || !cls || !inlets || !rcls) return fail(PSB200_ERR_INVALID, "flood_classes: NULL argument");
     int rc = check_dims("flood_classes", nz, ny, nx);
@@ -2002,7 +2004,7 @@ extern "C" int psb200_flood_classes(psb200_ctx *ctx, const uint8_t *cls, const u
     LtWorkspace w = carve_lt(&tmp, base, nz, ny, nx, PSB200_INLETS_MASK);
     if (!ws || w.total + 256 > ws_bytes)
         return fail(PSB200_ERR_WORKSPACE, "flood_classes needs %zu workspace bytes, got %zu", w.total + 256, ws_bytes);
-    InletSpec inl{PSB200_INLETS_MASK, 3, inlets, 0, (int)nz};
+    InletSpec inl{inlets_in_set ? 4 : PSB200_INLETS_MASK, 3, inlets, 0, (int)nz};
     uint8_t *jtime = w.reach, *acls = w.rcls;
     int *kmin = w.gate + 1;
     CUDA_TRY(cudaMemsetAsync(kmin, 0x7F, sizeof(int), st));

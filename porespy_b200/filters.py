@@ -350,13 +350,28 @@ def trim_nonpercolating_paths(im, inlets, outlets, strel=None):
     return _mask_to_host(hit)
 
 
+ONE_FLOOD_TRAPPED = True      # find_trapped_regions: one flood with join times for all bins (False: one flood per bin)
+
+
 def _trapped_mask(ctx, shape, temp_of, bins, out_t):
     """F:131-137 on the device: for every bin value i the voxels of `temp = seq >= i` whose component (cross
     neighbourhood, scipy's default) holds no outlet voxel.  temp_of(i) -> flat uint8 device mask."""
     torch = dev._torch()
     conn = 6 if len(shape) == 3 else 4
-    trapped = torch.zeros(int(np.prod(shape)), dtype=torch.bool, device=out_t.device)
     out_flat = out_t.reshape(-1)
+    bins = list(bins)
+    if ONE_FLOOD_TRAPPED and 0 < len(bins) <= 253 and all(b1 <= b0 for b0, b1 in zip(bins[:-1], bins[1:])):
+        # descending bins: the sets `seq >= i` are nested, so ONE flood with join times gives the first bin at which
+        # every voxel is connected to an outlet voxel of its set (psb200_flood_classes, outlets counted from their own
+        # bin on); connectivity only grows with the set, so a voxel is trapped for SOME bin iff it is not connected at
+        # the first bin that holds it
+        n = int(np.prod(shape))
+        cls = torch.full((n,), 254, dtype=torch.uint8, device=out_t.device)
+        for k in range(len(bins) - 1, -1, -1):                       # smallest k wins: write from the last bin down
+            _lib.check(ctx.lib.psb200_set_where_u8(ctx.handle, dev.ptr(cls), dev.ptr(temp_of(bins[k])), k, n, dev.stream_ptr()))
+        rcls = dev.flood_classes(ctx, cls, out_flat, len(bins), conn, host.shape3(shape), inlets_in_set=True)
+        return ((cls != 254) & (rcls != cls)).view(*shape)
+    trapped = torch.zeros(int(np.prod(shape)), dtype=torch.bool, device=out_t.device)
     for i in bins:
         temp = temp_of(i)
         reached = dev.flood(ctx, temp, temp * out_flat, conn, host.shape3(shape))

@@ -109,7 +109,7 @@ def drainage(im, voxel_size, pc=None, inlets=None, outlets=None, residual=None, 
         _lib.check(lib.psb200_drain_classify(h_, dev.ptr(dt), dev.ptr(im_u8), dev.ptr(pc_d), dev.ptr(res_d), *fnargs,
                                              pf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(pf), dev.ptr(cls),
                                              dev.stream_ptr()))
-        rcls = dev.flood_classes(ctx, cls, inl_d, len(pf), conn, shape3)
+        rcls = dev.flood_classes(ctx, cls, inl_d, len(pf), conn, shape3)             # inlets: nodes from step 0 on
         del cls
     else:
         seeds = torch.zeros(n, dtype=torch.uint8, device=device)

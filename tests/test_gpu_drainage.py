@@ -16,11 +16,11 @@ def psb(request):
     import torch
     assert torch.cuda.is_available()
     import porespy_b200 as psb
-    from porespy_b200 import simulations
-    saved = simulations.ONE_FLOOD
-    simulations.ONE_FLOOD = request.param == "one_flood"
+    from porespy_b200 import filters, simulations
+    saved = simulations.ONE_FLOOD, filters.ONE_FLOOD_TRAPPED
+    simulations.ONE_FLOOD = filters.ONE_FLOOD_TRAPPED = request.param == "one_flood"
     yield psb
-    simulations.ONE_FLOOD = saved
+    simulations.ONE_FLOOD, filters.ONE_FLOOD_TRAPPED = saved
 
 
 def same(r, want, name):

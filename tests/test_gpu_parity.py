@@ -563,18 +563,35 @@ def test_flood_users(psb, golden):
                         oc.find_disconnected_voxels(r, conn=conn, surface=surface), f"random {shape} {conn} {surface}")
 
 
-def test_find_trapped_regions(psb, golden):
-    """find_trapped_regions (one device flood per bin) against the reference-generated goldens."""
+@pytest.mark.parametrize("one_flood", [True, False])
+def test_find_trapped_regions(psb, golden, one_flood):
+    """find_trapped_regions (one flood with join times for all bins / one device flood per bin) against the
+    reference-generated goldens, and against the numpy restatement on a larger random sequence."""
     from tests.test_oracle import _trapped_cases
-    g = golden.trapped
-    cases, seq2, outl = _trapped_cases(g)
-    for kw, key in cases:
-        got = psb.filters.find_trapped_regions(**kw)
-        assert got.dtype == np.bool_
-        assert_same(got, g.mask(key), key)
-    s = psb.filters.find_trapped_regions(seq2, outlets=outl, bins=None, return_mask=False)
-    assert np.array_equal(s, g.raw("s2d_outlet_seq"))
-    assert np.array_equal(seq2, g.raw("seq2d"))                 # input not modified
+    from porespy_b200 import filters as F
+    saved = F.ONE_FLOOD_TRAPPED
+    F.ONE_FLOOD_TRAPPED = one_flood
+    try:
+        g = golden.trapped
+        cases, seq2, outl = _trapped_cases(g)
+        for kw, key in cases:
+            got = psb.filters.find_trapped_regions(**kw)
+            assert got.dtype == np.bool_
+            assert_same(got, g.mask(key), key)
+        s = psb.filters.find_trapped_regions(seq2, outlets=outl, bins=None, return_mask=False)
+        assert np.array_equal(s, g.raw("s2d_outlet_seq"))
+        assert np.array_equal(seq2, g.raw("seq2d"))                 # input not modified
+        rng = np.random.default_rng(9)
+        for shape in ((40, 36, 140), (90, 131)):
+            im = oc.blobs(list(shape), porosity=0.6, blobiness=1.5, seed=3)
+            seq = (rng.integers(1, 40, shape) * im).astype(np.int64)
+            outl = np.zeros(shape, dtype=bool)
+            outl[-1] = True
+            for bins in (25, 7, None):
+                assert_same(psb.filters.find_trapped_regions(seq, outlets=outl, bins=bins),
+                            oc.find_trapped_regions(seq, outlets=outl, bins=bins), f"{shape} bins={bins}")
+    finally:
+        F.ONE_FLOOD_TRAPPED = saved
 
 
 # -------------------------------------------------------------------- round-2 additions
