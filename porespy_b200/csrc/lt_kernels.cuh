@@ -386,6 +386,7 @@ lt_zsweep_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo, 
 // The same sweeps with 8 columns per thread (one 8-byte load per plane) and 16 planes in flight: half the threads,
 // four times the bytes in flight per thread -- the sweeps are bound by memory latency and bandwidth, not by the ALU.
 #define ZS2_UNROLL 16
+#define ZS2_IDXB 8           // planes per batch of the backward sweep (reach words + index words: register budget 72)
 // 128-thread blocks, 7 per SM (<= 73 registers): the plane/8 threads of a 1024^2 plane are 1024 blocks <= 148 * 7
 __global__ void __launch_bounds__(128, 7)
 lt_zsweep8_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo, int nlo,
@@ -437,15 +438,27 @@ lt_zsweep8_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo,
         }
     };
     z = nz - 1;
-    for (; z - ZS2_UNROLL + 1 >= 0; z -= ZS2_UNROLL) {
-        uint2 v[ZS2_UNROLL];
+    for (; z - ZS2_IDXB + 1 >= 0; z -= ZS2_IDXB) {
+        // batches of ZS2_IDXB planes: the reach words, then the cone values (ALU only, in place), then the index words
+        // of the covered planes as independent loads -- a load per plane inside the dependent chain left the sweep
+        // waiting for one DRAM round trip per covered plane
+        uint2 v[ZS2_IDXB], old[ZS2_IDXB];
 #pragma unroll
-        for (int i = 0; i < ZS2_UNROLL; ++i) v[i] = col[(int64_t)(z - i) * ps];
+        for (int i = 0; i < ZS2_IDXB; ++i) v[i] = col[(int64_t)(z - i) * ps];
 #pragma unroll
-        for (int i = 0; i < ZS2_UNROLL; ++i) {
+        for (int i = 0; i < ZS2_IDXB; ++i) {
             c0 = __vmaxu4(v[i].x, __vsubus4(c0, ONE4));
             c1 = __vmaxu4(v[i].y, __vsubus4(c1, ONE4));
-            commit(z - i);
+            v[i] = make_uint2(c0, c1);
+        }
+#pragma unroll
+        for (int i = 0; i < ZS2_IDXB; ++i)
+            old[i] = (v[i].x | v[i].y) ? icol[(int64_t)(z - i) * ps] : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+#pragma unroll
+        for (int i = 0; i < ZS2_IDXB; ++i) {
+            const uint32_t m0 = __vcmpne4(v[i].x, 0u) & __vcmpeq4(old[i].x, 0u);
+            const uint32_t m1 = __vcmpne4(v[i].y, 0u) & __vcmpeq4(old[i].y, 0u);
+            if (m0 | m1) icol[(int64_t)(z - i) * ps] = make_uint2(old[i].x | (val4 & m0), old[i].y | (val4 & m1));
         }
     }
     for (; z >= 0; --z) {
