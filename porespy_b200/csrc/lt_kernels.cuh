@@ -363,14 +363,20 @@ lt_zsweep_kernel(uint8_t *__restrict__ reach, const uint8_t *__restrict__ m_lo, 
         uint32_t v[ZS_UNROLL];
 #pragma unroll
         for (int i = 0; i < ZS_UNROLL; ++i) v[i] = col[(int64_t)(z - i) * ps];
+        // cone values first (in place), then the index words of the covered planes as independent loads (see
+        // lt_zsweep8_kernel: one dependent load per covered plane left the sweep waiting for DRAM round trips)
 #pragma unroll
         for (int i = 0; i < ZS_UNROLL; ++i) {
             c = __vmaxu4(v[i], __vsubus4(c, ONE4));
-            if (c) {
-                const uint32_t old = icol[(int64_t)(z - i) * ps];
-                const uint32_t m = __vcmpne4(c, 0u) & __vcmpeq4(old, 0u);      // covered and still unwritten
-                if (m) icol[(int64_t)(z - i) * ps] = old | (val4 & m);
-            }
+            v[i] = c;
+        }
+        uint32_t old[ZS_UNROLL];
+#pragma unroll
+        for (int i = 0; i < ZS_UNROLL; ++i) old[i] = v[i] ? icol[(int64_t)(z - i) * ps] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < ZS_UNROLL; ++i) {
+            const uint32_t m = __vcmpne4(v[i], 0u) & __vcmpeq4(old[i], 0u);      // covered and still unwritten
+            if (m) icol[(int64_t)(z - i) * ps] = old[i] | (val4 & m);
         }
     }
     for (; z >= 0; --z) {
