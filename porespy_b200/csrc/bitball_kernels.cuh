@@ -147,6 +147,44 @@ __device__ __forceinline__ void bb_commit(uint32_t *__restrict__ written, uint8_
     }
 }
 
+// Four consecutive words (wi a multiple of 4: 16-byte aligned in `written`, 128-byte aligned in `idx`): the written
+// words arrive as one load, and the index halves that receive new voxels are fetched two words (up to four 16-byte
+// loads) at a time before any of them is stored -- word by word every load waits behind the previous word's stores
+// (same arrays: the compiler must keep the order), a dozen serial memory round trips at the end of every thread.
+__device__ __forceinline__ void bb_commit4(uint32_t *__restrict__ written, uint8_t *__restrict__ idx, int64_t wi,
+                                           uint32_t A0, uint32_t A1, uint32_t A2, uint32_t A3, uint32_t val)
+{
+    const uint4 wm = *reinterpret_cast<const uint4 *>(written + wi);
+    const uint32_t N[4] = {A0 & ~wm.x, A1 & ~wm.y, A2 & ~wm.z, A3 & ~wm.w};
+    if ((N[0] | N[1] | N[2] | N[3]) == 0u) return;
+    *reinterpret_cast<uint4 *>(written + wi) = make_uint4(wm.x | N[0], wm.y | N[1], wm.z | N[2], wm.w | N[3]);
+    uint4 *ip = reinterpret_cast<uint4 *>(idx + 32 * wi);              // two 16-byte halves per word
+    const uint32_t val4 = val * 0x01010101u;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {                                       // words 2g, 2g + 1
+        if ((N[2 * g] | N[2 * g + 1]) == 0u) continue;
+        uint4 o[4];
+        uint32_t nh[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            nh[t] = (N[2 * g + (t >> 1)] >> (16 * (t & 1))) & 0xFFFFu;
+            if (nh[t]) o[t] = ip[4 * g + t];
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (nh[t] == 0u) continue;
+            uint32_t *ow = reinterpret_cast<uint32_t *>(&o[t]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t nib = (nh[t] >> (4 * q)) & 0xFu;
+                const uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;   // nibble -> byte mask
+                ow[q] |= val4 & bm;        // the bytes under bm are still 0 (written bit was clear)
+            }
+            ip[4 * g + t] = o[t];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ dilation
 // seeds: [nz_src][ny][nw] words (nw = nx / 32); output plane z reads seed plane z + z_off, so a
 // z-slab shard passes its slab with the neighbours' halo planes in front / behind (single GPU:
@@ -352,10 +390,7 @@ lt_bitball4_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ wr
     }
     if (!rowok) return;
     const int64_t wi = ((int64_t)z * ny + y) * NW + 4 * lr;
-    bb_commit(written, idx, wi, A0, val);
-    bb_commit(written, idx, wi + 1, A1, val);
-    bb_commit(written, idx, wi + 2, A2, val);
-    bb_commit(written, idx, wi + 3, A3, val);
+    bb_commit4(written, idx, wi, A0, A1, A2, A3, val);
 }
 
 // ------------------------------------------------- four words x two output rows per lane
@@ -456,14 +491,8 @@ lt_bitball4d_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ w
             }
         }
         const int64_t wi = ((int64_t)z * ny + y0) * NW + 4 * lr;
-        bb_commit(written, idx, wi, A0, val);
-        bb_commit(written, idx, wi + 1, A1, val);
-        bb_commit(written, idx, wi + 2, A2, val);
-        bb_commit(written, idx, wi + 3, A3, val);
-        bb_commit(written, idx, wi + NW, B0, val);
-        bb_commit(written, idx, wi + NW + 1, B1, val);
-        bb_commit(written, idx, wi + NW + 2, B2, val);
-        bb_commit(written, idx, wi + NW + 3, B3, val);
+        bb_commit4(written, idx, wi, A0, A1, A2, A3, val);
+        bb_commit4(written, idx, wi + NW, B0, B1, B2, B3, val);
         return;
     }
     // ---- border row groups: the one-output loop with bounds checks for each of the two rows
@@ -486,10 +515,7 @@ lt_bitball4d_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ w
             }
         }
         const int64_t wi = ((int64_t)z * ny + y) * NW + 4 * lr;
-        bb_commit(written, idx, wi, A0, val);
-        bb_commit(written, idx, wi + 1, A1, val);
-        bb_commit(written, idx, wi + 2, A2, val);
-        bb_commit(written, idx, wi + 3, A3, val);
+        bb_commit4(written, idx, wi, A0, A1, A2, A3, val);
     }
 #undef BB_DILATE4
 }
