@@ -54,7 +54,9 @@ def _slab_plan(shape3_, T):
     nslabs = int(cfg["slabs"])
     if nslabs < 2 or nz // nslabs < 2 * W + 1:          # halo work above the slab's own
         return None
-    cuts = [(nz * i) // nslabs for i in range(nslabs + 1)]
+    # a thin first slab: the host epilogue (the longest leg) starts as early as possible; the rest evenly
+    first = max(2 * W + 1, nz // (4 * nslabs))
+    cuts = [0] + [first + ((nz - first) * i) // (nslabs - 1) for i in range(nslabs)]
     return [(z0, z1, max(0, z0 - W), min(nz, z1 + W)) for z0, z1 in zip(cuts[:-1], cuts[1:])]
 
 
