@@ -271,8 +271,13 @@ class CudaBackend:
 
 
 class UfState:
-    """Buffers of one slab's union-find across the radius loop (owned by the backend)."""
-    pass
+    """Buffers of one slab's union-find across the radius loop (owned by the backend).
+
+    cls / rcls : class map in, reached-class map out (uint8, flat)      parent : nz*ny*nx + 1 node links (int32)
+    inlets, mode : inlet mask (or None) and PSB200_INLETS_*             shape, z0, nzg : slab geometry in the volume
+    flags : two device ints [changed by an inject, anything marked]    rec : record store of psb200_uf_*_records, or None
+    """
+    __slots__ = ("cls", "rcls", "parent", "inlets", "mode", "shape", "z0", "nzg", "flags", "rec")
 
 
 class ShardedVolume:
