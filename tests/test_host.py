@@ -226,3 +226,33 @@ def test_patch_install_logic_without_gpu():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_slab_plan_of_the_pipelined_numpy_result():
+    """filters._slab_plan: the slabs tile [0, nz) in order, every slab carries the largest reach as halo (clipped at
+    the volume), and the plan is declined when halos would outweigh the slabs or the volume is small."""
+    from porespy_b200 import filters as F
+    from porespy_b200 import _host
+    saved = dict(F.SLAB_PIPELINE)
+    try:
+        F.SLAB_PIPELINE.update(enabled=True, min_voxels=1 << 28, slabs=6)
+        T = [1700, 900, 300, 50, 2]                      # thresholds descend: reach of the first one is the halo
+        W = _host.isqrt(T[0] - 1)
+        plan = F._slab_plan((1024, 1024, 1024), T)
+        assert plan is not None and len(plan) == 6
+        assert plan[0][0] == 0 and plan[-1][1] == 1024
+        for (z0, z1, e0, e1), nxt in zip(plan, plan[1:] + [None]):
+            assert z0 < z1 and e0 == max(0, z0 - W) and e1 == min(1024, z1 + W)
+            if nxt is not None:
+                assert nxt[0] == z1
+        assert plan[0][1] - plan[0][0] < plan[1][1] - plan[1][0]            # thin first slab: the epilogue starts early
+        assert F._slab_plan((256, 256, 256), T) is None                    # below min_voxels
+        assert F._slab_plan((1024, 1024, 1024), []) is None
+        assert F._slab_plan((1024, 1024, 1024), list(range(400, 0, -1))) is None      # > 253 thresholds: grouped path
+        F.SLAB_PIPELINE.update(min_voxels=1)
+        assert F._slab_plan((60, 64, 64), [1700, 5]) is None               # 2 W + 1 planes of halo per 10-plane slab
+        F.SLAB_PIPELINE.update(enabled=False)
+        assert F._slab_plan((1024, 1024, 1024), T) is None
+    finally:
+        F.SLAB_PIPELINE.clear()
+        F.SLAB_PIPELINE.update(saved)
