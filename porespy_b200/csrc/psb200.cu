@@ -709,7 +709,7 @@ struct LtWorkspace {
     uint32_t *seedbits, *written;   // bit path: one bit per voxel (seed bits of up to PACKN_MAX consecutive radii)
     size_t seed_words;              // words of one seed-bit volume inside seedbits
     uint32_t *parent;
-    uint32_t *uf_list;    // voxels activated at the current radius (one segment of UF_SEG voxels at a time)
+    uint32_t *uf_list;    // link records sorted into (radius index, direction) slices; job list of the fallback path
     size_t uf_list_cap;
     uint32_t *uf_raw;     // unsorted records, one region of uf_cap entries per chunk; uf_ccount: records per chunk
     uint32_t *uf_ccount;
