@@ -507,7 +507,9 @@ def run_ours(args):
                      f"threads before the upload (psb200_upload_mask_u8)" if packed else "numpy bool volume, uploaded as bytes"),
            "result": f"float64 map of {im_host.size * 8 * world} bytes in host memory; {pdev.HOST_WIDEN_PERMILLE / 10:.0f} % of "
                      f"the volume leaves the device as 1-byte radius indices and is widened by the library's host "
-                     f"threads (psb200_expand_idx_f64_to_host)"}
+                     f"threads (psb200_expand_idx_f64_to_host)"
+                     + ("; the radius loop runs in z-slabs and the epilogue of a finished slab overlaps the next slab's "
+                        "kernels (porespy_b200.filters.SLAB_PIPELINE)" if world == 1 else "")}
     del im_host
 
     if rank != 0:
